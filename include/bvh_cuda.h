@@ -1,0 +1,175 @@
+/* bvh_cuda.h — C ABI of libbvh_cuda.so: the sm_100a CUDA replacement for voidin's `crates/bvh`.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the voidin checkout).
+ * All structs are byte-identical to the Rust `repr(C)` / WGSL ones, so the arrays this library writes can be
+ * pushed unchanged into voidin's wgpu storage buffers (crates/pools/src/mesh/mod.rs:322-330,285).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  "host" entry points take host pointers and do their own H2D/D2H copies;
+ *     the `_dev` twins take device pointers plus a `cudaStream_t` (passed as void*) and leave results on the
+ *     device.  Work of one context is serialised on the stream it is given.
+ *   - Every function returns a status: 0 ok, <0 error.  Nothing unwinds, nothing prints.  The reference has
+ *     no error channel — it panics (blas.rs:84 on N=0, mesh/mod.rs:321 on len%3!=0, OOB on bad indices) or
+ *     never terminates on degenerate input (blas.rs:115,139); those cases map to EINVAL / EDEGENERATE here.
+ *   - There is no CPU fallback: without a CUDA device bvh_cuda_create fails with BVH_CUDA_ECUDA.
+ */
+#ifndef BVH_CUDA_H
+#define BVH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVH_CUDA_OK 0
+#define BVH_CUDA_EINVAL (-1)      /* empty mesh, null pointer, index out of range, capacity too small */
+#define BVH_CUDA_EDEGENERATE (-2) /* a node with >3 triangles has no candidate split with finite cost */
+#define BVH_CUDA_ECUDA (-3)       /* CUDA runtime error; see bvh_cuda_last_error */
+#define BVH_CUDA_ENOMEM (-4)      /* device allocation failed */
+
+#define BVH_CUDA_MAX_DIST 1e30f /* crates/bvh/src/intersection.rs:3, shaders/utils/math.wgsl:4 */
+#define BVH_CUDA_NO_HIT 0xFFFFFFFFu
+
+/* crates/bvh/src/blas.rs:10-17; WGSL mirror shaders/utils/bvh.wgsl:11-16.
+ * Leaf <=> count > 0: left_first = first triangle (permuted order), count in {1,2,3}.
+ * Interior: count == 0, children at left_first and left_first+1 (relative to the mesh's own node array). */
+typedef struct BvhNode {
+    float min[3];
+    uint32_t left_first;
+    float max[3];
+    uint32_t count;
+} BvhNode;
+
+/* crates/bvh/src/tlas.rs:7-14; WGSL mirror shaders/utils/bvh.wgsl:4-9.
+ * Leaf <=> left_right == 0; interior left_right = a + (b << 16) in wrapping u32 (tlas.rs:71). */
+typedef struct TlasNode {
+    float min[3];
+    uint32_t left_right;
+    float max[3];
+    uint32_t instance_idx;
+} TlasNode;
+
+/* crates/components/src/shared.rs:67-75 (glam Mat4 is column-major); WGSL shaders/shared.wgsl:53-59. */
+typedef struct Instance {
+    float transform[16];
+    float inv_transform[16];
+    uint32_t mesh;
+    uint32_t material;
+    uint32_t junk[2];
+} Instance;
+
+/* crates/components/src/shared.rs:29-39; WGSL shaders/shared.wgsl:43-51. */
+typedef struct MeshInfo {
+    float min[3];
+    uint32_t index_count;
+    float max[3];
+    uint32_t base_index;
+    int32_t vertex_offset;
+    uint32_t bvh_index;
+    uint32_t junk[2];
+} MeshInfo;
+
+typedef struct bvh_cuda_ctx bvh_cuda_ctx;     /* one per host thread and device */
+typedef struct bvh_cuda_scene bvh_cuda_scene; /* the six buffers of voidin's trace bind group, on the device */
+
+/* Counters of the most recent BLAS build on a context (all derived on the device). */
+typedef struct BvhCudaBuildStats {
+    uint64_t sum_interior_prims; /* S: sum over interior nodes of their triangle count */
+    uint32_t n_nodes;            /* M = 2 + 2 * interior nodes */
+    uint32_t interior_nodes;
+    uint32_t grid_levels;        /* levels handled by the grid-wide tier */
+    uint32_t block_tasks;        /* nodes handled one block each from the device task queue */
+    uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each */
+    uint32_t kernel_launches;    /* kernels launched by this build */
+} BvhCudaBuildStats;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int bvh_cuda_create(int device, bvh_cuda_ctx** out);
+void bvh_cuda_destroy(bvh_cuda_ctx* ctx);
+/* Message of the last failing call on this context ("" if none).  Valid until the next call on the context. */
+const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
+/* Total kernels launched through this context since creation. */
+uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
+int bvh_cuda_abi_version(void);
+
+/* ---- BLAS: BvhBuilder::new(vertices, indices).build()  (crates/bvh/src/blas.rs:51-103) ----------------- *
+ * Caller: MeshPool::add, crates/pools/src/mesh/mod.rs:320-321.
+ * vertices: 3*n_vertices floats (glam Vec3, 12 B).  indices: 3*n_tris u32, permuted IN PLACE into the builder's
+ * final triangle order (blas.rs:95-100).  nodes_out: capacity nodes_cap >= 2*n_tris entries (blas.rs:52);
+ * *n_nodes_out = 2 + 2*interior (blas.rs:93), node 1 is all-zero (blas.rs:90).
+ * `set_bin_number` (blas.rs:64-67) has no counterpart: the reference never reads the value (blas.rs:136). */
+int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_vertices, uint32_t* indices,
+                        size_t n_tris, BvhNode* nodes_out, size_t nodes_cap, uint32_t* n_nodes_out);
+/* Same, device pointers.  n_nodes_out is a HOST pointer; the call returns after the node count is known
+ * (the build is a sequence of dependent launches with a few small read-backs). */
+int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                            size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
+                            void* stream);
+/* Optional: final triangle_indices of the last build (original triangle id per slot), n_tris entries, device->host. */
+int bvh_cuda_blas_last_order(bvh_cuda_ctx* ctx, uint32_t* order_out, size_t n_tris);
+int bvh_cuda_blas_last_stats(const bvh_cuda_ctx* ctx, BvhCudaBuildStats* out);
+
+/* ---- TLAS: Tlas::build(&mut self, instances, meshes)  (crates/bvh/src/tlas.rs:31-85) -------------------- *
+ * Caller: MeshPool::generate_tlas, crates/pools/src/mesh/mod.rs:279-286 (which guards n_inst == 0).
+ * nodes_out: 2*n_inst+1 entries (tlas.rs:32).  children_out (may be NULL): 2*(2*n_inst+1) u32, the unpacked
+ * child ids of every node — required by the traversal when n_inst > 32767 because left_right packs 16+16 bits. */
+int bvh_cuda_tlas_build(bvh_cuda_ctx* ctx, const Instance* instances, size_t n_inst, const MeshInfo* meshes,
+                        size_t n_mesh, TlasNode* nodes_out, uint32_t* children_out);
+int bvh_cuda_tlas_build_dev(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst,
+                            const MeshInfo* d_meshes, size_t n_mesh, TlasNode* d_nodes_out,
+                            uint32_t* d_children_out, void* stream);
+
+/* ---- scene: the trace bind group (crates/pools/src/mesh/mod.rs:136-238, crates/app/src/app.rs:255-287) -- */
+typedef struct BvhCudaSceneDesc {
+    const TlasNode* tlas_nodes;    size_t n_tlas_nodes;
+    const uint32_t* tlas_children; /* optional, 2*n_tlas_nodes */
+    const Instance* instances;     size_t n_instances;
+    const MeshInfo* meshes;        size_t n_meshes;
+    const BvhNode* bvh_nodes;      size_t n_bvh_nodes;
+    const float* vertices;         size_t n_vertices;  /* pooled, 3 floats each */
+    const uint32_t* indices;       size_t n_indices;   /* pooled, permuted */
+} BvhCudaSceneDesc;
+/* Copies host buffers to the device. */
+int bvh_cuda_scene_upload(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* host_desc, bvh_cuda_scene** out);
+/* Wraps device buffers that stay owned by the caller (no copy). */
+int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* dev_desc, bvh_cuda_scene** out);
+void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene);
+
+/* ---- traversal ----------------------------------------------------------------------------------------- *
+ * Rays: ray_o / ray_d are 3*n_rays floats each.  Ids are an extension of the reference, which returns none:
+ * tri = node.left_first + i in the mesh's permuted order, inst = TlasNode.instance_idx, both captured at the
+ * assignment that lowers t, in the reference's visit order.  Miss: t = 1e30, ids = 0xFFFFFFFF.            */
+
+/* Bvh::traverse_iter (crates/bvh/src/blas.rs:247-295) with the Rust intersection tests
+ * (crates/bvh/src/intersection.rs:47-55,68-92): division slabs, two-sided triangles, EPS 1e-4, far child first.
+ * Caller: src/bin/bvh_cpu.rs:87. */
+int bvh_cuda_trace_blas(bvh_cuda_ctx* ctx, const BvhNode* nodes, size_t n_nodes, const float* vertices,
+                        size_t n_vertices, const uint32_t* indices, size_t n_tris, const float* ray_o,
+                        const float* ray_d, size_t n_rays, float* t_out, uint32_t* tri_out);
+int bvh_cuda_trace_blas_dev(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
+                            const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d,
+                            size_t n_rays, float* d_t_out, uint32_t* d_tri_out, void* stream);
+
+/* traverse_tlas (shaders/utils/bvh.wgsl:89-123) with the WGSL tests (shaders/utils/intersections.wgsl:13-45):
+ * reciprocal slabs, back-face culling, 0 < t < hit, near child first.  tmax: initial res.dist (reference: 1e30). */
+int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o,
+                           const float* ray_d, size_t n_rays, float tmax, float* t_out, uint32_t* tri_out,
+                           uint32_t* inst_out);
+int bvh_cuda_trace_closest_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
+                               const float* d_ray_d, size_t n_rays, float tmax, float* d_t_out,
+                               uint32_t* d_tri_out, uint32_t* d_inst_out, void* stream);
+
+/* Shadow rays: occluded[r] = traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102), computed with
+ * early exit at the first accepted triangle of the same traversal order. */
+int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d,
+                       size_t n_rays, float tmax, uint8_t* occluded_out);
+int bvh_cuda_trace_any_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
+                           const float* d_ray_d, size_t n_rays, float tmax, uint8_t* d_occluded_out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVH_CUDA_H */

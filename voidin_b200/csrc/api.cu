@@ -1,0 +1,359 @@
+// api.cu — context management and the extern "C" entry points of include/bvh_cuda.h.
+// Host-pointer entry points stage through device buffers owned by the call and forward to the `_dev`
+// implementations; nothing here computes on the CPU.
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+int blas_t2_occupancy();
+
+int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what) {
+    if (ctx) ctx->err = what ? what : "";
+    return code;
+}
+
+int ctx_cuda_fail(bvh_cuda_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) {
+        ctx->err = std::string(where ? where : "cuda") + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    }
+    cudaGetLastError();  // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? BVH_CUDA_ENOMEM : BVH_CUDA_ECUDA;
+}
+
+int ctx_reserve(bvh_cuda_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return BVH_CUDA_OK;
+    if (ctx->ws) {
+        cudaFree(ctx->ws);
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+        ctx->d_last_order = nullptr;
+        ctx->last_n = 0;
+    }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&ctx->ws, bytes);
+        if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(workspace)");
+        ctx->ws_bytes = bytes;
+        return BVH_CUDA_OK;
+    }
+    ctx->ws_bytes = want;
+    return BVH_CUDA_OK;
+}
+
+namespace {
+
+// RAII device staging buffer for the host-pointer entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int bvh_cuda_abi_version(void) { return 1; }
+
+int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
+    if (!out) return BVH_CUDA_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return BVH_CUDA_ECUDA;  // no CPU fallback by design
+    }
+    bvh_cuda_ctx* ctx = new (std::nothrow) bvh_cuda_ctx();
+    if (!ctx) return BVH_CUDA_ENOMEM;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return BVH_CUDA_ECUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_pin, 4096) != cudaSuccess) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        cudaGetLastError();
+        return BVH_CUDA_ECUDA;
+    }
+    ctx->t2_blocks_per_sm = blas_t2_occupancy();
+    *out = ctx;
+    return BVH_CUDA_OK;
+}
+
+void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- BLAS ------------------------------------------------------------------------------------------
+int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                            size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_tris, d_nodes_out, nodes_cap, n_nodes_out,
+                             (cudaStream_t)stream);
+}
+
+int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_vertices, uint32_t* indices, size_t n_tris,
+                        BvhNode* nodes_out, size_t nodes_cap, uint32_t* n_nodes_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!vertices || !indices || !nodes_out || n_tris == 0 || n_vertices == 0)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: empty mesh or null pointer");
+    if (nodes_cap < 2 * n_tris) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: nodes_cap must be >= 2*n_tris");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    DevBuf dv, di, dn;
+    CU_CHECK(ctx, dv.alloc(sizeof(float) * 3 * n_vertices));
+    CU_CHECK(ctx, di.alloc(sizeof(uint32_t) * 3 * n_tris));
+    CU_CHECK(ctx, dn.alloc(sizeof(BvhNode) * 2 * n_tris));
+    CU_CHECK(ctx, cudaMemcpyAsync(dv.p, vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(di.p, indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
+    uint32_t m = 0;
+    int rc = blas_build_device(ctx, dv.as<float>(), n_vertices, di.as<uint32_t>(), n_tris, dn.as<BvhNode>(), 2 * n_tris, &m, s);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    CU_CHECK(ctx, cudaMemcpyAsync(nodes_out, dn.p, sizeof(BvhNode) * m, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(indices, di.p, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    if (n_nodes_out) *n_nodes_out = m;
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_blas_last_order(bvh_cuda_ctx* ctx, uint32_t* order_out, size_t n_tris) {
+    if (!ctx || !order_out) return BVH_CUDA_EINVAL;
+    if (!ctx->d_last_order || ctx->last_n != n_tris) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_last_order: no matching build");
+    DeviceGuard g(ctx->device);
+    CU_CHECK(ctx, cudaMemcpy(order_out, ctx->d_last_order, sizeof(uint32_t) * n_tris, cudaMemcpyDeviceToHost));
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_blas_last_stats(const bvh_cuda_ctx* ctx, BvhCudaBuildStats* out) {
+    if (!ctx || !out) return BVH_CUDA_EINVAL;
+    *out = ctx->stats;
+    return BVH_CUDA_OK;
+}
+
+// ---- TLAS ------------------------------------------------------------------------------------------
+int bvh_cuda_tlas_build_dev(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
+                            size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return tlas_build_device(ctx, d_instances, n_inst, d_meshes, n_mesh, d_nodes_out, d_children_out, (cudaStream_t)stream);
+}
+
+int bvh_cuda_tlas_build(bvh_cuda_ctx* ctx, const Instance* instances, size_t n_inst, const MeshInfo* meshes, size_t n_mesh,
+                        TlasNode* nodes_out, uint32_t* children_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!instances || !meshes || !nodes_out || n_inst == 0 || n_mesh == 0)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "tlas_build: no instances / null pointer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    const size_t total = 2 * n_inst + 1;
+    DevBuf di, dm, dn, dc;
+    CU_CHECK(ctx, di.alloc(sizeof(Instance) * n_inst));
+    CU_CHECK(ctx, dm.alloc(sizeof(MeshInfo) * n_mesh));
+    CU_CHECK(ctx, dn.alloc(sizeof(TlasNode) * total));
+    CU_CHECK(ctx, dc.alloc(sizeof(uint32_t) * 2 * total));
+    CU_CHECK(ctx, cudaMemcpyAsync(di.p, instances, sizeof(Instance) * n_inst, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(dm.p, meshes, sizeof(MeshInfo) * n_mesh, cudaMemcpyHostToDevice, s));
+    int rc = tlas_build_device(ctx, di.as<Instance>(), n_inst, dm.as<MeshInfo>(), n_mesh, dn.as<TlasNode>(), dc.as<uint32_t>(), s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(nodes_out, dn.p, sizeof(TlasNode) * total, cudaMemcpyDeviceToHost, s));
+    if (children_out) CU_CHECK(ctx, cudaMemcpyAsync(children_out, dc.p, sizeof(uint32_t) * 2 * total, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return BVH_CUDA_OK;
+}
+
+// ---- scene -----------------------------------------------------------------------------------------
+static int scene_check(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* d) {
+    if (!d || !d->tlas_nodes || !d->instances || !d->meshes || !d->bvh_nodes || !d->vertices || !d->indices ||
+        d->n_tlas_nodes == 0 || d->n_instances == 0 || d->n_meshes == 0)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene: missing buffer");
+    if (!d->tlas_children && d->n_instances > 32767)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene: more than 32767 instances need tlas_children (left_right packs 16+16 bits, tlas.rs:71)");
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_scene_upload(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* h, bvh_cuda_scene** out) {
+    if (!ctx || !out) return BVH_CUDA_EINVAL;
+    *out = nullptr;
+    int rc = scene_check(ctx, h);
+    if (rc) return rc;
+    DeviceGuard g(ctx->device);
+    const size_t sz[7] = {sizeof(TlasNode) * h->n_tlas_nodes,
+                          h->tlas_children ? sizeof(uint32_t) * 2 * h->n_tlas_nodes : 0,
+                          sizeof(Instance) * h->n_instances,
+                          sizeof(MeshInfo) * h->n_meshes,
+                          sizeof(BvhNode) * h->n_bvh_nodes,
+                          sizeof(float) * 3 * h->n_vertices,
+                          sizeof(uint32_t) * h->n_indices};
+    const void* src[7] = {h->tlas_nodes, h->tlas_children, h->instances, h->meshes, h->bvh_nodes, h->vertices, h->indices};
+    size_t off[7], total = 0;
+    for (int i = 0; i < 7; ++i) { off[i] = total; total += (sz[i] + 255) & ~(size_t)255; }
+    bvh_cuda_scene* sc = new (std::nothrow) bvh_cuda_scene();
+    if (!sc) return BVH_CUDA_ENOMEM;
+    cudaError_t e = cudaMalloc(&sc->block, total ? total : 256);
+    if (e != cudaSuccess) { delete sc; return ctx_cuda_fail(ctx, e, "cudaMalloc(scene)"); }
+    sc->owned = true;
+    char* b = (char*)sc->block;
+    for (int i = 0; i < 7; ++i)
+        if (sz[i]) {
+            e = cudaMemcpyAsync(b + off[i], src[i], sz[i], cudaMemcpyHostToDevice, ctx->own_stream);
+            if (e != cudaSuccess) { cudaFree(sc->block); delete sc; return ctx_cuda_fail(ctx, e, "cudaMemcpy(scene)"); }
+        }
+    e = cudaStreamSynchronize(ctx->own_stream);
+    if (e != cudaSuccess) { cudaFree(sc->block); delete sc; return ctx_cuda_fail(ctx, e, "cudaMemcpy(scene)"); }
+    sc->d = *h;
+    sc->d.tlas_nodes = (const TlasNode*)(b + off[0]);
+    sc->d.tlas_children = h->tlas_children ? (const uint32_t*)(b + off[1]) : nullptr;
+    sc->d.instances = (const Instance*)(b + off[2]);
+    sc->d.meshes = (const MeshInfo*)(b + off[3]);
+    sc->d.bvh_nodes = (const BvhNode*)(b + off[4]);
+    sc->d.vertices = (const float*)(b + off[5]);
+    sc->d.indices = (const uint32_t*)(b + off[6]);
+    *out = sc;
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* d, bvh_cuda_scene** out) {
+    if (!ctx || !out) return BVH_CUDA_EINVAL;
+    *out = nullptr;
+    int rc = scene_check(ctx, d);
+    if (rc) return rc;
+    bvh_cuda_scene* sc = new (std::nothrow) bvh_cuda_scene();
+    if (!sc) return BVH_CUDA_ENOMEM;
+    sc->d = *d;
+    sc->owned = false;
+    *out = sc;
+    return BVH_CUDA_OK;
+}
+
+void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene) {
+    if (!scene) return;
+    if (scene->owned && scene->block) {
+        if (ctx) { DeviceGuard g(ctx->device); cudaFree(scene->block); }
+        else cudaFree(scene->block);
+    }
+    delete scene;
+}
+
+// ---- traversal -------------------------------------------------------------------------------------
+int bvh_cuda_trace_blas_dev(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
+                            const float* d_ray_o, const float* d_ray_d, size_t n_rays, float* d_t_out, uint32_t* d_tri_out,
+                            void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return trace_blas_device(ctx, d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, d_t_out, d_tri_out, (cudaStream_t)stream);
+}
+
+int bvh_cuda_trace_blas(bvh_cuda_ctx* ctx, const BvhNode* nodes, size_t n_nodes, const float* vertices, size_t n_vertices,
+                        const uint32_t* indices, size_t n_tris, const float* ray_o, const float* ray_d, size_t n_rays,
+                        float* t_out, uint32_t* tri_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!nodes || !vertices || !indices || !ray_o || !ray_d || !t_out || !tri_out || n_nodes == 0)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    DevBuf dn, dv, di, dro, drd, dt, dtri;
+    CU_CHECK(ctx, dn.alloc(sizeof(BvhNode) * n_nodes));
+    CU_CHECK(ctx, dv.alloc(sizeof(float) * 3 * n_vertices));
+    CU_CHECK(ctx, di.alloc(sizeof(uint32_t) * 3 * n_tris));
+    CU_CHECK(ctx, dro.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, drd.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, dt.alloc(sizeof(float) * n_rays));
+    CU_CHECK(ctx, dtri.alloc(sizeof(uint32_t) * n_rays));
+    CU_CHECK(ctx, cudaMemcpyAsync(dn.p, nodes, sizeof(BvhNode) * n_nodes, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(dv.p, vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(di.p, indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(dro.p, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(drd.p, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    int rc = trace_blas_device(ctx, dn.as<BvhNode>(), dv.as<float>(), di.as<uint32_t>(), dro.as<float>(), drd.as<float>(), n_rays,
+                               dt.as<float>(), dtri.as<uint32_t>(), s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(t_out, dt.p, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(tri_out, dtri.p, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_trace_closest_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o, const float* d_ray_d,
+                               size_t n_rays, float tmax, float* d_t_out, uint32_t* d_tri_out, uint32_t* d_inst_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return trace_scene_device(ctx, scene, d_ray_o, d_ray_d, n_rays, tmax, 0, d_t_out, d_tri_out, d_inst_out, nullptr, (cudaStream_t)stream);
+}
+
+int bvh_cuda_trace_any_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o, const float* d_ray_d,
+                           size_t n_rays, float tmax, uint8_t* d_occluded_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return trace_scene_device(ctx, scene, d_ray_o, d_ray_d, n_rays, tmax, 1, nullptr, nullptr, nullptr, d_occluded_out, (cudaStream_t)stream);
+}
+
+int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
+                           float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!scene || !ray_o || !ray_d || !t_out || !tri_out || !inst_out) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_closest: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    DevBuf dro, drd, dt, dtri, dinst;
+    CU_CHECK(ctx, dro.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, drd.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, dt.alloc(sizeof(float) * n_rays));
+    CU_CHECK(ctx, dtri.alloc(sizeof(uint32_t) * n_rays));
+    CU_CHECK(ctx, dinst.alloc(sizeof(uint32_t) * n_rays));
+    CU_CHECK(ctx, cudaMemcpyAsync(dro.p, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(drd.p, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    int rc = trace_scene_device(ctx, scene, dro.as<float>(), drd.as<float>(), n_rays, tmax, 0, dt.as<float>(), dtri.as<uint32_t>(),
+                                dinst.as<uint32_t>(), nullptr, s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(t_out, dt.p, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(tri_out, dtri.p, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(inst_out, dinst.p, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return BVH_CUDA_OK;
+}
+
+int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
+                       float tmax, uint8_t* occluded_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!scene || !ray_o || !ray_d || !occluded_out) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_any: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    DevBuf dro, drd, docc;
+    CU_CHECK(ctx, dro.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, drd.alloc(sizeof(float) * 3 * n_rays));
+    CU_CHECK(ctx, docc.alloc(n_rays));
+    CU_CHECK(ctx, cudaMemcpyAsync(dro.p, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(drd.p, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    int rc = trace_scene_device(ctx, scene, dro.as<float>(), drd.as<float>(), n_rays, tmax, 1, nullptr, nullptr, nullptr,
+                                docc.as<uint8_t>(), s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(occluded_out, docc.p, n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return BVH_CUDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1400 @@
+// blas_build.cu — exact, order-faithful GPU restatement of BvhBuilder::build (crates/bvh/src/blas.rs:69-204).
+//
+// The reference is NOT a binned builder: for each of 21 candidate planes it physically re-partitions the
+// node's primitive range with an unstable two-cursor swap (partition_shuffle, blas.rs:168-182) and costs
+// the two halves with exact vertex bounds; the final order, the pivots and therefore the whole topology
+// depend on the running array order.  To be bit-exact every node replays all 22 shuffles, each as a
+// closed-form scan + scatter (see DESIGN.md "shuffle in scan form"), and evaluates the candidates from
+// 3x8 exact bins plus the <=21 "unexamined" primitives that the shuffles single out.
+//
+// Three tiers, by node size:
+//   T1  n > 2048   grid-wide, level-synchronous phases over 2048-slot tiles (global memory ping-pong)
+//   T2  33..2048   one block per node from a device task queue (everything in shared memory)
+//   T3  <= 32      one warp per whole sub-tree (registers + 2 KB shared memory), explicit DFS stack
+// Every node writes one 48-byte record at a collision-free slot (leaf: 2*start, interior: 2*split+1);
+// DFS pre-order pair numbering (blas.rs:110-112) is recovered afterwards from
+//   rank(X) = #interior nodes with start < X.start  +  #ancestors of X sharing X.start
+// with one prefix sum over N counters, and a final kernel emits the 32-byte BvhNodes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int T3_MAX = 32;
+constexpr int T2_CAP = 2048;
+constexpr int T2_THREADS = 256;
+constexpr int T1_TILE = 2048;
+constexpr int T1_THREADS = 256;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
+
+#define TF_RIGHT 1u
+#define TF_ROOT 2u
+
+struct Task {  // 32 B
+    uint32_t start, n, leftrun, pstart, pleftrun, flags, ready, pad;
+};
+
+struct LevelNode {  // 32 B
+    uint32_t start, n, leftrun, pstart, pleftrun, flags, tile_base, pad;
+};
+
+struct NodeScratch {
+    uint32_t bnd[12];  // ordered-uint: vlo[3], vhi[3], cmin[3], cmax[3]
+    uint32_t nL, f, best, pad;
+    uint32_t piv[21], uid[21];
+    uint32_t bins[3][8][6];
+};
+
+struct BuildState {
+    uint32_t err;
+    uint32_t q_head, q_tail, q_pending;
+    uint32_t t3_count;
+    uint32_t lv_count[2];
+    uint32_t lv_tiles[2];
+    uint32_t interior_total;
+    unsigned long long sum_interior;
+    uint32_t t2_done;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+__device__ __forceinline__ void emit_rec(uint4* recs, uint32_t slot, const float* lo, const float* hi,
+                                         uint32_t start, uint32_t count, uint32_t leftrun, uint32_t pstart,
+                                         uint32_t pleftrun, uint32_t flags) {
+    uint4* r = recs + 3 * (size_t)slot;
+    r[0] = make_uint4(__float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]), start);
+    r[1] = make_uint4(__float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), count);
+    r[2] = make_uint4(leftrun, pstart, pleftrun, flags);
+}
+
+// 3-bit plane counts of one centroid: k_a = #{b in 1..7 : !(c_a < pos_ab)}, pos_ab = lerp(cmin,cmax,b/8)[a]
+// (blas.rs:145-146,173).  Planes are monotone in b, so "c_a < pos_ab" <=> k_a < b.
+__device__ __forceinline__ uint32_t plane_counts(float cx, float cy, float cz, const float* cmin,
+                                                 const float* cmax) {
+    uint32_t kb = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float c = (a == 0) ? cx : ((a == 1) ? cy : cz);
+        uint32_t k = 0;
+#pragma unroll
+        for (int b = 1; b < 8; ++b) {
+            const float pos = lerp1(cmin[a], cmax[a], (float)b * 0.125f);
+            k += (c < pos) ? 0u : 1u;
+        }
+        kb |= k << (3 * a);
+    }
+    return kb;
+}
+
+// SAH cost of one candidate (blas.rs:155): area(bb1) * n1 as f32 + area(bb2) * n2 as f32
+__device__ __forceinline__ float sah_cost(const float* L, const float* R, uint32_t n1, uint32_t n2) {
+    const float a1 = aabb_area(L[0], L[1], L[2], L[3], L[4], L[5]);
+    const float a2 = aabb_area(R[0], R[1], R[2], R[3], R[4], R[5]);
+    return __fadd_rn(__fmul_rn(a1, __uint2float_rn(n1)), __fmul_rn(a2, __uint2float_rn(n2)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 setup: centroid ((v0+v1)+v2)/3 (blas.rs:70-81), per-triangle AABB folded from +-1e30 (blas.rs:185-186),
+// identity triangle_indices (blas.rs:83), index validation.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint32_t nV,
+                                               const uint32_t* __restrict__ I, uint32_t N, float4* cent,
+                                               float4* box, uint32_t* ids, BuildState* st) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t i0 = I[3 * (size_t)i], i1 = I[3 * (size_t)i + 1], i2 = I[3 * (size_t)i + 2];
+    if (i0 >= nV || i1 >= nV || i2 >= nV) {
+        atomicOr(&st->err, DERR_BAD_INDEX);
+        i0 = i1 = i2 = 0;
+    }
+    const float* a = V + 3 * (size_t)i0;
+    const float* b = V + 3 * (size_t)i1;
+    const float* c = V + 3 * (size_t)i2;
+    float lo[3], hi[3], ce[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = a[k], y = b[k], z = c[k];
+        ce[k] = __fdiv_rn(__fadd_rn(__fadd_rn(x, y), z), 3.0f);
+        lo[k] = fminf(fminf(fminf(1e30f, x), y), z);
+        hi[k] = fmaxf(fmaxf(fmaxf(-1e30f, x), y), z);
+    }
+    cent[i] = make_float4(ce[0], ce[1], ce[2], 0.0f);
+    box[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    box[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    ids[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// T3: one warp builds a whole sub-tree of <= 32 primitives.  Lane j owns slot j of the range.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint32_t* ids,
+                                            const float4* __restrict__ cent, const float4* __restrict__ box,
+                                            uint4* recs, uint32_t* A, BuildState* st) {
+    __shared__ float s_box[8][6][32];
+    __shared__ float s_cent[8][3][32];
+    __shared__ uint32_t s_gid[8][32];
+    __shared__ uint8_t s_tab[8][32];
+    __shared__ uint16_t s_pay[8][32];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t n_tasks = st->t3_count;
+
+    for (uint32_t ti = blockIdx.x * 8 + w; ti < n_tasks; ti += gridDim.x * 8) {
+        const Task t = tasks[ti];
+        __syncwarp();
+        if (lane < t.n) {
+            const uint32_t g = __ldcg(&ids[t.start + lane]);
+            const float4 c = cent[g];
+            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+            s_box[w][0][lane] = b0.x; s_box[w][1][lane] = b0.y; s_box[w][2][lane] = b0.z;
+            s_box[w][3][lane] = b1.x; s_box[w][4][lane] = b1.y; s_box[w][5][lane] = b1.z;
+            s_cent[w][0][lane] = c.x; s_cent[w][1][lane] = c.y; s_cent[w][2][lane] = c.z;
+            s_gid[w][lane] = g;
+        }
+        __syncwarp();
+        uint32_t pay = lane;  // bits 0-4: local primitive, 5-13: plane counts of the current node
+        uint32_t s = 0, n = t.n, leftrun = t.leftrun, pstart = t.pstart, pleftrun = t.pleftrun, fl = t.flags;
+        uint32_t stk_a = 0, stk_b = 0, stk_c = 0;  // lane i holds stack entry i
+        int sp = 0;
+
+        for (;;) {
+            const bool active = lane >= s && lane < s + n;
+            const uint32_t e = pay & 31u;
+            const uint32_t abs_start = t.start + s;
+            // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
+            float lo[3], hi[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t mn = active ? f2o(s_box[w][c][e]) : ENC_POS_INIT;
+                uint32_t mx = active ? f2o(s_box[w][3 + c][e]) : ENC_NEG_INIT;
+                mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
+                mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
+                lo[c] = o2f(mn);
+                hi[c] = o2f(mx);
+            }
+            bool descend = false;
+            if (n <= 3) {  // leaf (blas.rs:106-109)
+                if (lane == 0) emit_rec(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
+            } else {
+                // centroid bounds (blas.rs:142)
+                float cmin[3], cmax[3], cc[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    cc[c] = active ? s_cent[w][c][e] : 0.0f;
+                    uint32_t mn = active ? f2o(cc[c]) : ENC_POS_INIT;
+                    uint32_t mx = active ? f2o(cc[c]) : ENC_NEG_INIT;
+                    mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
+                    mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
+                    cmin[c] = o2f(mn);
+                    cmax[c] = o2f(mx);
+                }
+                pay = e | (plane_counts(cc[0], cc[1], cc[2], cmin, cmax) << 5);
+
+                const uint32_t j = lane - s;
+                const uint32_t nmask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+                // closed form of partition_shuffle (blas.rs:168-182) on the current order
+                auto do_shuffle = [&](uint32_t a, uint32_t b) -> uint32_t {
+                    const bool L = active && (((pay >> (5 + 3 * a)) & 7u) < b);
+                    const uint32_t Lm = __ballot_sync(FULL_MASK, L) >> s;
+                    const uint32_t Rm = ~Lm & nmask;
+                    const uint32_t below = active ? ((1u << j) - 1u) : 0u;
+                    const uint32_t RF = __popc(Rm & below), LF = j - RF;
+                    const uint32_t nL = __popc(Lm);
+                    const uint32_t LBB = (j + 2 < 32) ? __popc(Lm >> (j + 2)) : 0u;
+                    const bool pred = active && (j + 2 <= n) && (LBB >= RF);
+                    const uint32_t f = __popc(__ballot_sync(FULL_MASK, pred));
+                    const uint32_t pivot = nL - ((Lm >> f) & 1u);
+                    const uint32_t LB = nL - LF - (L ? 1u : 0u);
+                    if (active) {
+                        if (L) s_tab[w][n - 1 - LB] = (uint8_t)j;
+                        else s_tab[w][RF] = (uint8_t)j;
+                    }
+                    __syncwarp();
+                    if (active) {
+                        uint32_t dest;
+                        if (j < f) dest = L ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[w][n - RF] - 1u);
+                        else if (j == f) dest = pivot;
+                        else dest = L ? (uint32_t)s_tab[w][LB] : j - 1;
+                        s_pay[w][dest] = (uint16_t)pay;
+                    }
+                    __syncwarp();
+                    if (active) pay = s_pay[w][j];
+                    return pivot;
+                };
+
+                uint32_t my_u = 0xFFu, my_piv = 0;
+                for (uint32_t c = 0; c < 21; ++c) {
+                    const uint32_t pivot = do_shuffle(c / 7, c % 7 + 1);
+                    const uint32_t up = __shfl_sync(FULL_MASK, pay, s + pivot);
+                    if (lane == c) { my_u = up & 31u; my_piv = pivot; }
+                }
+                // candidate `lane` (< 21): exact boxes of {L}\{u} and {R}+{u} (blas.rs:149-155)
+                const uint32_t ca = (lane < 21) ? lane / 7 : 0, cb = lane % 7 + 1;
+                float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                for (uint32_t tt = 0; tt < n; ++tt) {
+                    const uint32_t p = __shfl_sync(FULL_MASK, pay, s + tt);
+                    const uint32_t et = p & 31u;
+                    const bool left = (((p >> (5 + 3 * ca)) & 7u) < cb) && (et != my_u);
+                    const float x0 = s_box[w][0][et], x1 = s_box[w][1][et], x2 = s_box[w][2][et];
+                    const float x3 = s_box[w][3][et], x4 = s_box[w][4][et], x5 = s_box[w][5][et];
+                    if (left) {
+                        Lb[0] = fminf(Lb[0], x0); Lb[1] = fminf(Lb[1], x1); Lb[2] = fminf(Lb[2], x2);
+                        Lb[3] = fmaxf(Lb[3], x3); Lb[4] = fmaxf(Lb[4], x4); Lb[5] = fmaxf(Lb[5], x5);
+                    } else {
+                        Rb[0] = fminf(Rb[0], x0); Rb[1] = fminf(Rb[1], x1); Rb[2] = fminf(Rb[2], x2);
+                        Rb[3] = fmaxf(Rb[3], x3); Rb[4] = fmaxf(Rb[4], x4); Rb[5] = fmaxf(Rb[5], x5);
+                    }
+                }
+                const float cost = sah_cost(Lb, Rb, my_piv, n - my_piv);
+                // strict <, first candidate wins, NaN/inf never win (blas.rs:140,156)
+                const uint32_t key = (lane < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
+                const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
+                if (mk == 0xFFFFFFFFu) {
+                    if (lane == 0) atomicOr(&st->err, DERR_DEGENERATE);
+                } else {
+                    const uint32_t win = __ffs(__ballot_sync(FULL_MASK, key == mk)) - 1;
+                    const uint32_t p = __shfl_sync(FULL_MASK, my_piv, win);  // recorded pivot (blas.rs:159,165)
+                    do_shuffle(win / 7, win % 7 + 1);                       // blas.rs:164
+                    if (lane == 0) {
+                        emit_rec(recs, 2 * (abs_start + p) + 1, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
+                        if (p <= 3) A[abs_start] = leftrun + 1;
+                    }
+                    if ((int)lane == sp) {
+                        stk_a = (s + p) | ((n - p) << 8);
+                        stk_b = abs_start;
+                        stk_c = leftrun;
+                    }
+                    sp++;
+                    pstart = abs_start; pleftrun = leftrun; leftrun = leftrun + 1; n = p; fl = 0;
+                    descend = true;
+                }
+            }
+            if (descend) continue;
+            if (sp == 0) break;
+            sp--;
+            const uint32_t a = __shfl_sync(FULL_MASK, stk_a, sp);
+            pstart = __shfl_sync(FULL_MASK, stk_b, sp);
+            pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
+            s = a & 0xFFu; n = a >> 8; leftrun = 0; fl = TF_RIGHT;
+        }
+        if (lane < t.n) ids[t.start + lane] = s_gid[w][pay & 31u];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T2: one block per node (33..CAP primitives), tasks from a device queue; children go back to the
+// queue (> 32) or to the T3 list.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_child(Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, BuildState* st,
+                                           uint32_t epoch, uint32_t start, uint32_t n, uint32_t leftrun,
+                                           uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
+    if (n > T3_MAX) {
+        atomicAdd(&st->q_pending, 1u);
+        const uint32_t idx = atomicAdd(&st->q_tail, 1u);
+        if (idx >= q_cap) {
+            atomicOr(&st->err, DERR_QUEUE);
+            atomicSub(&st->q_pending, 1u);
+            return;
+        }
+        Task* d = q + idx;
+        d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
+        d->flags = flags; d->pad = 0;
+        __threadfence();
+        *(volatile uint32_t*)&d->ready = epoch;
+    } else {
+        const uint32_t idx = atomicAdd(&st->t3_count, 1u);
+        if (idx >= t3_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
+        Task* d = t3 + idx;
+        d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
+        d->flags = flags; d->ready = epoch; d->pad = 0;
+    }
+}
+
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, uint32_t* ids,
+                                                const float4* __restrict__ cent,
+                                                const float4* __restrict__ box, uint4* recs, uint32_t* A,
+                                                BuildState* st, uint32_t epoch) {
+    constexpr int NW = THREADS / 32;
+    constexpr int EPT = CAP / THREADS;
+    constexpr int CHUNK = 32 * EPT;
+    __shared__ uint32_t s_pay[2][CAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
+    __shared__ uint32_t s_gid[CAP];
+    __shared__ uint16_t s_tab[CAP];
+    __shared__ uint16_t s_k[CAP];
+    __shared__ uint32_t s_wtot[NW];
+    __shared__ uint32_t s_red[NW][12];
+    __shared__ uint32_t s_node[12];
+    __shared__ uint32_t s_bins[3][8][6];
+    __shared__ uint32_t s_f;
+    __shared__ uint32_t s_u[21], s_piv[21], s_uk[21];
+    __shared__ float s_ubox[21][6];
+    __shared__ Task s_task;
+    __shared__ int s_have;
+    __shared__ uint32_t s_best;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        // ---- pop ----
+        if (tid == 0) {
+            int have = 0;
+            uint32_t idx = 0;
+            for (uint32_t spins = 0;;) {
+                const uint32_t h = ld_vol(&st->q_head), tl = ld_vol(&st->q_tail);
+                if (h < tl && h < q_cap) {
+                    if (atomicCAS(&st->q_head, h, h + 1) == h) { idx = h; have = 1; break; }
+                    continue;
+                }
+                if (ld_vol(&st->q_pending) == 0) break;
+                __nanosleep(100);
+                if (++spins > SPIN_LIMIT) { atomicOr(&st->err, DERR_QUEUE); break; }
+            }
+            if (have) {
+                uint32_t spins = 0;
+                while (ld_vol(&q[idx].ready) != epoch) {
+                    __nanosleep(50);
+                    if (++spins > SPIN_LIMIT) { atomicOr(&st->err, DERR_QUEUE); have = 0; break; }
+                }
+                __threadfence();
+                if (have) {
+                    const volatile Task* vq = q + idx;
+                    s_task.start = vq->start; s_task.n = vq->n; s_task.leftrun = vq->leftrun;
+                    s_task.pstart = vq->pstart; s_task.pleftrun = vq->pleftrun; s_task.flags = vq->flags;
+                }
+            }
+            s_have = have;
+            s_f = 0;
+        }
+        __syncthreads();
+        if (!s_have) break;
+        const Task t = s_task;
+        const uint32_t n = t.n, start = t.start;
+
+        // ---- 1. load, own vertex box, centroid bounds ----
+        float ccx[EPT], ccy[EPT], ccz[EPT];
+        {
+            float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                ccx[i] = ccy[i] = ccz[i] = 0.0f;
+                if (j < n) {
+                    const uint32_t g = __ldcg(&ids[start + j]);
+                    s_gid[j] = g;
+                    const float4 c = cent[g];
+                    const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                    ccx[i] = c.x; ccy[i] = c.y; ccz[i] = c.z;
+                    acc[0] = fminf(acc[0], b0.x); acc[1] = fminf(acc[1], b0.y); acc[2] = fminf(acc[2], b0.z);
+                    acc[3] = fmaxf(acc[3], b1.x); acc[4] = fmaxf(acc[4], b1.y); acc[5] = fmaxf(acc[5], b1.z);
+                    acc[6] = fminf(acc[6], c.x); acc[7] = fminf(acc[7], c.y); acc[8] = fminf(acc[8], c.z);
+                    acc[9] = fmaxf(acc[9], c.x); acc[10] = fmaxf(acc[10], c.y); acc[11] = fmaxf(acc[11], c.z);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const bool is_min = (k < 3) || (k >= 6 && k < 9);
+                const uint32_t v = f2o(acc[k]);
+                const uint32_t r = is_min ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                if (lane == 0) s_red[warp][k] = r;
+            }
+        }
+        __syncthreads();
+        if (tid < 12) {
+            const bool is_min = (tid < 3) || (tid >= 6 && tid < 9);
+            uint32_t r = s_red[0][tid];
+            for (int w2 = 1; w2 < NW; ++w2) r = is_min ? min(r, s_red[w2][tid]) : max(r, s_red[w2][tid]);
+            s_node[tid] = r;
+        }
+        for (uint32_t k = tid; k < 144; k += THREADS) (&s_bins[0][0][0])[k] = ((k % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+        __syncthreads();
+
+        // ---- 2. plane counts ----
+        float cmin[3], cmax[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { cmin[c] = o2f(s_node[6 + c]); cmax[c] = o2f(s_node[9 + c]); }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = warp * CHUNK + i * 32 + lane;
+            if (j < n) {
+                const uint32_t kb = plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax);
+                s_k[j] = (uint16_t)kb;
+                s_pay[0][j] = j | (kb << 16);
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. shuffles ----
+        auto shuffle = [&](int cur, uint32_t a, uint32_t b, int cidx) {
+            const uint32_t sh = 16 + 3 * a;
+            uint32_t bal[EPT], LFv[EPT];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                const bool L = (j < n) && (((s_pay[cur][j] >> sh) & 7u) < b);
+                bal[i] = __ballot_sync(FULL_MASK, L);
+                cnt += __popc(bal[i]);
+            }
+            if (lane == 0) s_wtot[warp] = cnt;
+            __syncthreads();  // S1
+            uint32_t wpre = 0, nL = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const uint32_t v = s_wtot[w2];
+                nL += v;
+                if (w2 < (int)warp) wpre += v;
+            }
+            uint32_t running = wpre, predc = 0;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                const uint32_t LF = running + __popc(bal[i] & lt_mask);
+                LFv[i] = LF;
+                bool pred = false;
+                if (j < n) {
+                    const uint32_t RF = j - LF;
+                    uint32_t Lnext;
+                    if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
+                    else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
+                    else Lnext = (j + 1 < n) ? ((((s_pay[cur][j + 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
+                    const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
+                    pred = (j + 2 <= n) && (LBB >= RF);
+                    if (Lbit) s_tab[n - 1 - (nL - LF - 1)] = (uint16_t)j;
+                    else s_tab[RF] = (uint16_t)j;
+                }
+                predc += __popc(__ballot_sync(FULL_MASK, pred));
+                running += __popc(bal[i]);
+            }
+            if (lane == 0 && predc) atomicAdd(&s_f, predc);
+            __syncthreads();  // S2
+            const uint32_t f = s_f;
+            const uint32_t Lf = (((s_pay[cur][f] >> sh) & 7u) < b) ? 1u : 0u;
+            const uint32_t pivot = nL - Lf;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                if (j < n) {
+                    uint32_t pay = s_pay[cur][j];
+                    const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                    const uint32_t LF = LFv[i], RF = j - LF;
+                    uint32_t dest;
+                    if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[n - RF] - 1u);
+                    else if (j == f) {
+                        dest = pivot;
+                        pay |= 0x80000000u;
+                        if (cidx >= 0) { s_u[cidx] = pay & 0xFFFFu; s_piv[cidx] = pivot; }
+                    } else dest = Lbit ? (uint32_t)s_tab[nL - LF - 1] : j - 1;
+                    s_pay[cur ^ 1][dest] = pay;
+                }
+            }
+            __syncthreads();  // S3
+            if (tid == 0) s_f = 0;
+        };
+
+        int cur = 0;
+        for (uint32_t c = 0; c < 21; ++c) { shuffle(cur, c / 7, c % 7 + 1, (int)c); cur ^= 1; }
+
+        // ---- 4. exact bins over the non-special primitives ----
+        {
+            float lo[EPT][3], hi[EPT][3];
+            uint32_t kk[EPT];
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                kk[i] = 0xFFFFFFFFu;
+                lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
+                hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
+                if (j < n) {
+                    const uint32_t pay = s_pay[cur][j];
+                    if (!(pay & 0x80000000u)) {
+                        const uint32_t g = s_gid[pay & 0xFFFFu];
+                        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                        lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
+                        hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
+                        kk[i] = (pay >> 16) & 0x1FFu;
+                    }
+                }
+            }
+            for (uint32_t a = 0; a < 3; ++a) {
+                for (uint32_t k = 0; k < 8; ++k) {
+                    float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < EPT; ++i) {
+                        const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
+                        if (in) {
+                            any = true;
+                            m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
+                            m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                        }
+                    }
+                    if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const uint32_t v = f2o(m[c]);
+                        const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                        if (lane == 0) {
+                            if (c < 3) atomicMin(&s_bins[a][k][c], r);
+                            else atomicMax(&s_bins[a][k][c], r);
+                        }
+                    }
+                }
+            }
+        }
+        if (tid < 21) {
+            const uint32_t e = s_u[tid];
+            const uint32_t g = s_gid[e];
+            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+            s_ubox[tid][0] = b0.x; s_ubox[tid][1] = b0.y; s_ubox[tid][2] = b0.z;
+            s_ubox[tid][3] = b1.x; s_ubox[tid][4] = b1.y; s_ubox[tid][5] = b1.z;
+            s_uk[tid] = s_k[e];
+        }
+        __syncthreads();
+
+        // ---- 5. candidate costs and selection (warp 0) ----
+        if (warp == 0) {
+            const uint32_t c = lane;
+            const uint32_t a = (c < 21) ? c / 7 : 0, b = c % 7 + 1;
+            float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+            float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+            for (uint32_t k = 0; k < 8; ++k) {
+                float* side = (k < b) ? Lb : Rb;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    side[x] = fminf(side[x], o2f(s_bins[a][k][x]));
+                    side[3 + x] = fmaxf(side[3 + x], o2f(s_bins[a][k][3 + x]));
+                }
+            }
+            const uint32_t myu = s_u[(c < 21) ? c : 0];
+            for (uint32_t s2 = 0; s2 < 21; ++s2) {
+                const bool left = (s_u[s2] != myu) && (((s_uk[s2] >> (3 * a)) & 7u) < b);
+                float* side = left ? Lb : Rb;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    side[x] = fminf(side[x], s_ubox[s2][x]);
+                    side[3 + x] = fmaxf(side[3 + x], s_ubox[s2][3 + x]);
+                }
+            }
+            const uint32_t n1 = s_piv[(c < 21) ? c : 0];
+            const float cost = sah_cost(Lb, Rb, n1, n - n1);
+            const uint32_t key = (c < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
+            const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
+            const uint32_t win = (mk == 0xFFFFFFFFu) ? 0xFFFFFFFFu : (uint32_t)(__ffs(__ballot_sync(FULL_MASK, key == mk)) - 1);
+            if (lane == 0) s_best = win;
+        }
+        __syncthreads();
+        const uint32_t best = s_best;
+        if (best == 0xFFFFFFFFu) {
+            if (tid == 0) {
+                atomicOr(&st->err, DERR_DEGENERATE);
+                atomicSub(&st->q_pending, 1u);
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- 6. final shuffle (blas.rs:164), write the order back ----
+        shuffle(cur, best / 7, best % 7 + 1, -1);
+        cur ^= 1;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = warp * CHUNK + i * 32 + lane;
+            if (j < n) ids[start + j] = s_gid[s_pay[cur][j] & 0xFFFFu];
+        }
+        __threadfence();
+        __syncthreads();
+        // ---- 7. record + children ----
+        if (tid == 0) {
+            const uint32_t p = s_piv[best];
+            float lo[3], hi[3];
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = o2f(min(s_node[c], ENC_POS_INIT));
+                hi[c] = o2f(max(s_node[3 + c], ENC_NEG_INIT));
+            }
+            emit_rec(recs, 2 * (start + p) + 1, lo, hi, start, n, t.leftrun, t.pstart, t.pleftrun, t.flags);
+            if (p <= 3) A[start] = t.leftrun + 1;
+            push_child(q, q_cap, t3, t3_cap, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, 0);
+            push_child(q, q_cap, t3, t3_cap, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT);
+            atomicAdd(&st->t2_done, 1u);
+            __threadfence();
+            atomicSub(&st->q_pending, 1u);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T1: grid-wide phases over tiles of nodes with more than T2_CAP primitives.
+// ------------------------------------------------------------------------------------------------
+struct T1Args {
+    const LevelNode* nodes;
+    NodeScratch* sc;
+    uint32_t n_nodes, n_tiles;
+    uint32_t* ids[2];
+    uint16_t* flags[2];
+    uint32_t* table;
+    uint32_t* tileL;
+    uint32_t* tileLF;
+    const float4* cent;
+    const float4* box;
+    BuildState* st;
+};
+
+__device__ __forceinline__ uint32_t find_node(const LevelNode* nodes, uint32_t n_nodes, uint32_t tile) {
+    uint32_t lo = 0, hi = n_nodes;  // last node with tile_base <= tile
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (nodes[mid].tile_base <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void cand_of(const NodeScratch* sc, uint32_t node, int cand, uint32_t& a, uint32_t& b) {
+    const uint32_t c = (cand >= 0) ? (uint32_t)cand : sc[node].best;
+    a = c / 7; b = c % 7 + 1;
+}
+
+__global__ void __launch_bounds__(256) k_t1_init(T1Args g) {
+    for (uint32_t node = blockIdx.x; node < g.n_nodes; node += gridDim.x) {
+        NodeScratch* s = g.sc + node;
+        const uint32_t tid = threadIdx.x;
+        if (tid < 12) s->bnd[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+        if (tid == 12) { s->nL = 0; s->f = 0; s->best = 0xFFFFFFFFu; }
+        if (tid < 144) (&s->bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+    }
+}
+
+__global__ void __launch_bounds__(T1_THREADS) k_t1_bounds(T1Args g) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_red[T1_THREADS / 32][12];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + i * T1_THREADS + tid;
+            if (j < nd.n) {
+                const uint32_t id = g.ids[0][nd.start + j];
+                const float4 c = g.cent[id];
+                const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
+                acc[0] = fminf(acc[0], b0.x); acc[1] = fminf(acc[1], b0.y); acc[2] = fminf(acc[2], b0.z);
+                acc[3] = fmaxf(acc[3], b1.x); acc[4] = fmaxf(acc[4], b1.y); acc[5] = fmaxf(acc[5], b1.z);
+                acc[6] = fminf(acc[6], c.x); acc[7] = fminf(acc[7], c.y); acc[8] = fminf(acc[8], c.z);
+                acc[9] = fmaxf(acc[9], c.x); acc[10] = fmaxf(acc[10], c.y); acc[11] = fmaxf(acc[11], c.z);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const bool is_min = (k < 3) || (k >= 6 && k < 9);
+            const uint32_t v = f2o(acc[k]);
+            const uint32_t r = is_min ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+            if (lane == 0) s_red[warp][k] = r;
+        }
+        __syncthreads();
+        if (tid < 12) {
+            const bool is_min = (tid < 3) || (tid >= 6 && tid < 9);
+            uint32_t r = s_red[0][tid];
+            for (int w2 = 1; w2 < T1_THREADS / 32; ++w2) r = is_min ? min(r, s_red[w2][tid]) : max(r, s_red[w2][tid]);
+            if (is_min) atomicMin(&g.sc[node].bnd[tid], r);
+            else atomicMax(&g.sc[node].bnd[tid], r);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(T1_THREADS) k_t1_flags(T1Args g) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        float cmin[3], cmax[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { cmin[c] = o2f(g.sc[node].bnd[6 + c]); cmax[c] = o2f(g.sc[node].bnd[9 + c]); }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + i * T1_THREADS + tid;
+            if (j < nd.n) {
+                const float4 c = g.cent[g.ids[0][nd.start + j]];
+                g.flags[0][nd.start + j] = (uint16_t)plane_counts(c.x, c.y, c.z, cmin, cmax);
+            }
+        }
+    }
+}
+
+// Per-tile L count of the current order for one candidate.
+__global__ void __launch_bounds__(T1_THREADS) k_t1_count(T1Args g, int cur, int cand) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_w[T1_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        uint32_t a, b;
+        cand_of(g.sc, node, cand, a, b);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + i * T1_THREADS + tid;
+            const bool L = (j < nd.n) && ((((uint32_t)g.flags[cur][nd.start + j] >> (3 * a)) & 7u) < b);
+            cnt += __popc(__ballot_sync(FULL_MASK, L));
+        }
+        if (lane == 0) s_w[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) tot += s_w[w2];
+            g.tileL[tile] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// One warp per node: exclusive scan of its tiles' L counts.
+__global__ void __launch_bounds__(256) k_t1_tilescan(T1Args g) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t node = gw; node < g.n_nodes; node += nw) {
+        const LevelNode nd = g.nodes[node];
+        const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nt; base += 32) {
+            const uint32_t i = base + lane;
+            const uint32_t v = (i < nt) ? g.tileL[nd.tile_base + i] : 0;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL_MASK, x, o);
+                if ((int)lane >= o) x += y;
+            }
+            if (i < nt) g.tileLF[nd.tile_base + i] = carry + x - v;
+            carry += __shfl_sync(FULL_MASK, x, 31);
+        }
+        if (lane == 0) { g.sc[node].nL = carry; g.sc[node].f = 0; }
+    }
+}
+
+// Shared by table and scatter: per-element #L before it (LF) inside the node, via tile prefix + ballots.
+// Element layout inside a tile: j = j0 + warp*256 + i*32 + lane (a warp owns 256 consecutive slots).
+template <int EPT>
+__device__ __forceinline__ void t1_prefix(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint32_t a,
+                                          uint32_t b, uint32_t tile_lf, uint32_t* s_w, uint32_t* bal,
+                                          uint32_t* LFv) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+        const bool L = (j < n) && ((((uint32_t)fl[start + j] >> (3 * a)) & 7u) < b);
+        bal[i] = __ballot_sync(FULL_MASK, L);
+        cnt += __popc(bal[i]);
+    }
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    uint32_t running = tile_lf;
+    for (uint32_t w2 = 0; w2 < warp; ++w2) running += s_w[w2];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        LFv[i] = running + __popc(bal[i] & lt_mask);
+        running += __popc(bal[i]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(T1_THREADS) k_t1_table(T1Args g, int cur, int cand) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_w[T1_THREADS / 32];
+    __shared__ uint32_t s_cnt;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        uint32_t a, b;
+        cand_of(g.sc, node, cand, a, b);
+        const uint32_t nL = g.sc[node].nL;
+        const uint16_t* fl = g.flags[cur];
+        uint32_t bal[EPT], LFv[EPT];
+        if (tid == 0) s_cnt = 0;
+        t1_prefix<EPT>(fl, nd.start, nd.n, j0, a, b, g.tileLF[tile], s_w, bal, LFv);
+        uint32_t predc = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            bool pred = false;
+            if (j < nd.n) {
+                const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                const uint32_t LF = LFv[i], RF = j - LF;
+                uint32_t Lnext;
+                if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
+                else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
+                else Lnext = (j + 1 < nd.n) ? (((((uint32_t)fl[nd.start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
+                const uint32_t LBB = nL - LF - Lbit - Lnext;
+                pred = (j + 2 <= nd.n) && (LBB >= RF);
+                if (Lbit) g.table[nd.start + nd.n - 1 - (nL - LF - 1)] = j;
+                else g.table[nd.start + RF] = j;
+            }
+            predc += __popc(__ballot_sync(FULL_MASK, pred));
+        }
+        if (lane == 0 && predc) atomicAdd(&s_cnt, predc);
+        __syncthreads();
+        if (tid == 0 && s_cnt) atomicAdd(&g.sc[node].f, s_cnt);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(T1_THREADS) k_t1_scatter(T1Args g, int cur, int cand, int cidx) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_w[T1_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        uint32_t a, b;
+        cand_of(g.sc, node, cand, a, b);
+        const uint32_t nL = g.sc[node].nL, f = g.sc[node].f, n = nd.n;
+        const uint16_t* fl = g.flags[cur];
+        const uint32_t Lf = ((((uint32_t)fl[nd.start + f] >> (3 * a)) & 7u) < b) ? 1u : 0u;
+        const uint32_t pivot = nL - Lf;
+        uint32_t bal[EPT], LFv[EPT];
+        t1_prefix<EPT>(fl, nd.start, n, j0, a, b, g.tileLF[tile], s_w, bal, LFv);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            if (j < n) {
+                const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                const uint32_t LF = LFv[i], RF = j - LF;
+                const uint32_t id = g.ids[cur][nd.start + j];
+                uint32_t fw = fl[nd.start + j];
+                uint32_t dest;
+                if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : g.table[nd.start + n - RF] - 1u);
+                else if (j == f) {
+                    dest = pivot;
+                    fw |= 0x8000u;
+                    if (cidx >= 0) { g.sc[node].piv[cidx] = pivot; g.sc[node].uid[cidx] = id; }
+                } else dest = Lbit ? g.table[nd.start + (nL - LF - 1)] : j - 1;
+                g.ids[cur ^ 1][nd.start + dest] = id;
+                g.flags[cur ^ 1][nd.start + dest] = (uint16_t)fw;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T1_THREADS) k_t1_bins(T1Args g, int cur) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_bins[3][8][6];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        if (tid < 144) (&s_bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+        __syncthreads();
+        float lo[EPT][3], hi[EPT][3];
+        uint32_t kk[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + i * T1_THREADS + tid;
+            kk[i] = 0xFFFFFFFFu;
+            lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
+            hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
+            if (j < nd.n) {
+                const uint32_t fw = g.flags[cur][nd.start + j];
+                if (!(fw & 0x8000u)) {
+                    const uint32_t id = g.ids[cur][nd.start + j];
+                    const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
+                    lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
+                    hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
+                    kk[i] = fw & 0x1FFu;
+                }
+            }
+        }
+        for (uint32_t a = 0; a < 3; ++a) {
+            for (uint32_t k = 0; k < 8; ++k) {
+                float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
+                    if (in) {
+                        any = true;
+                        m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
+                        m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                    }
+                }
+                if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const uint32_t v = f2o(m[c]);
+                    const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                    if (lane == 0) {
+                        if (c < 3) atomicMin(&s_bins[a][k][c], r);
+                        else atomicMax(&s_bins[a][k][c], r);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 144) {
+            const uint32_t v = (&s_bins[0][0][0])[tid];
+            const bool is_min = (tid % 6) < 3;
+            if (is_min) { if (v != ENC_POS_INIT) atomicMin(&(&g.sc[node].bins[0][0][0])[tid], v); }
+            else { if (v != ENC_NEG_INIT) atomicMax(&(&g.sc[node].bins[0][0][0])[tid], v); }
+        }
+        __syncthreads();
+    }
+}
+
+// One warp per node: evaluate the 21 candidates from bins + specials, pick the winner (blas.rs:155-161).
+__global__ void __launch_bounds__(256) k_t1_select(T1Args g) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t node = gw; node < g.n_nodes; node += nw) {
+        const LevelNode nd = g.nodes[node];
+        NodeScratch* s = g.sc + node;
+        float cmin[3], cmax[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { cmin[c] = o2f(s->bnd[6 + c]); cmax[c] = o2f(s->bnd[9 + c]); }
+        const uint32_t c = lane;
+        const uint32_t cs = (c < 21) ? c : 0;
+        // lane c also owns special c
+        const uint32_t my_uid = s->uid[cs];
+        const float4 ce = g.cent[my_uid];
+        const float4 b0 = g.box[2 * (size_t)my_uid], b1 = g.box[2 * (size_t)my_uid + 1];
+        const uint32_t my_kb = plane_counts(ce.x, ce.y, ce.z, cmin, cmax);
+        const uint32_t a = cs / 7, b = cs % 7 + 1;
+        float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+        float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+        for (uint32_t k = 0; k < 8; ++k) {
+            float* side = (k < b) ? Lb : Rb;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                side[x] = fminf(side[x], o2f(s->bins[a][k][x]));
+                side[3 + x] = fmaxf(side[3 + x], o2f(s->bins[a][k][3 + x]));
+            }
+        }
+        for (uint32_t s2 = 0; s2 < 21; ++s2) {
+            const uint32_t uid2 = __shfl_sync(FULL_MASK, my_uid, s2);
+            const uint32_t kb2 = __shfl_sync(FULL_MASK, my_kb, s2);
+            float bx[6];
+            bx[0] = __shfl_sync(FULL_MASK, b0.x, s2); bx[1] = __shfl_sync(FULL_MASK, b0.y, s2);
+            bx[2] = __shfl_sync(FULL_MASK, b0.z, s2); bx[3] = __shfl_sync(FULL_MASK, b1.x, s2);
+            bx[4] = __shfl_sync(FULL_MASK, b1.y, s2); bx[5] = __shfl_sync(FULL_MASK, b1.z, s2);
+            const bool left = (uid2 != my_uid) && (((kb2 >> (3 * a)) & 7u) < b);
+            float* side = left ? Lb : Rb;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                side[x] = fminf(side[x], bx[x]);
+                side[3 + x] = fmaxf(side[3 + x], bx[3 + x]);
+            }
+        }
+        const uint32_t n1 = s->piv[cs];
+        const float cost = sah_cost(Lb, Rb, n1, nd.n - n1);
+        const uint32_t key = (c < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
+        const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
+        const uint32_t bal = __ballot_sync(FULL_MASK, key == mk);
+        if (lane == 0) {
+            if (mk == 0xFFFFFFFFu) {
+                atomicOr(&g.st->err, DERR_DEGENERATE);
+                s->best = 0;  // keep the remaining phases well-defined; the build is reported as failed
+            } else s->best = __ffs(bal) - 1;
+        }
+    }
+}
+
+// One thread per node: record, A counter, children to the next level / T2 queue / T3 list.
+__global__ void __launch_bounds__(256) k_t1_children(T1Args g, LevelNode* next_nodes, uint32_t next_cap, int next_slot,
+                                                     Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, uint4* recs,
+                                                     uint32_t* A, uint32_t epoch) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= g.n_nodes) return;
+    const LevelNode nd = g.nodes[node];
+    const NodeScratch* s = g.sc + node;
+    const uint32_t p = s->piv[s->best];
+    float lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) { lo[c] = o2f(min(s->bnd[c], ENC_POS_INIT)); hi[c] = o2f(max(s->bnd[3 + c], ENC_NEG_INIT)); }
+    if (p == 0 || p >= nd.n) { atomicOr(&g.st->err, DERR_DEGENERATE); return; }
+    emit_rec(recs, 2 * (nd.start + p) + 1, lo, hi, nd.start, nd.n, nd.leftrun, nd.pstart, nd.pleftrun, nd.flags);
+    if (p <= 3) A[nd.start] = nd.leftrun + 1;
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t cs = side ? nd.start + p : nd.start;
+        const uint32_t cn = side ? nd.n - p : p;
+        const uint32_t clr = side ? 0 : nd.leftrun + 1;
+        const uint32_t cfl = side ? TF_RIGHT : 0;
+        if (cn > T2_CAP) {
+            const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
+            if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
+            LevelNode c;
+            c.start = cs; c.n = cn; c.leftrun = clr; c.pstart = nd.start; c.pleftrun = nd.leftrun; c.flags = cfl;
+            c.tile_base = 0; c.pad = 0;
+            next_nodes[idx] = c;
+        } else {
+            push_child(q, q_cap, t3, t3_cap, g.st, epoch, cs, cn, clr, nd.start, nd.leftrun, cfl);
+        }
+    }
+}
+
+// Single block: tile_base prefix of the next level's node list.
+__global__ void __launch_bounds__(1024) k_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = st->lv_count[slot];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = tid * per, e = min(n, b + per);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += (nodes[i].n + T1_TILE - 1) / T1_TILE;
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < 1024; ++i) { const uint32_t v = s_part[i]; s_part[i] = acc; acc += v; }
+        st->lv_tiles[slot] = acc;
+        st->lv_count[other] = 0;
+    }
+    __syncthreads();
+    uint32_t acc = s_part[tid];
+    for (uint32_t i = b; i < e; ++i) {
+        nodes[i].tile_base = acc;
+        acc += (nodes[i].n + T1_TILE - 1) / T1_TILE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive prefix sum over n u32 (in place), three small kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_TILE = 4096;  // 1024 threads x 4
+
+__global__ void __launch_bounds__(1024) k_scan_reduce(const uint32_t* x, uint32_t n, uint32_t* sums) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE;
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t k = base + i * 1024 + threadIdx.x;
+        if (k < n) v += x[k];
+    }
+    v = __reduce_add_sync(FULL_MASK, v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t t = s_w[threadIdx.x];
+        t = __reduce_add_sync(FULL_MASK, t);
+        if (threadIdx.x == 0) sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_top(uint32_t* sums, uint32_t nb, uint32_t* total) {
+    __shared__ uint32_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t b = min(nb, tid * per), e = min(nb, b + per);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += sums[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < 1024; ++i) { const uint32_t v = s_part[i]; s_part[i] = acc; acc += v; }
+        *total = acc;
+    }
+    __syncthreads();
+    uint32_t acc = s_part[tid];
+    for (uint32_t i = b; i < e; ++i) { const uint32_t v = sums[i]; sums[i] = acc; acc += v; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_apply(uint32_t* x, uint32_t n, const uint32_t* sums) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v[4], tot = 0;
+    for (int i = 0; i < 4; ++i) { v[i] = (base + i < n) ? x[base + i] : 0; tot += v[i]; }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL_MASK, inc, o);
+        if ((int)lane >= o) inc += y;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = s_w[lane], ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL_MASK, ti, o);
+            if ((int)lane >= o) ti += y;
+        }
+        s_w[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t acc = sums[blockIdx.x] + s_w[warp] + inc - tot;
+    for (int i = 0; i < 4; ++i) {
+        if (base + i < n) x[base + i] = acc;
+        acc += v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Emit: records -> BvhNode[] in DFS pre-order pair numbering (blas.rs:90,110-112,125-126).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_emit(const uint4* __restrict__ recs, uint32_t n_slots,
+                                              const uint32_t* __restrict__ P, BvhNode* nodes, uint32_t nodes_cap,
+                                              BuildState* st) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long s_add = 0;
+    uint32_t i_add = 0;
+    if (slot == 0 && nodes_cap > 1) {
+        uint4* z = reinterpret_cast<uint4*>(nodes + 1);  // node 1 is never used (blas.rs:90)
+        z[0] = make_uint4(0, 0, 0, 0);
+        z[1] = make_uint4(0, 0, 0, 0);
+    }
+    if (slot < n_slots) {
+        const uint4 r1 = recs[3 * (size_t)slot + 1];
+        if (r1.w != 0) {
+            const uint4 r0 = recs[3 * (size_t)slot], r2 = recs[3 * (size_t)slot + 2];
+            const uint32_t start = r0.w, count = r1.w;
+            const uint32_t pos = (r2.w & TF_ROOT) ? 0u : 2u + 2u * (P[r2.y] + r2.z) + (r2.w & TF_RIGHT);
+            uint32_t lf, cn;
+            if (count > 3) { lf = 2u + 2u * (P[start] + r2.x); cn = 0; s_add = count; i_add = 1; }
+            else { lf = start; cn = count; }
+            if (pos < nodes_cap) {
+                uint4* o = reinterpret_cast<uint4*>(nodes + pos);
+                o[0] = make_uint4(r0.x, r0.y, r0.z, lf);
+                o[1] = make_uint4(r1.x, r1.y, r1.z, cn);
+            } else atomicOr(&st->err, DERR_QUEUE);
+        }
+    }
+    // block-level aggregation of the S / interior counters
+    __shared__ unsigned long long s_s;
+    __shared__ uint32_t s_i;
+    if (threadIdx.x == 0) { s_s = 0; s_i = 0; }
+    __syncthreads();
+    if (s_add) { atomicAdd(&s_s, s_add); atomicAdd(&s_i, i_add); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_i) { atomicAdd(&st->sum_interior, s_s); atomicAdd(&st->interior_total, s_i); }
+}
+
+// indices[i] <- indices_in[order[i]]  (blas.rs:95-100)
+__global__ void __launch_bounds__(256) k_permute_gather(const uint32_t* __restrict__ I, const uint32_t* __restrict__ order,
+                                                        uint32_t N, uint32_t* tmp) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t s = 3 * (size_t)order[i];
+    tmp[3 * (size_t)i] = I[s];
+    tmp[3 * (size_t)i + 1] = I[s + 1];
+    tmp[3 * (size_t)i + 2] = I[s + 2];
+}
+
+__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_q, Task* first_t3, LevelNode* first_lv,
+                                                    uint32_t N, uint32_t epoch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    BuildState s{};
+    Task root{};
+    root.start = 0; root.n = N; root.leftrun = 0; root.pstart = 0; root.pleftrun = 0; root.flags = TF_ROOT;
+    root.ready = epoch; root.pad = 0;
+    if (N > T2_CAP) {
+        LevelNode l;
+        l.start = 0; l.n = N; l.leftrun = 0; l.pstart = 0; l.pleftrun = 0; l.flags = TF_ROOT; l.tile_base = 0; l.pad = 0;
+        first_lv[0] = l;
+        s.lv_count[0] = 1;
+        s.lv_tiles[0] = (N + T1_TILE - 1) / T1_TILE;
+    } else if (N > T3_MAX) {
+        first_q[0] = root;
+        s.q_tail = 1;
+        s.q_pending = 1;
+    } else {
+        first_t3[0] = root;
+        s.t3_count = 1;
+    }
+    *st = s;
+}
+
+}  // namespace
+
+int blas_t2_occupancy() {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2<T2_CAP, T2_THREADS>, T2_THREADS, 0) != cudaSuccess) occ = 1;
+    return occ < 1 ? 1 : occ;
+}
+
+namespace {
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace
+
+int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                      size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
+                      cudaStream_t stream) {
+    if (!d_vertices || !d_indices || !d_nodes_out || n_tris == 0 || n_vertices == 0)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: empty mesh or null pointer");
+    if (n_tris > 0x7FFFFFFFull / 2 || n_vertices > 0xFFFFFFFFull)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: mesh too large (2*n_tris must fit in 31 bits)");
+    if (nodes_cap < 2 * n_tris)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: nodes_cap must be >= 2*n_tris");
+    const uint32_t N = (uint32_t)n_tris;
+    const uint32_t max_large = N / T2_CAP + 2;
+    const uint32_t max_tiles = N / T1_TILE + max_large + 2;
+    const uint32_t q_cap = N / 4 + 4096;
+    const uint32_t t3_cap = N + 16;
+    const uint32_t scan_n = N + 1;
+    const uint32_t scan_blocks = (scan_n + SCAN_TILE - 1) / SCAN_TILE;
+
+    // carve the workspace (first pass sizes, second pass assigns)
+    float4 *cent = nullptr, *box = nullptr;
+    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr,
+             *scan_sums = nullptr, *scan_total = nullptr;
+    uint16_t *fl0 = nullptr, *fl1 = nullptr;
+    uint4* recs = nullptr;
+    Task *q = nullptr, *t3 = nullptr;
+    LevelNode* lv[2] = {nullptr, nullptr};
+    NodeScratch* sc = nullptr;
+    BuildState* st = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver c{pass ? (char*)ctx->ws : nullptr};
+        st = c.take<BuildState>(1);
+        cent = c.take<float4>(N);
+        box = c.take<float4>(2 * (size_t)N);
+        ids0 = c.take<uint32_t>(N);
+        ids1 = c.take<uint32_t>(N);
+        fl0 = c.take<uint16_t>(N);
+        fl1 = c.take<uint16_t>(N);
+        table = c.take<uint32_t>(N);
+        A = c.take<uint32_t>(scan_n);
+        recs = c.take<uint4>(3 * 2 * (size_t)N);
+        q = c.take<Task>(q_cap);
+        t3 = c.take<Task>(t3_cap);
+        lv[0] = c.take<LevelNode>(max_large);
+        lv[1] = c.take<LevelNode>(max_large);
+        sc = c.take<NodeScratch>(max_large);
+        tileL = c.take<uint32_t>(max_tiles);
+        tileLF = c.take<uint32_t>(max_tiles);
+        scan_sums = c.take<uint32_t>(scan_blocks + 1);
+        scan_total = c.take<uint32_t>(4);
+        if (pass == 0) {
+            int rc = ctx_reserve(ctx, c.off + 256);
+            if (rc) return rc;
+        }
+    }
+    ctx->epoch++;
+    const uint32_t epoch = ctx->epoch;
+    uint32_t launches = 0;
+    BvhCudaBuildStats stats{};
+
+    CU_CHECK(ctx, cudaMemsetAsync(A, 0, sizeof(uint32_t) * scan_n, stream));
+    CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
+    k_init_state<<<1, 32, 0, stream>>>(st, q, t3, lv[0], N, epoch);
+    k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, cent, box, ids0, st);
+    launches += 2;
+
+    // ---- T1: level-synchronous grid-wide phases ----
+    if (N > (uint32_t)T2_CAP) {
+        int slot = 0;
+        uint32_t n_nodes = 1, n_tiles = (N + T1_TILE - 1) / T1_TILE;
+        const uint32_t max_grid = (uint32_t)ctx->sm_count * 16;
+        while (n_nodes > 0) {
+            T1Args g;
+            g.nodes = lv[slot]; g.sc = sc; g.n_nodes = n_nodes; g.n_tiles = n_tiles;
+            g.ids[0] = ids0; g.ids[1] = ids1; g.flags[0] = fl0; g.flags[1] = fl1;
+            g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.cent = cent; g.box = box; g.st = st;
+            const uint32_t grid_t = n_tiles < max_grid ? n_tiles : max_grid;
+            const uint32_t grid_w = (n_nodes + 7) / 8 < max_grid ? (n_nodes + 7) / 8 : max_grid;
+            k_t1_init<<<n_nodes < max_grid ? n_nodes : max_grid, 256, 0, stream>>>(g);
+            k_t1_bounds<<<grid_t, T1_THREADS, 0, stream>>>(g);
+            k_t1_flags<<<grid_t, T1_THREADS, 0, stream>>>(g);
+            launches += 3;
+            int cur = 0;
+            for (int c = 0; c < 22; ++c) {
+                const int cand = (c < 21) ? c : -1;
+                if (c == 21) {
+                    k_t1_bins<<<grid_t, T1_THREADS, 0, stream>>>(g, cur);
+                    k_t1_select<<<grid_w, 256, 0, stream>>>(g);
+                    launches += 2;
+                }
+                k_t1_count<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand);
+                k_t1_tilescan<<<grid_w, 256, 0, stream>>>(g);
+                k_t1_table<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand);
+                k_t1_scatter<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand, cand);
+                launches += 4;
+                cur ^= 1;
+            }
+            const int next = slot ^ 1;
+            k_t1_children<<<(n_nodes + 255) / 256, 256, 0, stream>>>(g, lv[next], max_large, next, q, q_cap, t3, t3_cap,
+                                                                       recs, A, epoch);
+            k_t1_nextlevel<<<1, 1024, 0, stream>>>(lv[next], st, next, slot);
+            launches += 2;
+            CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
+            CU_CHECK(ctx, cudaStreamSynchronize(stream));
+            const BuildState* hs = reinterpret_cast<const BuildState*>(ctx->h_pin);
+            stats.grid_levels++;
+            if (hs->err) break;
+            n_nodes = hs->lv_count[next];
+            n_tiles = hs->lv_tiles[next];
+            slot = next;
+            if (stats.grid_levels > 4096) return ctx_fail(ctx, BVH_CUDA_EDEGENERATE, "blas_build: runaway level count");
+        }
+    }
+
+    // ---- T2: persistent blocks on the device task queue ----
+    {
+        const int blocks = ctx->sm_count * (ctx->t2_blocks_per_sm > 0 ? ctx->t2_blocks_per_sm : 1);
+        k_t2<T2_CAP, T2_THREADS><<<blocks, T2_THREADS, 0, stream>>>(q, q_cap, t3, t3_cap, ids0, cent, box, recs, A, st, epoch);
+        launches++;
+    }
+    // ---- T3: one warp per small sub-tree ----
+    {
+        const int blocks = ctx->sm_count * 8;
+        k_t3<<<blocks, 256, 0, stream>>>(t3, ids0, cent, box, recs, A, st);
+        launches++;
+    }
+    // ---- numbering + emit ----
+    k_scan_reduce<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
+    k_scan_top<<<1, 1024, 0, stream>>>(scan_sums, scan_blocks, scan_total);
+    k_scan_apply<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
+    k_emit<<<(2 * N + 255) / 256, 256, 0, stream>>>(recs, 2 * N, A, d_nodes_out, (uint32_t)(nodes_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : nodes_cap), st);
+    // permute the caller's index buffer in place (box[] is dead by now and is reused as the staging copy)
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(box);
+    k_permute_gather<<<(N + 255) / 256, 256, 0, stream>>>(d_indices, ids0, N, tmp);
+    CU_CHECK(ctx, cudaMemcpyAsync(d_indices, tmp, sizeof(uint32_t) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, stream));
+    launches += 5;
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    const BuildState* hs = reinterpret_cast<const BuildState*>(ctx->h_pin);
+    ctx->launches += launches;
+    ctx->d_last_order = ids0;
+    ctx->last_n = N;
+    if (hs->err & DERR_BAD_INDEX) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: vertex index out of range");
+    if (hs->err & DERR_DEGENERATE)
+        return ctx_fail(ctx, BVH_CUDA_EDEGENERATE, "blas_build: a node with >3 triangles has no finite-cost split (the reference would not terminate)");
+    if (hs->err) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: device task queue overflow or stall");
+    const uint32_t interior = ctx->h_pin[64];
+    stats.interior_nodes = interior;
+    stats.n_nodes = 2 + 2 * interior;
+    stats.sum_interior_prims = hs->sum_interior;
+    stats.block_tasks = hs->t2_done;
+    stats.warp_tasks = hs->t3_count;
+    stats.kernel_launches = launches;
+    ctx->stats = stats;
+    if (n_nodes_out) *n_nodes_out = stats.n_nodes;
+    if (hs->interior_total != interior) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: internal node count mismatch");
+    return BVH_CUDA_OK;
+}

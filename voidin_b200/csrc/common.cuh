@@ -1,0 +1,91 @@
+// common.cuh — shared declarations of libbvh_cuda.so (sm_100a only; compiled with -fmad=false so that no
+// a*b+c is ever fused: the reference is rustc/x86-64 scalar f32, which never contracts).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/bvh_cuda.h"
+
+#define FULL_MASK 0xFFFFFFFFu
+
+// device-side error bits (OR-ed into one word, read back at the end of a build)
+#define DERR_BAD_INDEX 1u
+#define DERR_DEGENERATE 2u
+#define DERR_QUEUE 4u   // task queue overflow or spin limit hit
+#define DERR_DEPTH 8u
+
+struct bvh_cuda_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    uint64_t launches = 0;
+    cudaStream_t own_stream = nullptr;
+    // growable device workspace (one allocation, carved per call)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // pinned host scratch for small read-backs
+    uint32_t* h_pin = nullptr;
+    // last BLAS build
+    BvhCudaBuildStats stats{};
+    uint32_t* d_last_order = nullptr;
+    size_t last_n = 0;
+    uint32_t epoch = 0;
+    int t2_blocks_per_sm = 0;
+};
+
+struct bvh_cuda_scene {
+    BvhCudaSceneDesc d{};  // device pointers
+    bool owned = false;
+    void* block = nullptr;  // single allocation when owned
+};
+
+int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what);
+int ctx_cuda_fail(bvh_cuda_ctx* ctx, cudaError_t e, const char* where);
+int ctx_reserve(bvh_cuda_ctx* ctx, size_t bytes);
+
+#define CU_CHECK(ctx, call)                                          \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return ctx_cuda_fail(ctx, _e, #call); \
+    } while (0)
+
+// implemented in blas_build.cu / tlas.cu / trace.cu
+int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                      size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
+                      cudaStream_t stream);
+int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
+                      size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, cudaStream_t stream);
+int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
+                      const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d, size_t n_rays,
+                      float* d_t, uint32_t* d_tri, cudaStream_t stream);
+int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
+                       const float* d_ray_d, size_t n_rays, float tmax, int any_hit, float* d_t, uint32_t* d_tri,
+                       uint32_t* d_inst, uint8_t* d_occ, cudaStream_t stream);
+
+#ifdef __CUDACC__
+// Order-preserving float <-> uint map (so min/max can use integer redux / atomics).  -0.0 sorts below +0.0.
+__device__ __forceinline__ uint32_t f2o(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(b);
+}
+#define ENC_POS_INIT 0xF149F2CAu /* f2o(1e30f):  0x7149F2CA | 0x80000000 */
+#define ENC_NEG_INIT 0x0EB60D35u /* f2o(-1e30f): ~0xF149F2CA */
+
+// Aabb::area (crates/bvh/src/intersection.rs:16-19): (dx*dy + dx*dz + dy*dz) * 2, left to right, unfused.
+__device__ __forceinline__ float aabb_area(float lx, float ly, float lz, float hx, float hy, float hz) {
+    float dx = __fsub_rn(hx, lx), dy = __fsub_rn(hy, ly), dz = __fsub_rn(hz, lz);
+    float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dy), __fmul_rn(dx, dz)), __fmul_rn(dy, dz));
+    return __fmul_rn(s, 2.0f);
+}
+// Vec3::lerp component (glam 0.24): a + (b - a) * s
+__device__ __forceinline__ float lerp1(float a, float b, float s) {
+    return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), s));
+}
+#endif

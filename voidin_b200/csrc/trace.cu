@@ -1,0 +1,290 @@
+// trace.cu — ray traversal kernels.
+//   k_trace_blas   Bvh::traverse_iter (crates/bvh/src/blas.rs:247-295) with the Rust tests
+//                  (crates/bvh/src/intersection.rs:47-55,68-92): division slabs, two-sided triangles,
+//                  near pushed first => far popped first.
+//   k_trace_scene  traverse_tlas / instance_intersect / traverse_bvh (shaders/utils/bvh.wgsl:35-123) with the
+//                  WGSL tests (shaders/utils/intersections.wgsl:13-45): reciprocal slabs, back-face culling,
+//                  near child popped first; ANY = early exit at the first accepted triangle, which yields
+//                  exactly traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102).
+// One thread per ray; nodes are fetched as two 16-byte loads (32-byte aligned); per-ray stacks live in
+// local memory (64 entries; the reference's 32 / 24-entry stacks overflow silently on deeper trees).
+// Compiled with -fmad=false: hit ids depend on exact, unfused float arithmetic in the reference's order.
+#include "common.cuh"
+
+namespace {
+
+constexpr int STACK_CAP = 64;
+constexpr float MAXD = 1e30f;
+
+struct NodeW {  // BvhNode / TlasNode as two float4
+    float4 a, b;
+};
+
+__device__ __forceinline__ NodeW ld_node(const void* base, uint32_t i) {
+    const float4* p = reinterpret_cast<const float4*>(base) + 2 * (size_t)i;
+    NodeW n;
+    n.a = __ldg(p);
+    n.b = __ldg(p + 1);
+    return n;
+}
+
+// ---- Rust-mode tests --------------------------------------------------------------------------------
+struct RDist {
+    bool hit;
+    float t;
+};
+__device__ __forceinline__ bool dist_gt(RDist a, RDist b) {  // derive(PartialOrd) on enum {Hit(f32), Miss}
+    if (a.hit && b.hit) return a.t > b.t;
+    if (!a.hit && !b.hit) return false;
+    return !a.hit;
+}
+// intersection.rs:47-55
+__device__ __forceinline__ RDist aabb_rs(const float* o, const float* d, const float4& mn, const float4& mx, float t) {
+    const float ax = __fdiv_rn(mn.x - o[0], d[0]), ay = __fdiv_rn(mn.y - o[1], d[1]), az = __fdiv_rn(mn.z - o[2], d[2]);
+    const float bx = __fdiv_rn(mx.x - o[0], d[0]), by = __fdiv_rn(mx.y - o[1], d[1]), bz = __fdiv_rn(mx.z - o[2], d[2]);
+    const float tmax = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+    const float tmin = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    RDist r;
+    r.hit = (tmax >= tmin) && (tmin < t) && (tmax > 0.0f);
+    r.t = tmin;
+    return r;
+}
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return (ax * bx + ay * by) + az * bz;
+}
+// intersection.rs:68-92
+__device__ __forceinline__ RDist tri_rs(const float* o, const float* d, const float* v0, const float* v1,
+                                        const float* v2) {
+    const float EPS = 0.0001f;
+    RDist miss{false, 0.0f};
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    const float hx = d[1] * e2z - e2y * d[2], hy = d[2] * e2x - e2z * d[0], hz = d[0] * e2y - e2x * d[1];
+    const float a = dot3(e1x, e1y, e1z, hx, hy, hz);
+    if (-EPS < a && a < EPS) return miss;
+    const float f = __fdiv_rn(1.0f, a);
+    const float sx = o[0] - v0[0], sy = o[1] - v0[1], sz = o[2] - v0[2];
+    const float u = f * dot3(sx, sy, sz, hx, hy, hz);
+    if (!(0.0f <= u && u <= 1.0f)) return miss;
+    const float qx = sy * e1z - e1y * sz, qy = sz * e1x - e1z * sx, qz = sx * e1y - e1x * sy;
+    const float v = f * dot3(d[0], d[1], d[2], qx, qy, qz);
+    if (v < 0.0f || u + v > 1.0f) return miss;
+    const float t = f * dot3(e2x, e2y, e2z, qx, qy, qz);
+    RDist r;
+    r.hit = t > EPS;
+    r.t = t;
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_trace_blas(const BvhNode* __restrict__ nodes, const float* __restrict__ V,
+                                                    const uint32_t* __restrict__ I, const float* __restrict__ ro,
+                                                    const float* __restrict__ rd, size_t R, float* t_out,
+                                                    uint32_t* tri_out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float o[3] = {ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]};
+    const float d[3] = {rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]};
+    uint32_t stack[STACK_CAP];
+    int head = 0;
+    stack[head++] = 0;
+    bool hit = false;
+    float t = 0.0f;
+    uint32_t tri = BVH_CUDA_NO_HIT;
+    while (head > 0) {
+        const NodeW node = ld_node(nodes, stack[--head]);
+        const uint32_t left_first = __float_as_uint(node.a.w), count = __float_as_uint(node.b.w);
+        if (count > 0) {
+            for (uint32_t i = 0; i < count; ++i) {
+                const uint32_t* idx = I + 3 * (size_t)(left_first + i);
+                const float* p0 = V + 3 * (size_t)idx[0];
+                const float* p1 = V + 3 * (size_t)idx[1];
+                const float* p2 = V + 3 * (size_t)idx[2];
+                const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+                const RDist h = tri_rs(o, d, v0, v1, v2);
+                if (h.hit) {
+                    if (!hit) { hit = true; t = h.t; tri = left_first + i; }
+                    else if (h.t < t) { t = h.t; tri = left_first + i; }
+                }
+            }
+        } else {
+            uint32_t min_index = left_first, max_index = left_first + 1;
+            const NodeW ca = ld_node(nodes, min_index), cb = ld_node(nodes, max_index);
+            const float lim = hit ? t : MAXD;
+            RDist min_dist = aabb_rs(o, d, ca.a, ca.b, lim);
+            RDist max_dist = aabb_rs(o, d, cb.a, cb.b, lim);
+            if (dist_gt(min_dist, max_dist)) {
+                const uint32_t ti = min_index; min_index = max_index; max_index = ti;
+                const RDist td = min_dist; min_dist = max_dist; max_dist = td;
+            }
+            if (!min_dist.hit) continue;
+            if (head < STACK_CAP) stack[head++] = min_index;
+            if (max_dist.hit && head < STACK_CAP) stack[head++] = max_index;
+        }
+    }
+    t_out[r] = hit ? t : MAXD;
+    tri_out[r] = tri;
+}
+
+// ---- WGSL-mode tests --------------------------------------------------------------------------------
+// intersections.wgsl:13-23
+__device__ __forceinline__ float aabb_w(const float* eye, const float* inv, const float4& mn, const float4& mx, float t) {
+    const float ax = (mn.x - eye[0]) * inv[0], ay = (mn.y - eye[1]) * inv[1], az = (mn.z - eye[2]) * inv[2];
+    const float bx = (mx.x - eye[0]) * inv[0], by = (mx.y - eye[1]) * inv[1], bz = (mx.z - eye[2]) * inv[2];
+    const float tmax = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+    const float tmin = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    return ((tmax >= tmin) && (tmin < t) && (tmax > 0.0f)) ? tmin : MAXD;
+}
+// intersections.wgsl:25-45
+__device__ __forceinline__ bool trig_w(const float* eye, const float* dir, const float* v0, const float* v1,
+                                       const float* v2, float* hit) {
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    const float ux = dir[1] * e2z - e2y * dir[2], uy = dir[2] * e2x - e2z * dir[0], uz = dir[0] * e2y - e2x * dir[1];
+    const float det = dot3(e1x, e1y, e1z, ux, uy, uz);
+    if (det < 1e-10f) return false;
+    const float inv_det = __fdiv_rn(1.0f, det);
+    const float ox = eye[0] - v0[0], oy = eye[1] - v0[1], oz = eye[2] - v0[2];
+    const float u = inv_det * dot3(ox, oy, oz, ux, uy, uz);
+    if (u < 0.0f || 1.0f < u) return false;
+    const float vx = oy * e1z - e1y * oz, vy = oz * e1x - e1z * ox, vz = ox * e1y - e1x * oy;
+    const float v = inv_det * dot3(dir[0], dir[1], dir[2], vx, vy, vz);
+    if (v < 0.0f || u + v > 1.0f) return false;
+    const float t = inv_det * dot3(e2x, e2y, e2z, vx, vy, vz);
+    if (t > 0.0f && t < *hit) { *hit = t; return true; }
+    return false;
+}
+
+// mat4 * vec4 as column sums, left to right (bvh.wgsl:82-83)
+__device__ __forceinline__ void mat_mul(const float4* m, const float* p, float w, float* out) {
+    const float4 c0 = __ldg(m), c1 = __ldg(m + 1), c2 = __ldg(m + 2), c3 = __ldg(m + 3);
+    out[0] = ((c0.x * p[0] + c1.x * p[1]) + c2.x * p[2]) + c3.x * w;
+    out[1] = ((c0.y * p[0] + c1.y * p[1]) + c2.y * p[2]) + c3.y * w;
+    out[2] = ((c0.z * p[0] + c1.z * p[1]) + c2.z * p[2]) + c3.z * w;
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float* __restrict__ ro,
+                                                     const float* __restrict__ rd, size_t R, float tmax, float* t_out,
+                                                     uint32_t* tri_out, uint32_t* inst_out, uint8_t* occ_out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float eye[3] = {ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]};
+    const float dir[3] = {rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]};
+    const float inv[3] = {__fdiv_rn(1.0f, dir[0]), __fdiv_rn(1.0f, dir[1]), __fdiv_rn(1.0f, dir[2])};
+    uint32_t tstack[STACK_CAP], bstack[STACK_CAP];
+    int th = 0;
+    tstack[th++] = 0;
+    float dist = tmax;
+    uint32_t tri = BVH_CUDA_NO_HIT, inst = BVH_CUDA_NO_HIT;
+    bool res_hit = false, done = false;
+    while (th > 0 && !done) {
+        const uint32_t ni = tstack[--th];
+        const NodeW node = ld_node(sc.tlas_nodes, ni);
+        const uint32_t left_right = __float_as_uint(node.a.w);
+        if (left_right == 0) {
+            // instance_intersect (bvh.wgsl:78-87)
+            const uint32_t ii = __float_as_uint(node.b.w);
+            const Instance* in = sc.instances + ii;
+            const MeshInfo* mesh = sc.meshes + in->mesh;
+            const uint32_t base_index = mesh->base_index, voff = (uint32_t)mesh->vertex_offset, bvh_index = mesh->bvh_index;
+            float e2[3], d2[3];
+            const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
+            mat_mul(im, eye, 1.0f, e2);
+            mat_mul(im, dir, 0.0f, d2);
+            const float inv2[3] = {__fdiv_rn(1.0f, d2[0]), __fdiv_rn(1.0f, d2[1]), __fdiv_rn(1.0f, d2[2])};
+            // traverse_bvh (bvh.wgsl:35-76)
+            int bh = 0;
+            bstack[bh++] = bvh_index;
+            float hit = dist;
+            while (bh > 0) {
+                const NodeW bn = ld_node(sc.bvh_nodes, bstack[--bh]);
+                const uint32_t left_first = __float_as_uint(bn.a.w), count = __float_as_uint(bn.b.w);
+                if (count > 0) {
+                    for (uint32_t i = 0; i < count; ++i) {
+                        const uint32_t idx = left_first + i;
+                        const uint32_t* ip = sc.indices + base_index + 3 * (size_t)idx;
+                        const float* p0 = sc.vertices + 3 * (size_t)(voff + ip[0]);
+                        const float* p1 = sc.vertices + 3 * (size_t)(voff + ip[1]);
+                        const float* p2 = sc.vertices + 3 * (size_t)(voff + ip[2]);
+                        const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+                        if (trig_w(e2, d2, v0, v1, v2, &hit)) {
+                            dist = hit; tri = idx; inst = ii; res_hit = true;
+                            if (ANY) { done = true; break; }
+                        }
+                    }
+                    if (ANY && done) break;
+                } else {
+                    uint32_t min_index = bvh_index + left_first, max_index = bvh_index + left_first + 1;
+                    const NodeW ca = ld_node(sc.bvh_nodes, min_index), cb = ld_node(sc.bvh_nodes, max_index);
+                    float min_dist = aabb_w(e2, inv2, ca.a, ca.b, hit);
+                    float max_dist = aabb_w(e2, inv2, cb.a, cb.b, hit);
+                    if (min_dist > max_dist) {
+                        const uint32_t ti = min_index; min_index = max_index; max_index = ti;
+                        const float td = min_dist; min_dist = max_dist; max_dist = td;
+                    }
+                    if (min_dist >= hit) continue;
+                    if (max_dist <= hit && bh < STACK_CAP) bstack[bh++] = max_index;
+                    if (bh < STACK_CAP) bstack[bh++] = min_index;
+                }
+            }
+        } else {
+            uint32_t min_index, max_index;
+            if (sc.tlas_children) {
+                const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                min_index = k.x; max_index = k.y;
+            } else {
+                min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
+            }
+            const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
+            float min_dist = aabb_w(eye, inv, ca.a, ca.b, dist);
+            float max_dist = aabb_w(eye, inv, cb.a, cb.b, dist);
+            if (min_dist > max_dist) {
+                const uint32_t ti = min_index; min_index = max_index; max_index = ti;
+                const float td = min_dist; min_dist = max_dist; max_dist = td;
+            }
+            if (min_dist >= dist) continue;
+            if (max_dist < dist && th < STACK_CAP) tstack[th++] = max_index;
+            if (th < STACK_CAP) tstack[th++] = min_index;
+        }
+    }
+    if (ANY) {
+        occ_out[r] = res_hit ? 1 : 0;
+    } else {
+        t_out[r] = res_hit ? dist : MAXD;
+        tri_out[r] = tri;
+        inst_out[r] = inst;
+    }
+}
+
+}  // namespace
+
+int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
+                      const float* d_ray_o, const float* d_ray_d, size_t n_rays, float* d_t, uint32_t* d_tri,
+                      cudaStream_t stream) {
+    if (!d_nodes || !d_vertices || !d_indices || !d_ray_o || !d_ray_d || !d_t || !d_tri)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    const size_t blocks = (n_rays + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: too many rays for one call");
+    k_trace_blas<<<(unsigned)blocks, 128, 0, stream>>>(d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, d_t, d_tri);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return BVH_CUDA_OK;
+}
+
+int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o, const float* d_ray_d,
+                       size_t n_rays, float tmax, int any_hit, float* d_t, uint32_t* d_tri, uint32_t* d_inst,
+                       uint8_t* d_occ, cudaStream_t stream) {
+    if (!scene || !d_ray_o || !d_ray_d) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null pointer");
+    if (any_hit ? !d_occ : (!d_t || !d_tri || !d_inst)) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null output");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    const size_t blocks = (n_rays + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: too many rays for one call");
+    if (any_hit)
+        k_trace_scene<true><<<(unsigned)blocks, 128, 0, stream>>>(scene->d, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ);
+    else
+        k_trace_scene<false><<<(unsigned)blocks, 128, 0, stream>>>(scene->d, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return BVH_CUDA_OK;
+}
