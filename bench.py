@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its config 2: dragon-class SAH BLAS build (Mtris/s) followed by 16 M any-hit
+shadow rays toward a rect area light (Mrays/s), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic input, inputs resident in HBM:
+    BLAS build of the ground plane + BLAS build of the dragon-class mesh (871 422 triangles)  -> `value` (Mtris/s)
+    TLAS build over the 2 instances
+    16 M any-hit shadow rays through the two-level BVH                                         -> `rays.value`
+Top-level `metric` is the first half of BASELINE.json's metric (build Mtris/s on dragon); the second half (shadow-ray
+Mrays/s) is the `rays` object with the same sub-keys.  N > 1: the single-mesh build does not shard ("replicas
+only": every rank builds its own copy, which it needs anyway to trace), rays are sharded (each rank traces its own
+16 M-ray shard, no data-path collective) -> "scaling": "weak".
+
+`e2e` repeats the measurement through the host-pointer C ABI (bvh_cuda_blas_build / bvh_cuda_trace_any) with
+pinned HOST buffers, H2D/D2H copies inside the timed region.  `--impl reference` times the CPU oracle port
+(oracle/, the restatement of the reference's Rust; the reference itself cannot be compiled: no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 16 * 1024 * 1024
+WORKLOAD = "config2: dragon_class BLAS build (871422 tris, stand-in for assets/dragon.obj) + 16Mi any-hit shadow rays toward a rect area light"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_inputs(rank: int, n_rays: int):
+    from voidin_b200 import scenes as S
+
+    dv, di = S.dragon_class()
+    pv, pi = S.make_plane_mesh()
+    mats, mesh_ids = S.dragon_scene_instances()
+    inst = S.make_instances(mats, mesh_ids)
+    ro, rd = S.gbuffer_shadow_rays(n_rays, S.world_triangles(dv, di, mats[1]), S.rect_light_corners(), seed=12 + rank)
+    return dv, di, pv, pi, inst, ro, rd
+
+
+def build_bytes(n_tris, n_verts, S_sum, M):
+    """12N + 12V + 36N + 44*S + 32*M + 24N."""
+    return 12 * n_tris + 12 * n_verts + 36 * n_tris + 44 * S_sum + 32 * M + 24 * n_tris
+
+
+def ray_bytes(counters_per_ray, out_bytes):
+    """24 + out + 32*pops + 64*interior + 48*tri tests + 192*instance visits."""
+    c = counters_per_ray
+    return 24 + out_bytes + 32 * c["pops"] + 64 * c["interior_visits"] + 48 * c["triangle_tests"] + 192 * c["instance_visits"]
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's Rust on the host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from voidin_b200 import scenes as S
+
+    threads = O.max_threads()
+    total = args.steps + args.warmup
+    full = total <= 6
+    if full:
+        dv, di = S.dragon_class()
+        sample = "full dragon_class mesh (871422 tris) per step"
+    else:
+        dv, di = S.displaced_sphere(165, 330, 2)
+        sample = f"displaced_sphere(165,330) = {di.size // 3} tris per step (1/8 of the dragon-class mesh; Mtris/s is near size-independent)"
+    pv, pi = S.make_plane_mesh()
+    mats, mesh_ids = S.dragon_scene_instances()
+    inst = S.make_instances(mats, mesh_ids)
+    n_rays = 1 << 20
+    ro, rd = S.gbuffer_shadow_rays(n_rays, S.world_triangles(dv, di, mats[1]), S.rect_light_corners(), seed=12)
+    bt, rt = [], []
+    for step in range(total):
+        t0 = time.perf_counter()
+        rc, pn, pperm, _, _ = O.blas_build(pv, pi)
+        rc, dn, dperm, _, st = O.blas_build(dv, di)
+        t1 = time.perf_counter()
+        pool = S.MeshPool(None)
+        pool.add_built(pv, pperm, pn); pool.add_built(dv, dperm, dn)
+        verts, inds, nodes, infos = pool.pooled()
+        rc, tl, kids, _, _ = O.tlas_build(inst, infos)
+        t2 = time.perf_counter()
+        O.trace_scene(tl, kids, inst, infos, nodes, verts, inds, ro, rd, any_hit=True, threads=threads)
+        t3 = time.perf_counter()
+        if step >= args.warmup:
+            bt.append(t1 - t0); rt.append(t3 - t2)
+    n_tris = di.size // 3 + 2
+    b_ms, r_ms = 1e3 * float(np.mean(bt)), 1e3 * float(np.mean(rt))
+    val = n_tris / (b_ms * 1e-3) / 1e6
+    rval = n_rays / (r_ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "dragon_blas_build_Mtris_per_s", "value": val, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": b_ms + r_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mtris/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rays": {"metric": "shadow_ray_Mrays_per_s", "value": rval, "unit": "Mrays/s", "ms": r_ms,
+                 "cpu_baseline": {"value": rval, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                  "sample": f"{n_rays} any-hit rays per step, std::thread over rays (the reference itself is single-threaded)"},
+                 "e2e": {"value": rval, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "phase_ms": {"build": b_ms, "trace": r_ms},
+        "note": "reference = C++ oracle port of crates/bvh (Rust toolchain absent, so oracle/_ref cannot exist); build is single-threaded like the reference",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(dv, di, pv, pi, inst):
+    """Bounded CPU sample on rank 0 at N=1: one full single-threaded dragon-class build (the reference path is
+    single-threaded) and 2^19 any-hit rays on 1 thread; also returns the oracle's per-ray visit counters, which
+    feed the traversal byte model."""
+    from oracle import oracle as O
+    from voidin_b200 import scenes as S
+
+    t0 = time.perf_counter()
+    rc, pn, pperm, _, _ = O.blas_build(pv, pi)
+    rc, dn, dperm, _, st = O.blas_build(dv, di)
+    t1 = time.perf_counter()
+    pool = S.MeshPool(None)
+    pool.add_built(pv, pperm, pn); pool.add_built(dv, dperm, dn)
+    verts, inds, nodes, infos = pool.pooled()
+    rc, tl, kids, _, _ = O.tlas_build(inst, infos)
+    mats, _ = S.dragon_scene_instances()
+    n_s = 1 << 19
+    ro, rd = S.gbuffer_shadow_rays(n_s, S.world_triangles(dv, di, mats[1]), S.rect_light_corners(), seed=12)
+    t2 = time.perf_counter()
+    *_, occ, rs = O.trace_scene(tl, kids, inst, infos, nodes, verts, inds, ro, rd, any_hit=True, threads=1)
+    t3 = time.perf_counter()
+    n_tris = di.size // 3 + 2
+    per_ray = {k: rs[k] / n_s for k in ("pops", "interior_visits", "triangle_tests", "instance_visits")}
+    build = {"value": n_tris / (t1 - t0) / 1e6, "unit": "Mtris/s", "cores": 1, "kind": "port",
+             "sample": f"one full dragon_class + plane build ({n_tris} tris), single thread, {t1 - t0:.2f} s"}
+    rays = {"value": n_s / (t3 - t2) / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+            "sample": f"{n_s} any-hit rays of the same distribution, single thread, {t3 - t2:.2f} s", "occluded_frac": float(occ.mean())}
+    return build, rays, per_ray, {"S": st["sum_interior_prims"], "M": int(len(dn))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=N_RAYS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import voidin_b200 as vb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dv, di, pv, pi, inst, ro, rd = build_inputs(rank, args.rays)
+    n_dtris, n_ptris = di.size // 3, pi.size // 3
+    n_tris = n_dtris + n_ptris
+    n_rays = ro.shape[0]
+    ctx = vb.Context(local_rank)
+    ctx.set_profiling(True)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dev_t(a, dtype):
+        return torch.from_numpy(np.ascontiguousarray(a).view(dtype).reshape(-1)).to(dev)
+
+    d_dv, d_pv = dev_t(dv, np.float32), dev_t(pv, np.float32)
+    d_di_src, d_pi_src = dev_t(di, np.int32), dev_t(pi, np.int32)
+    d_ro, d_rd = dev_t(ro, np.float32), dev_t(rd, np.float32)
+    d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
+    # pooled scene buffers laid out as MeshPool::add does (mesh/mod.rs:309-351): plane first, then the dragon
+    n_verts = pv.shape[0] + dv.shape[0]
+    d_verts = torch.cat([d_pv, d_dv])
+    d_inds = torch.empty(3 * n_tris, dtype=torch.int32, device=dev)
+    nodes_cap = 2 * n_ptris + 2 * n_dtris
+    d_nodes = torch.zeros(nodes_cap * 8, dtype=torch.int32, device=dev)
+    d_tlas = torch.zeros((2 * 2 + 1) * 8, dtype=torch.int32, device=dev)
+    d_kids = torch.zeros((2 * 2 + 1) * 2, dtype=torch.int32, device=dev)
+    d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
+    d_infos = torch.zeros(2 * 48, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    from voidin_b200.types import MESH_INFO
+    infos = np.zeros(2, dtype=MESH_INFO)
+    infos["min"][0], infos["max"][0] = pv.min(0), pv.max(0)
+    infos["min"][1], infos["max"][1] = dv.min(0), dv.max(0)
+    infos["index_count"] = [pi.size, di.size]
+    infos["base_index"] = [0, pi.size]
+    infos["vertex_offset"] = [0, pv.shape[0]]
+
+    state = {}
+
+    def step_dev(ev=None):
+        """One step on device-resident inputs.  ev: optional list of 4 torch events."""
+        d_inds[: 3 * n_ptris].copy_(d_pi_src)      # builds permute indices in place: restore the unpermuted input
+        d_inds[3 * n_ptris:].copy_(d_di_src)
+        if ev: ev[0].record()
+        m0 = ctx.blas_build_dev(d_pv.data_ptr(), pv.shape[0], d_inds.data_ptr(), n_ptris, d_nodes.data_ptr(), 2 * n_ptris, stream)
+        m1 = ctx.blas_build_dev(d_dv.data_ptr(), dv.shape[0], d_inds.data_ptr() + 12 * n_ptris, n_dtris,
+                                d_nodes.data_ptr() + 32 * m0, 2 * n_dtris, stream)
+        state["stats"] = ctx.last_build_stats()
+        if ev: ev[1].record()
+        infos["bvh_index"] = [0, m0]
+        d_infos.copy_(torch.from_numpy(infos.view(np.uint8).reshape(-1)), non_blocking=False)
+        ctx.tlas_build_dev(d_inst.data_ptr(), 2, d_infos.data_ptr(), 2, d_tlas.data_ptr(), d_kids.data_ptr(), stream)
+        if ev: ev[2].record()
+        scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
+                         d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
+                         counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": m0 + m1, "vertices": n_verts,
+                                 "indices": 3 * n_tris})
+        scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
+        if ev: ev[3].record()
+        scene.close()
+        state["M"] = m0 + m1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu_build = cpu_rays = None
+    per_ray = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_build, cpu_rays, per_ray, _ = cpu_baseline_leg(dv, di, pv, pi, inst)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+
+    # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = ctx.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    phase_lib = []
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed: outside the event brackets)
+        step_dev(evs[k])
+        phase_lib.append(state["stats"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    b_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    t_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
+    r_ms = np.array([e[2].elapsed_time(e[3]) for e in evs])
+    s_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
+    tot = torch.tensor([b_ms.sum(), r_ms.sum(), s_ms.sum(), t_ms.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    b_tot, r_tot, s_tot, t_tot = [float(x) for x in tot.tolist()]
+    occ_frac = float(d_occ.float().mean().item())
+
+    # ---- end-to-end through the host-pointer C ABI, pinned host buffers ----
+    h_dv = torch.from_numpy(dv.reshape(-1)).pin_memory()
+    h_di = torch.from_numpy(di.view(np.int32)).pin_memory()
+    h_di_work = torch.empty_like(h_di).pin_memory()
+    h_nodes = torch.empty(2 * n_dtris * 8, dtype=torch.int32).pin_memory()
+    h_ro, h_rd = torch.from_numpy(ro.reshape(-1)).pin_memory(), torch.from_numpy(rd.reshape(-1)).pin_memory()
+    h_occ = torch.empty(n_rays, dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    lib = ctx.lib
+    host_scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
+                          d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
+                          counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": state["M"], "vertices": n_verts,
+                                  "indices": 3 * n_tris})
+    e2e_steps = max(3, min(args.steps, 5))
+    eb, er = [], []
+    for k in range(e2e_steps + 1):
+        h_di_work.copy_(h_di)
+        m = C.c_uint32(0)
+        barrier()
+        t0 = time.perf_counter()
+        ctx.check(lib.bvh_cuda_blas_build(ctx.h, h_dv.data_ptr(), dv.shape[0], h_di_work.data_ptr(), n_dtris, h_nodes.data_ptr(),
+                                          2 * n_dtris, C.byref(m)))
+        t1 = time.perf_counter()
+        ctx.check(lib.bvh_cuda_trace_any(ctx.h, host_scene.h, h_ro.data_ptr(), h_rd.data_ptr(), n_rays, 1e30, h_occ.data_ptr()))
+        t2 = time.perf_counter()
+        if k > 0:
+            eb.append(t1 - t0); er.append(t2 - t1)
+    e2e_t = torch.tensor([float(np.mean(eb)), float(np.mean(er))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_b, e2e_r = [float(x) for x in e2e_t.tolist()]
+    m_dragon = int(m.value)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        st = phase_lib[-1]  # stats of the dragon build (the last build of a step)
+        bb = build_bytes(n_dtris, dv.shape[0], st["sum_interior_prims"], st["n_nodes"])
+        b_ms_step = b_tot / args.steps
+        r_ms_step = r_tot / args.steps
+        value = world * n_tris / (b_ms_step * 1e-3) / 1e6
+        rvalue = world * n_rays / (r_ms_step * 1e-3) / 1e6
+        lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_block", "ms_warp_node", "ms_warp", "ms_emit", "ms_total")}
+        build_roof = {"bound": "hbm", "achieved": bb / (lib_ms["ms_total"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                      "kernel": "whole dragon build (latency-bound chain of dependent passes); per-phase device ms in phase_ms_dragon",
+                      "algorithmic_bytes": bb, "S": st["sum_interior_prims"], "M": st["n_nodes"]}
+        if per_ray is None:
+            per_ray = {"pops": 0.0, "interior_visits": 0.0, "triangle_tests": 0.0, "instance_visits": 0.0}
+            rb_note = "visit counters unavailable (CPU leg skipped): compulsory bytes only"
+        else:
+            rb_note = "per-ray visit counters from the oracle on a 2^19-ray sample of the same distribution"
+        rb = ray_bytes(per_ray, 1)
+        scene_bytes = 32 * state["M"] + 12 * n_verts + 12 * n_tris + 5 * 32 + 2 * 192
+        ray_roof = {"bound": "hbm", "achieved": rb * n_rays / (r_ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": rb * n_rays / (r_ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel": "k_trace_scene<ANY> (one launch per step)", "bytes_per_ray": rb, "counters_per_ray": per_ray,
+                    "compulsory_GBps": ((25 * n_rays + scene_bytes) / (r_ms_step * 1e-3) / 1e9), "note": rb_note}
+        line = {
+            "metric": "dragon_blas_build_Mtris_per_s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": s_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tris": n_tris, "rays_per_gpu": n_rays, "l2": "flushed between timed iterations (256 MiB fill)",
+                       "multi_gpu": "build: replicas only; rays: sharded, no collective"},
+            "phase_ms": {"build": b_ms_step, "tlas": t_tot / args.steps, "trace": r_ms_step},
+            "phase_ms_dragon": lib_ms,
+            "roofline": build_roof,
+            "cpu_baseline": cpu_build,
+            "e2e": {"value": world * n_dtris / e2e_b / 1e6, "unit": "Mtris/s", "ms": e2e_b * 1e3,
+                    "h2d_bytes_per_step": int(dv.nbytes + di.nbytes), "d2h_bytes_per_step": int(32 * m_dragon + di.nbytes),
+                    "api": "bvh_cuda_blas_build (host pointers, pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "rays": {"metric": "shadow_ray_Mrays_per_s", "value": rvalue, "unit": "Mrays/s", "ms": r_ms_step, "occluded_frac": occ_frac,
+                     "roofline": ray_roof, "cpu_baseline": cpu_rays,
+                     "e2e": {"value": world * n_rays / e2e_r / 1e6, "unit": "Mrays/s", "ms": e2e_r * 1e3,
+                             "h2d_bytes_per_step": int(ro.nbytes + rd.nbytes), "d2h_bytes_per_step": int(n_rays),
+                             "api": "bvh_cuda_trace_any (host pointers, pinned)"}},
+            "wall_s_timed_region_incl_flush": t_wall,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,10 +79,21 @@ typedef struct BvhCudaBuildStats {
     uint64_t sum_interior_prims; /* S: sum over interior nodes of their triangle count */
     uint32_t n_nodes;            /* M = 2 + 2 * interior nodes */
     uint32_t interior_nodes;
-    uint32_t grid_levels;        /* levels handled by the grid-wide tier */
-    uint32_t block_tasks;        /* nodes handled one block each from the device task queue */
+    uint32_t grid_levels;        /* levels handled by the grid-wide tier (nodes > 2048 triangles) */
+    uint32_t block_tasks;        /* nodes handled one block each from the device task queue (257..2048) */
+    uint32_t warp_node_tasks;    /* nodes handled one warp each from the second task queue (33..256) */
     uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each */
     uint32_t kernel_launches;    /* kernels launched by this build */
+    uint32_t reserved;
+    /* Device time per phase in ms (CUDA events on the build's stream); all zero unless profiling is enabled. */
+    float ms_setup;              /* k_setup: centroids, triangle boxes */
+    float ms_grid;               /* grid-wide tier, all levels */
+    float ms_block;              /* k_t2: block-per-node task-queue kernel (one launch) */
+    float ms_warp_node;          /* k_t2w: warp-per-node task-queue kernel (one launch) */
+    float ms_warp;               /* k_t3: warp-per-sub-tree kernel (one launch) */
+    float ms_emit;               /* numbering scan + node emit + index permutation */
+    float ms_total;
+    float reserved_f;
 } BvhCudaBuildStats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -93,6 +104,9 @@ const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
 /* Total kernels launched through this context since creation. */
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
 int bvh_cuda_abi_version(void);
+/* enable != 0: later BLAS builds record per-phase CUDA-event timings into BvhCudaBuildStats (a few extra event
+ * records per build, no extra synchronisation). */
+int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable);
 
 /* ---- BLAS: BvhBuilder::new(vertices, indices).build()  (crates/bvh/src/blas.rs:51-103) ----------------- *
  * Caller: MeshPool::add, crates/pools/src/mesh/mod.rs:320-321.

@@ -1,0 +1,73 @@
+"""The C-ABI shared library loads and exports every symbol include/bvh_cuda.h declares; struct layouts match;
+the host mirror refuses to run without the CUDA path (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import voidin_b200 as vb
+from voidin_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "bvh_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bvh_cuda_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bvh_cuda.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names
+    assert lib.bvh_cuda_abi_version() == 1
+
+
+def test_struct_layouts_match_the_reference():
+    assert vb.BVH_NODE.itemsize == 32 and vb.TLAS_NODE.itemsize == 32
+    assert vb.INSTANCE.itemsize == 144 and vb.MESH_INFO.itemsize == 48
+    assert vb.BVH_NODE.fields["left_first"][1] == 12 and vb.BVH_NODE.fields["count"][1] == 28
+    assert vb.TLAS_NODE.fields["left_right"][1] == 12 and vb.TLAS_NODE.fields["instance_idx"][1] == 28
+    assert vb.INSTANCE.fields["inv_transform"][1] == 64 and vb.INSTANCE.fields["mesh"][1] == 128
+    assert vb.MESH_INFO.fields["vertex_offset"][1] == 32 and vb.MESH_INFO.fields["bvh_index"][1] == 36
+    assert C.sizeof(_lib.BuildStats) == 72
+
+
+def test_null_context_calls_are_rejected_not_crashing():
+    lib = _lib.load()
+    assert lib.bvh_cuda_blas_build(None, None, 0, None, 0, None, 0, None) == -1
+    assert lib.bvh_cuda_tlas_build(None, None, 0, None, 0, None, None) == -1
+    assert lib.bvh_cuda_launch_count(None) == 0
+    lib.bvh_cuda_destroy(None)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(vb.BvhCudaError):
+        vb.Context(0)
+
+
+def test_builder_argument_checks_mirror_the_reference():
+    v = np.zeros((3, 3), np.float32)
+    with pytest.raises(TypeError):
+        vb.BvhBuilder(v, [0, 1, 2], ctx=object())  # not an in-place-permutable u32 buffer
+    with pytest.raises(vb.BvhCudaError):
+        vb.BvhBuilder(v, np.zeros(4, np.uint32), ctx=object())  # len % 3 != 0 (mesh/mod.rs:321)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "voidin_b200")
+    pat = re.compile(r"(^\s*(from|import)\s+oracle\b|libbvh_oracle|#include\s+\"[^\"]*oracle)", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f

@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (via the host mirror), against the oracle on
+the same seeded inputs — bit-exact nodes, topology, primitive order and hit ids; t within 1e-6 relative (in
+practice bit-exact, since the kernels are compiled without FMA contraction)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import voidin_b200 as vb
+from voidin_b200 import scenes as S
+
+from helpers import check_bvh_structure, make_scene, sha, small_meshes
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_hashes.json")
+T_RTOL = 1e-6  # north_star: "hit distance t agrees within 1e-6 relative"
+
+
+def gpu_build(ctx, v, idx):
+    gi = np.array(idx, dtype=np.uint32, copy=True)
+    bvh = vb.BvhBuilder(v, gi, ctx).build()
+    return bvh, gi
+
+
+@pytest.mark.parametrize("name,v,idx", small_meshes(), ids=lambda x: x if isinstance(x, str) else None)
+def test_blas_bit_exact(ctx, oracle, name, v, idx):
+    bvh, gi = gpu_build(ctx, v, idx)
+    rc, onodes, oidx, oorder, st = oracle.blas_build(v, idx)
+    assert rc == 0
+    assert len(bvh.nodes) == len(onodes)
+    assert bvh.nodes.tobytes() == onodes.tobytes()          # node AABBs + topology
+    assert (gi == oidx).all()                               # permuted index buffer
+    assert (ctx.last_order(idx.size // 3) == oorder).all()  # primitive order
+    gst = ctx.last_build_stats()
+    assert gst["sum_interior_prims"] == st["sum_interior_prims"] and gst["interior_nodes"] == st["interior_nodes"]
+
+
+@pytest.mark.parametrize("n,seed,edge", [(100_000, 0, 0.01), (300_000, 21, 0.01)])
+def test_blas_bit_exact_grid_tier(ctx, oracle, n, seed, edge):
+    v, idx = S.soup(n, seed, edge)
+    bvh, gi = gpu_build(ctx, v, idx)
+    rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+    assert rc == 0 and bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
+    assert ctx.last_build_stats()["grid_levels"] >= 5
+
+
+def test_blas_matches_committed_golden_hashes(ctx):
+    gold = json.load(open(GOLDEN))
+    for name, (v, idx) in {"uv_sphere_10": S.make_uv_sphere(1.0, 10), "soup_1000_seed7": S.soup(1000, 7, 0.05),
+                           "soup_100000_seed0_edge0.01": S.soup(100000, 0, 0.01), "grid_20x20": S.grid_mesh(20, 20)}.items():
+        assert sha(v, idx) == gold[name]["input"]
+        bvh, gi = gpu_build(ctx, v, idx)
+        assert sha(bvh.nodes) == gold[name]["nodes"] and sha(gi) == gold[name]["indices"]
+        assert sha(ctx.last_order(idx.size // 3)) == gold[name]["order"]
+
+
+def test_blas_full_size_dragon_class_properties(ctx, oracle):
+    """BASELINE config 2 size (871 K triangles): size-independent properties + idempotence; the bit-exact
+    comparison with the (slow, single-threaded) oracle at this size lives in test_blas_dragon_class_vs_oracle."""
+    v, idx = S.dragon_class()
+    bvh, gi = gpu_build(ctx, v, idx)
+    n = idx.size // 3
+    order = ctx.last_order(n)
+    check_bvh_structure(v, idx, bvh.nodes, gi, order)
+    bvh2, gi2 = gpu_build(ctx, v, idx)  # deterministic
+    assert bvh2.nodes.tobytes() == bvh.nodes.tobytes() and (gi2 == gi).all()
+
+
+def test_blas_dragon_class_vs_oracle(ctx, oracle):
+    v, idx = S.dragon_class()
+    bvh, gi = gpu_build(ctx, v, idx)
+    rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+    assert rc == 0 and bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
+
+
+def test_blas_errors(ctx):
+    v, idx = S.soup(4, 1, 0.05)
+    with pytest.raises(vb.BvhCudaError) as e:
+        vb.BvhBuilder(v, np.zeros(0, np.uint32), ctx).build()  # empty mesh: blas.rs:84 panics
+    assert e.value.code == vb.types.EINVAL
+    bad = idx.copy(); bad[5] = 10_000
+    with pytest.raises(vb.BvhCudaError) as e:
+        vb.BvhBuilder(v, bad, ctx).build()
+    assert e.value.code == vb.types.EINVAL
+    dv = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (8, 1))
+    with pytest.raises(vb.BvhCudaError) as e:
+        vb.BvhBuilder(dv, np.arange(24, dtype=np.uint32), ctx).build()
+    assert e.value.code == vb.types.EDEGENERATE
+    # the context stays usable after an error
+    bvh, _ = gpu_build(ctx, v, idx)
+    assert len(bvh.nodes) == 4
+
+
+def test_set_bin_number_is_inert_like_the_reference(ctx):
+    v, idx = S.soup(500, 3, 0.05)
+    a = vb.BvhBuilder(v, idx.copy(), ctx).build()
+    b = vb.BvhBuilder(v, idx.copy(), ctx).set_bin_number(32).build()  # blas.rs:64-67,136
+    assert a.nodes.tobytes() == b.nodes.tobytes()
+
+
+@pytest.mark.parametrize("n_inst", [1, 2, 3, 10, 100, 1000, 3000])
+def test_tlas_bit_exact(ctx, oracle, n_inst):
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, _ = make_scene(builder)
+    inst = S.random_instances(n_inst, 3, seed=n_inst, extent=20.0)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    rc, otl, okids, _, _ = oracle.tlas_build(inst, infos)
+    assert rc == 0 and tl.nodes.tobytes() == otl.tobytes() and (tl.children == okids).all()
+
+
+def test_tlas_ties_on_a_regular_grid(ctx, oracle):
+    """Identical meshes on a lattice: many exactly equal union areas, so first-index tie-breaking decides."""
+    v, idx = S.make_uv_sphere(1.0, 1)
+    b, gi = gpu_build(ctx, v, idx)
+    pool = S.MeshPool(lambda vv, ii: (b.nodes, gi))
+    pool.add(v, idx)
+    verts, inds, nodes, infos = pool.pooled()
+    mats = np.stack([S.mat_translation([3.0 * (k % 16), 0.0, 3.0 * (k // 16)]) for k in range(256)])
+    inst = S.make_instances(mats, np.zeros(256, dtype=np.int64))
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    rc, otl, okids, _, _ = oracle.tlas_build(inst, infos)
+    assert tl.nodes.tobytes() == otl.tobytes() and (tl.children == okids).all()
+
+
+def test_trace_two_level_ids_exact(ctx, oracle):
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=300)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    ro, rd = S.rays_toward_box(200_000, [-20, -20, -20], [20, 20, 20], seed=77)
+    t, tri, ins = scene.traverse_tlas(ro, rd)
+    occ = scene.occluded(ro, rd)
+    ot, otri, oins, _, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd,
+                                               threads=oracle.max_threads())
+    _, _, _, oocc, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd, any_hit=True,
+                                          threads=oracle.max_threads())
+    assert (tri == otri).all() and (ins == oins).all()
+    assert np.allclose(t, ot, rtol=T_RTOL, atol=0.0)
+    assert (occ == oocc).all() and (occ == (ot < np.float32(1e30))).all()
+    assert (otri != 0xFFFFFFFF).sum() > 10_000
+    # unnormalised directions (shadow rays, raytraced_shadows.wgsl:98-99) and a finite tmax
+    rd2 = (rd * np.float32(7.5)).astype(np.float32)
+    t2, tri2, ins2 = scene.traverse_tlas(ro, rd2, tmax=2.0)
+    ot2, otri2, oins2, _, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd2, tmax=2.0,
+                                                 threads=oracle.max_threads())
+    assert (tri2 == otri2).all() and (ins2 == oins2).all() and np.allclose(t2, ot2, rtol=T_RTOL, atol=0.0)
+    # packed 16+16 children (no side buffer) give the same answer while I <= 32767
+    scene_packed = vb.Scene(tl.nodes, None, inst, infos, nodes, verts, inds, ctx)
+    t3, tri3, ins3 = scene_packed.traverse_tlas(ro[:20000], rd[:20000])
+    assert (tri3 == otri[:20000]).all() and (ins3 == oins[:20000]).all()
+
+
+def test_trace_blas_rust_mode_ids_exact(ctx, oracle):
+    v, idx = S.bunny_class()
+    bvh, gi = gpu_build(ctx, v, idx)
+    ro, rd = S.rays_toward_box(200_000, v.min(0), v.max(0), seed=11)
+    t, tri = bvh.traverse_iter_batch(v, gi, ro, rd)
+    ot, otri, _ = oracle.trace_blas(bvh.nodes, v, gi, ro, rd, threads=oracle.max_threads())
+    assert (tri == otri).all() and np.allclose(t, ot, rtol=T_RTOL, atol=0.0)
+    one = bvh.traverse_iter(v, gi, vb.Ray.new(ro[0], rd[0]))
+    assert one == (vb.MISS if ot[0] >= np.float32(1e30) else vb.Hit(ot[0]))
+
+
+def test_trace_empty_and_degenerate_rays(ctx, oracle):
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=5)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    t, tri, ins = scene.traverse_tlas(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert t.size == 0
+    # axis-aligned directions (zero components -> infinite reciprocals) and zero-length directions
+    ro = np.array([[0, 50, 0], [0, 0, 0], [5, 5, 5], [1, 2, 3]], np.float32)
+    rd = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 0], [0, 0, 1]], np.float32)
+    t, tri, ins = scene.traverse_tlas(ro, rd)
+    ot, otri, oins, _, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd)
+    assert (tri == otri).all() and (ins == oins).all() and (t == ot).all()

@@ -1,0 +1,154 @@
+"""CPU tests of the oracle: the sequential restatement against the independently written scan/bin/rank model,
+structural self-checks, the closed-form shuffle against the sequential loop, TLAS invariants, brute-force
+traversal, and the committed golden hashes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from voidin_b200 import scenes as S
+
+from helpers import check_bvh_structure, make_scene, sha, small_meshes
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_hashes.json")
+
+
+@pytest.mark.parametrize("name,v,idx", small_meshes(), ids=lambda x: x if isinstance(x, str) else None)
+def test_sequential_equals_model_and_structure(oracle, name, v, idx):
+    rc, nodes, perm, order, st = oracle.blas_build(v, idx)
+    rc2, nodes2, perm2, order2, _ = oracle.blas_build(v, idx, model=True)
+    assert rc == 0 and rc2 == 0
+    assert nodes.tobytes() == nodes2.tobytes()
+    assert (perm == perm2).all() and (order == order2).all()
+    check_bvh_structure(v, idx, nodes, perm, order)
+    assert len(nodes) == 2 + 2 * st["interior_nodes"]
+
+
+def _shuffle_closed_form(flags):
+    """SURVEY.md Appendix B as used by the kernels, on a bare L/R flag vector; returns (dest[], pivot)."""
+    n = len(flags)
+    L = np.asarray(flags, dtype=bool)
+    nL = int(L.sum())
+    RF = np.concatenate([[0], np.cumsum(~L)[:-1]])
+    LF = np.arange(n) - RF
+    tab = np.zeros(n, dtype=np.int64)
+    for j in range(n):
+        if L[j]:
+            tab[n - 1 - (nL - LF[j] - 1)] = j
+        else:
+            tab[RF[j]] = j
+    f = 0
+    for j in range(n):
+        lnext = int(L[j + 1]) if j + 1 < n else 0
+        lbb = nL - LF[j] - int(L[j]) - lnext
+        if j + 2 <= n and lbb >= RF[j]:
+            f += 1
+    pivot = nL - int(L[f])
+    dest = np.zeros(n, dtype=np.int64)
+    for j in range(n):
+        if j < f:
+            dest[j] = j if L[j] else (n - 1 if RF[j] == 0 else tab[n - RF[j]] - 1)
+        elif j == f:
+            dest[j] = pivot
+        else:
+            dest[j] = tab[nL - LF[j] - 1] if L[j] else j - 1
+    return dest, pivot
+
+
+def test_closed_form_shuffle_equals_sequential(oracle):
+    rng = np.random.default_rng(0)
+    for trial in range(3000):
+        n = int(rng.integers(1, 40))
+        p = rng.random()
+        flags = (rng.random(n) < p).astype(np.uint8)
+        piv, ids = oracle.shuffle_seq(np.arange(n, dtype=np.uint32), flags)
+        dest, pivot = _shuffle_closed_form(flags)
+        out = np.empty(n, dtype=np.int64)
+        out[dest] = np.arange(n)
+        assert pivot == piv, (flags, pivot, piv)
+        assert (out == ids).all(), (flags, out, ids)
+
+
+def test_empty_and_invalid_inputs(oracle):
+    v, idx = S.soup(4, 1, 0.05)
+    rc, *_ = oracle.blas_build(v, np.zeros(0, dtype=np.uint32))
+    assert rc == oracle.EINVAL
+    bad = idx.copy()
+    bad[5] = 10_000
+    rc, *_ = oracle.blas_build(v, bad)
+    assert rc == oracle.EINVAL
+
+
+def test_degenerate_input_is_reported(oracle):
+    # >= 4 triangles with identical centroids: every candidate has an empty left side (blas.rs:139,115)
+    v = np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (8, 1))
+    idx = np.arange(24, dtype=np.uint32)
+    rc, _, perm, _, _ = oracle.blas_build(v, idx)
+    assert rc == oracle.EDEGENERATE
+    assert (perm == idx).all()  # untouched
+    rc2, *_ = oracle.blas_build(v, idx, model=True)
+    assert rc2 == oracle.EDEGENERATE
+
+
+def test_tlas_invariants(oracle):
+    def builder(v, i):
+        rc, nodes, perm, _, _ = oracle.blas_build(v, i)
+        assert rc == 0
+        return nodes, perm
+
+    verts, inds, nodes, infos, _ = make_scene(builder)
+    for n_inst in (1, 2, 3, 17, 300):
+        inst = S.random_instances(n_inst, 3, seed=n_inst, extent=20.0)
+        rc, tl, kids, calls, pairs = oracle.tlas_build(inst, infos)
+        assert rc == 0 and len(tl) == 2 * n_inst + 1  # tlas.rs:32
+        # self-merged root (tlas.rs:61): both children of node 0 are the same node
+        assert kids[0][0] == kids[0][1]
+        assert tl["left_right"][0] == np.uint32((int(kids[0][0]) + (int(kids[0][1]) << 16)) & 0xFFFFFFFF)
+        leaves = tl[1:n_inst + 1]
+        assert (leaves["left_right"] == 0).all() and (leaves["instance_idx"] == np.arange(n_inst)).all()
+        # leaf boxes contain the untransformed local box (tlas.rs:39 quirk)
+        mi = infos[inst["mesh"]]
+        assert (leaves["min"] <= mi["min"]).all() and (leaves["max"] >= mi["max"]).all()
+        # every interior box is the exact union of its children
+        for k in range(n_inst + 1, 2 * n_inst + 1):
+            a, b = kids[k]
+            assert (tl["min"][k] == np.minimum(tl["min"][a], tl["min"][b])).all()
+            assert (tl["max"][k] == np.maximum(tl["max"][a], tl["max"][b])).all()
+            assert tl["instance_idx"][k] == 0xFFFFFFFF
+
+
+def test_traversal_equals_brute_force(oracle):
+    v, idx = S.displaced_sphere(36, 72, 9)
+    rc, nodes, perm, _, _ = oracle.blas_build(v, idx)
+    ro, rd = S.rays_toward_box(3000, v.min(0), v.max(0), seed=11)
+    t, tri, st = oracle.trace_blas(nodes, v, perm, ro, rd)
+    bf = oracle.brute_force(v, perm, ro, rd, mode=0)
+    assert (t == bf).all()
+    hit = tri != 0xFFFFFFFF
+    assert hit.sum() > 500 and (t[~hit] == np.float32(1e30)).all()
+    # two-level, WGSL semantics, single identity instance == brute force with culling
+    pool = S.MeshPool(lambda vv, ii: (nodes, perm))
+    pool.add(v, idx)
+    verts, inds, bnodes, infos = pool.pooled()
+    inst = S.make_instances(np.eye(4)[None], [0])
+    rc, tl, kids, _, _ = oracle.tlas_build(inst, infos)
+    t2, tri2, ins2, occ, _ = oracle.trace_scene(tl, kids, inst, infos, bnodes, verts, inds, ro, rd)
+    bf2 = oracle.brute_force(v, perm, ro, rd, mode=1)
+    assert (t2 == bf2).all()
+    _, _, _, occ_any, _ = oracle.trace_scene(tl, kids, inst, infos, bnodes, verts, inds, ro, rd, any_hit=True)
+    assert (occ_any == (t2 < np.float32(1e30))).all() and (occ == occ_any).all()
+    # packed 16+16 children decode to the same traversal when I <= 32767
+    t3, tri3, ins3, _, _ = oracle.trace_scene(tl, None, inst, infos, bnodes, verts, inds, ro, rd)
+    assert (t3 == t2).all() and (tri3 == tri2).all() and (ins3 == ins2).all()
+
+
+def test_golden_hashes(oracle):
+    """Regression pin of the oracle's own outputs (tests/golden/make_golden.py wrote them; the reference has no
+    golden vectors of its own — 'parity unpinned', see oracle/bvh_oracle.cpp header)."""
+    with open(GOLDEN) as f:
+        gold = json.load(f)
+    from golden.make_golden import compute
+
+    now = compute()
+    assert now == gold

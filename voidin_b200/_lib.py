@@ -15,6 +15,7 @@ SYMBOLS = [
     "bvh_cuda_destroy",
     "bvh_cuda_last_error",
     "bvh_cuda_launch_count",
+    "bvh_cuda_set_profiling",
     "bvh_cuda_blas_build",
     "bvh_cuda_blas_build_dev",
     "bvh_cuda_blas_last_order",
@@ -40,12 +41,22 @@ class BuildStats(C.Structure):
         ("interior_nodes", C.c_uint32),
         ("grid_levels", C.c_uint32),
         ("block_tasks", C.c_uint32),
+        ("warp_node_tasks", C.c_uint32),
         ("warp_tasks", C.c_uint32),
         ("kernel_launches", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("ms_setup", C.c_float),
+        ("ms_grid", C.c_float),
+        ("ms_block", C.c_float),
+        ("ms_warp_node", C.c_float),
+        ("ms_warp", C.c_float),
+        ("ms_emit", C.c_float),
+        ("ms_total", C.c_float),
+        ("reserved_f", C.c_float),
     ]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        return {k: (float(getattr(self, k)) if k.startswith("ms_") else int(getattr(self, k))) for k, _ in self._fields_}
 
 
 class SceneDesc(C.Structure):
@@ -89,6 +100,7 @@ def load() -> C.CDLL:
     lib.bvh_cuda_last_error.restype = C.c_char_p
     lib.bvh_cuda_launch_count.argtypes = [vp]
     lib.bvh_cuda_launch_count.restype = C.c_uint64
+    lib.bvh_cuda_set_profiling.argtypes = [vp, C.c_int]
     lib.bvh_cuda_blas_build.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p]
     lib.bvh_cuda_blas_build_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p, vp]
     lib.bvh_cuda_blas_last_order.argtypes = [vp, vp, sz]

@@ -52,6 +52,9 @@ class Context:
         if rc != 0:
             raise _lib.BvhCudaError(rc, self.lib.bvh_cuda_last_error(self.h).decode())
 
+    def set_profiling(self, enable: bool):
+        self.check(self.lib.bvh_cuda_set_profiling(self.h, 1 if enable else 0))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.bvh_cuda_launch_count(self.h))

@@ -8,6 +8,8 @@
 #include <new>
 
 int blas_t2_occupancy();
+int blas_t2w_occupancy();
+int blas_t1_coop_occupancy();
 
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what) {
     if (ctx) ctx->err = what ? what : "";
@@ -43,7 +45,35 @@ int ctx_reserve(bvh_cuda_ctx* ctx, size_t bytes) {
     return BVH_CUDA_OK;
 }
 
+int ctx_stage_reserve(bvh_cuda_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return BVH_CUDA_OK;
+    if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    cudaError_t e = cudaMalloc(&ctx->stage, bytes);
+    if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(staging)");
+    ctx->stage_bytes = bytes;
+    return BVH_CUDA_OK;
+}
+
 namespace {
+
+// Carves the context's staging arena for one host-pointer call.
+struct Stage {
+    bvh_cuda_ctx* ctx;
+    size_t sizes[8];
+    int n = 0;
+    explicit Stage(bvh_cuda_ctx* c) : ctx(c) {}
+    int add(size_t bytes) { sizes[n] = (bytes + 255) & ~(size_t)255; return n++; }
+    int commit() {
+        size_t tot = 0;
+        for (int i = 0; i < n; ++i) tot += sizes[i];
+        return ctx_stage_reserve(ctx, tot ? tot : 256);
+    }
+    template <class T> T* ptr(int i) const {
+        size_t off = 0;
+        for (int k = 0; k < i; ++k) off += sizes[k];
+        return reinterpret_cast<T*>((char*)ctx->stage + off);
+    }
+};
 
 // RAII device staging buffer for the host-pointer entry points
 struct DevBuf {
@@ -88,6 +118,9 @@ int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
         return BVH_CUDA_ECUDA;
     }
     ctx->t2_blocks_per_sm = blas_t2_occupancy();
+    ctx->t2w_blocks_per_sm = blas_t2w_occupancy();
+    ctx->t1_blocks_per_sm = blas_t1_coop_occupancy();
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
     *out = ctx;
     return BVH_CUDA_OK;
 }
@@ -96,6 +129,8 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -104,6 +139,12 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    ctx->profiling = enable != 0;
+    return BVH_CUDA_OK;
+}
 
 // ---- BLAS ------------------------------------------------------------------------------------------
 int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
@@ -122,17 +163,21 @@ int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_verti
     if (nodes_cap < 2 * n_tris) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: nodes_cap must be >= 2*n_tris");
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->own_stream;
-    DevBuf dv, di, dn;
-    CU_CHECK(ctx, dv.alloc(sizeof(float) * 3 * n_vertices));
-    CU_CHECK(ctx, di.alloc(sizeof(uint32_t) * 3 * n_tris));
-    CU_CHECK(ctx, dn.alloc(sizeof(BvhNode) * 2 * n_tris));
-    CU_CHECK(ctx, cudaMemcpyAsync(dv.p, vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(di.p, indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
+    Stage st(ctx);
+    const int iv = st.add(sizeof(float) * 3 * n_vertices), ii = st.add(sizeof(uint32_t) * 3 * n_tris),
+              in = st.add(sizeof(BvhNode) * 2 * n_tris);
+    int rc = st.commit();
+    if (rc) return rc;
+    float* dv = st.ptr<float>(iv);
+    uint32_t* di = st.ptr<uint32_t>(ii);
+    BvhNode* dn = st.ptr<BvhNode>(in);
+    CU_CHECK(ctx, cudaMemcpyAsync(dv, vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(di, indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
     uint32_t m = 0;
-    int rc = blas_build_device(ctx, dv.as<float>(), n_vertices, di.as<uint32_t>(), n_tris, dn.as<BvhNode>(), 2 * n_tris, &m, s);
+    rc = blas_build_device(ctx, dv, n_vertices, di, n_tris, dn, 2 * n_tris, &m, s);
     if (rc) { cudaStreamSynchronize(s); return rc; }
-    CU_CHECK(ctx, cudaMemcpyAsync(nodes_out, dn.p, sizeof(BvhNode) * m, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(indices, di.p, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(nodes_out, dn, sizeof(BvhNode) * m, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(indices, di, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     if (n_nodes_out) *n_nodes_out = m;
     return BVH_CUDA_OK;
@@ -317,20 +362,23 @@ int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const
     if (n_rays == 0) return BVH_CUDA_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->own_stream;
-    DevBuf dro, drd, dt, dtri, dinst;
-    CU_CHECK(ctx, dro.alloc(sizeof(float) * 3 * n_rays));
-    CU_CHECK(ctx, drd.alloc(sizeof(float) * 3 * n_rays));
-    CU_CHECK(ctx, dt.alloc(sizeof(float) * n_rays));
-    CU_CHECK(ctx, dtri.alloc(sizeof(uint32_t) * n_rays));
-    CU_CHECK(ctx, dinst.alloc(sizeof(uint32_t) * n_rays));
-    CU_CHECK(ctx, cudaMemcpyAsync(dro.p, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(drd.p, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    int rc = trace_scene_device(ctx, scene, dro.as<float>(), drd.as<float>(), n_rays, tmax, 0, dt.as<float>(), dtri.as<uint32_t>(),
-                                dinst.as<uint32_t>(), nullptr, s);
+    Stage st(ctx);
+    const int io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays),
+              it = st.add(sizeof(float) * n_rays), itr = st.add(sizeof(uint32_t) * n_rays), iin = st.add(sizeof(uint32_t) * n_rays);
+    int rc = st.commit();
     if (rc) return rc;
-    CU_CHECK(ctx, cudaMemcpyAsync(t_out, dt.p, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(tri_out, dtri.p, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(inst_out, dinst.p, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    float* dro = st.ptr<float>(io);
+    float* drd = st.ptr<float>(id);
+    float* dt = st.ptr<float>(it);
+    uint32_t* dtri = st.ptr<uint32_t>(itr);
+    uint32_t* dinst = st.ptr<uint32_t>(iin);
+    CU_CHECK(ctx, cudaMemcpyAsync(dro, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(drd, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    rc = trace_scene_device(ctx, scene, dro, drd, n_rays, tmax, 0, dt, dtri, dinst, nullptr, s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(t_out, dt, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(tri_out, dtri, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(inst_out, dinst, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     return BVH_CUDA_OK;
 }
@@ -342,16 +390,18 @@ int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     if (n_rays == 0) return BVH_CUDA_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t s = ctx->own_stream;
-    DevBuf dro, drd, docc;
-    CU_CHECK(ctx, dro.alloc(sizeof(float) * 3 * n_rays));
-    CU_CHECK(ctx, drd.alloc(sizeof(float) * 3 * n_rays));
-    CU_CHECK(ctx, docc.alloc(n_rays));
-    CU_CHECK(ctx, cudaMemcpyAsync(dro.p, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(drd.p, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    int rc = trace_scene_device(ctx, scene, dro.as<float>(), drd.as<float>(), n_rays, tmax, 1, nullptr, nullptr, nullptr,
-                                docc.as<uint8_t>(), s);
+    Stage st(ctx);
+    const int io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays), ic = st.add(n_rays);
+    int rc = st.commit();
     if (rc) return rc;
-    CU_CHECK(ctx, cudaMemcpyAsync(occluded_out, docc.p, n_rays, cudaMemcpyDeviceToHost, s));
+    float* dro = st.ptr<float>(io);
+    float* drd = st.ptr<float>(id);
+    uint8_t* docc = st.ptr<uint8_t>(ic);
+    CU_CHECK(ctx, cudaMemcpyAsync(dro, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(drd, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    rc = trace_scene_device(ctx, scene, dro, drd, n_rays, tmax, 1, nullptr, nullptr, nullptr, docc, s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(occluded_out, docc, n_rays, cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     return BVH_CUDA_OK;
 }

@@ -17,9 +17,13 @@
 // with one prefix sum over N counters, and a final kernel emits the 32-byte BvhNodes.
 #include "common.cuh"
 
+#include <cstdlib>
+#include <atomic>
+
 namespace {
 
 constexpr int T3_MAX = 32;
+constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
 constexpr int T2_CAP = 2048;
 constexpr int T2_THREADS = 256;
 constexpr int T1_TILE = 2048;
@@ -39,7 +43,8 @@ struct LevelNode {  // 32 B
 
 struct NodeScratch {
     uint32_t bnd[12];  // ordered-uint: vlo[3], vhi[3], cmin[3], cmax[3]
-    uint32_t nL, f, best, pad;
+    uint32_t nL[22], f[22];  // per shuffle: #L in the node, #front-examined
+    uint32_t best, pad;
     uint32_t piv[21], uid[21];
     uint32_t bins[3][8][6];
 };
@@ -50,10 +55,14 @@ struct BuildState {
     uint32_t t3_count;
     uint32_t lv_count[2];
     uint32_t lv_tiles[2];
+    uint32_t lv_maxtiles[2];
     uint32_t interior_total;
     unsigned long long sum_interior;
     uint32_t t2_done;
-    uint32_t pad[3];
+    uint32_t w_head, w_tail, w_pending;
+    uint32_t t2w_done;
+    uint32_t levels_done;
+    uint32_t pad[2];
 };
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -285,39 +294,73 @@ __global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint
 // T2: one block per node (33..CAP primitives), tasks from a device queue; children go back to the
 // queue (> 32) or to the T3 list.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void push_child(Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, BuildState* st,
-                                           uint32_t epoch, uint32_t start, uint32_t n, uint32_t leftrun,
-                                           uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
+struct Queues {
+    Task* q;    // block-per-node tasks (T2W_CAP < n <= T2_CAP)
+    Task* qw;   // warp-per-node tasks  (T3_MAX < n <= T2W_CAP)
+    Task* t3;   // warp-per-sub-tree tasks (n <= T3_MAX)
+    uint32_t q_cap, qw_cap, t3_cap;
+};
+
+__device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint32_t epoch, uint32_t start, uint32_t n,
+                                           uint32_t leftrun, uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
     if (n > T3_MAX) {
-        atomicAdd(&st->q_pending, 1u);
-        const uint32_t idx = atomicAdd(&st->q_tail, 1u);
-        if (idx >= q_cap) {
+        const bool big = n > T2W_CAP;
+        uint32_t* pending = big ? &st->q_pending : &st->w_pending;
+        uint32_t* tail = big ? &st->q_tail : &st->w_tail;
+        const uint32_t cap = big ? Q.q_cap : Q.qw_cap;
+        atomicAdd(pending, 1u);
+        const uint32_t idx = atomicAdd(tail, 1u);
+        if (idx >= cap) {
             atomicOr(&st->err, DERR_QUEUE);
-            atomicSub(&st->q_pending, 1u);
+            atomicSub(pending, 1u);
             return;
         }
-        Task* d = q + idx;
+        Task* d = (big ? Q.q : Q.qw) + idx;
         d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
         d->flags = flags; d->pad = 0;
         __threadfence();
         *(volatile uint32_t*)&d->ready = epoch;
     } else {
         const uint32_t idx = atomicAdd(&st->t3_count, 1u);
-        if (idx >= t3_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
-        Task* d = t3 + idx;
+        if (idx >= Q.t3_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
+        Task* d = Q.t3 + idx;
         d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
         d->flags = flags; d->ready = epoch; d->pad = 0;
     }
 }
 
+// Pop one task from a device queue (called by one thread per consumer).  Ticket scheme: every consumer takes
+// the next slot number with one atomicAdd (no CAS retries under contention) and then waits for that slot to be
+// published, or for the queue to drain: `pending` counts tasks pushed but not yet finished, and a finished task
+// has already pushed its children, so pending == 0 with the ticket still unpublished means no task will ever
+// land in it.  Returns false when the queue has drained.
+__device__ __forceinline__ bool queue_pop(Task* q, uint32_t cap, uint32_t* head, uint32_t* tail, uint32_t* pending,
+                                          BuildState* st, uint32_t epoch, uint32_t* out_idx) {
+    (void)tail;
+    const uint32_t idx = atomicAdd(head, 1u);
+    *out_idx = idx;
+    if (idx >= cap) return false;
+    uint32_t ns = 32;
+    for (uint32_t spins = 0;; ++spins) {
+        if (ld_vol(&q[idx].ready) == epoch) { __threadfence(); return true; }
+        if (ld_vol(pending) == 0) {
+            // re-check: the producer publishes the slot before it decrements `pending`
+            if (ld_vol(&q[idx].ready) == epoch) { __threadfence(); return true; }
+            return false;
+        }
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+        if (spins > SPIN_LIMIT) { atomicOr(&st->err, DERR_QUEUE); return false; }
+    }
+}
+
 template <int CAP, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, uint32_t* ids,
-                                                const float4* __restrict__ cent,
+__global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
                                                 const float4* __restrict__ box, uint4* recs, uint32_t* A,
                                                 BuildState* st, uint32_t epoch) {
     constexpr int NW = THREADS / 32;
     constexpr int EPT = CAP / THREADS;
-    constexpr int CHUNK = 32 * EPT;
+    Task* const q = Q.q;
     __shared__ uint32_t s_pay[2][CAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
     __shared__ uint32_t s_gid[CAP];
     __shared__ uint16_t s_tab[CAP];
@@ -339,38 +382,23 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
     for (;;) {
         // ---- pop ----
         if (tid == 0) {
-            int have = 0;
             uint32_t idx = 0;
-            for (uint32_t spins = 0;;) {
-                const uint32_t h = ld_vol(&st->q_head), tl = ld_vol(&st->q_tail);
-                if (h < tl && h < q_cap) {
-                    if (atomicCAS(&st->q_head, h, h + 1) == h) { idx = h; have = 1; break; }
-                    continue;
-                }
-                if (ld_vol(&st->q_pending) == 0) break;
-                __nanosleep(100);
-                if (++spins > SPIN_LIMIT) { atomicOr(&st->err, DERR_QUEUE); break; }
-            }
+            const bool have = queue_pop(q, Q.q_cap, &st->q_head, &st->q_tail, &st->q_pending, st, epoch, &idx);
             if (have) {
-                uint32_t spins = 0;
-                while (ld_vol(&q[idx].ready) != epoch) {
-                    __nanosleep(50);
-                    if (++spins > SPIN_LIMIT) { atomicOr(&st->err, DERR_QUEUE); have = 0; break; }
-                }
-                __threadfence();
-                if (have) {
-                    const volatile Task* vq = q + idx;
-                    s_task.start = vq->start; s_task.n = vq->n; s_task.leftrun = vq->leftrun;
-                    s_task.pstart = vq->pstart; s_task.pleftrun = vq->pleftrun; s_task.flags = vq->flags;
-                }
+                const volatile Task* vq = q + idx;
+                s_task.start = vq->start; s_task.n = vq->n; s_task.leftrun = vq->leftrun;
+                s_task.pstart = vq->pstart; s_task.pleftrun = vq->pleftrun; s_task.flags = vq->flags;
             }
-            s_have = have;
+            s_have = have ? 1 : 0;
             s_f = 0;
         }
         __syncthreads();
         if (!s_have) break;
         const Task t = s_task;
         const uint32_t n = t.n, start = t.start;
+        // balanced layout: every warp owns E*32 consecutive slots, E = ceil(n / THREADS) <= EPT
+        const uint32_t E = (n + THREADS - 1) / THREADS;
+        const uint32_t CHUNK = 32 * E;
 
         // ---- 1. load, own vertex box, centroid bounds ----
         float ccx[EPT], ccy[EPT], ccz[EPT];
@@ -380,7 +408,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
             for (int i = 0; i < EPT; ++i) {
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
                 ccx[i] = ccy[i] = ccz[i] = 0.0f;
-                if (j < n) {
+                if (i < (int)E && j < n) {
                     const uint32_t g = __ldcg(&ids[start + j]);
                     s_gid[j] = g;
                     const float4 c = cent[g];
@@ -417,7 +445,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = warp * CHUNK + i * 32 + lane;
-            if (j < n) {
+            if (i < (int)E && j < n) {
                 const uint32_t kb = plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax);
                 s_k[j] = (uint16_t)kb;
                 s_pay[0][j] = j | (kb << 16);
@@ -432,10 +460,14 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
             uint32_t cnt = 0;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
-                const uint32_t j = warp * CHUNK + i * 32 + lane;
-                const bool L = (j < n) && (((s_pay[cur][j] >> sh) & 7u) < b);
-                bal[i] = __ballot_sync(FULL_MASK, L);
-                cnt += __popc(bal[i]);
+                bal[i] = 0;
+                LFv[i] = 0;
+                if (i < (int)E) {
+                    const uint32_t j = warp * CHUNK + i * 32 + lane;
+                    const bool L = (j < n) && (((s_pay[cur][j] >> sh) & 7u) < b);
+                    bal[i] = __ballot_sync(FULL_MASK, L);
+                    cnt += __popc(bal[i]);
+                }
             }
             if (lane == 0) s_wtot[warp] = cnt;
             __syncthreads();  // S1
@@ -449,6 +481,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
             uint32_t running = wpre, predc = 0;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
+                if (i >= (int)E) break;
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
                 const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
@@ -458,7 +491,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
                     const uint32_t RF = j - LF;
                     uint32_t Lnext;
                     if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                    else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
+                    else if (i + 1 < (int)E) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
                     else Lnext = (j + 1 < n) ? ((((s_pay[cur][j + 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
                     const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
                     pred = (j + 2 <= n) && (LBB >= RF);
@@ -476,7 +509,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
-                if (j < n) {
+                if (i < (int)E && j < n) {
                     uint32_t pay = s_pay[cur][j];
                     const uint32_t Lbit = (bal[i] >> lane) & 1u;
                     const uint32_t LF = LFv[i], RF = j - LF;
@@ -507,7 +540,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
                 kk[i] = 0xFFFFFFFFu;
                 lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
                 hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
-                if (j < n) {
+                if (i < (int)E && j < n) {
                     const uint32_t pay = s_pay[cur][j];
                     if (!(pay & 0x80000000u)) {
                         const uint32_t g = s_gid[pay & 0xFFFFu];
@@ -601,7 +634,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = warp * CHUNK + i * 32 + lane;
-            if (j < n) ids[start + j] = s_gid[s_pay[cur][j] & 0xFFFFu];
+            if (i < (int)E && j < n) ids[start + j] = s_gid[s_pay[cur][j] & 0xFFFFu];
         }
         __threadfence();
         __syncthreads();
@@ -615,13 +648,278 @@ __global__ void __launch_bounds__(THREADS) k_t2(Task* q, uint32_t q_cap, Task* t
             }
             emit_rec(recs, 2 * (start + p) + 1, lo, hi, start, n, t.leftrun, t.pstart, t.pleftrun, t.flags);
             if (p <= 3) A[start] = t.leftrun + 1;
-            push_child(q, q_cap, t3, t3_cap, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, 0);
-            push_child(q, q_cap, t3, t3_cap, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT);
+            push_child(Q, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, 0);
+            push_child(Q, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT);
             atomicAdd(&st->t2_done, 1u);
             __threadfence();
             atomicSub(&st->q_pending, 1u);
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T2w: one WARP per node (33..WCAP primitives), tasks from a second device queue.  Same algorithm as k_t2,
+// but warp-synchronous: ballots and popcounts replace the block scan, bins and specials live in registers
+// (lane a*8+k owns bin (a,k); lane c owns candidate c and special c).  No block barriers.
+// ------------------------------------------------------------------------------------------------
+template <int WCAP>
+__global__ void __launch_bounds__(256) k_t2w(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
+                                             const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st,
+                                             uint32_t epoch) {
+    constexpr int EPL = WCAP / 32;
+    constexpr int NWB = 8;
+    __shared__ uint32_t s_pay[NWB][2][WCAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
+    __shared__ uint32_t s_gid[NWB][WCAP];
+    __shared__ uint16_t s_tab[NWB][WCAP];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        // ---- pop (lane 0) ----
+        uint32_t have = 0, t_start = 0, t_n = 0, t_leftrun = 0, t_pstart = 0, t_pleftrun = 0, t_flags = 0;
+        if (lane == 0) {
+            uint32_t idx = 0;
+            if (queue_pop(Q.qw, Q.qw_cap, &st->w_head, &st->w_tail, &st->w_pending, st, epoch, &idx)) {
+                const volatile Task* vq = Q.qw + idx;
+                t_start = vq->start; t_n = vq->n; t_leftrun = vq->leftrun; t_pstart = vq->pstart;
+                t_pleftrun = vq->pleftrun; t_flags = vq->flags;
+                have = 1;
+            }
+        }
+        have = __shfl_sync(FULL_MASK, have, 0);
+        if (!have) break;
+        const uint32_t start = __shfl_sync(FULL_MASK, t_start, 0), n = __shfl_sync(FULL_MASK, t_n, 0);
+        const uint32_t leftrun = __shfl_sync(FULL_MASK, t_leftrun, 0), pstart = __shfl_sync(FULL_MASK, t_pstart, 0);
+        const uint32_t pleftrun = __shfl_sync(FULL_MASK, t_pleftrun, 0), tflags = __shfl_sync(FULL_MASK, t_flags, 0);
+        const uint32_t E = (n + 31) >> 5;  // chunks in use, <= EPL
+
+        // ---- 1. load, own vertex box, centroid bounds ----
+        float ccx[EPL], ccy[EPL], ccz[EPL];
+        float nlo[3], nhi[3], cmin[3], cmax[3];
+        {
+            float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const uint32_t j = i * 32 + lane;
+                ccx[i] = ccy[i] = ccz[i] = 0.0f;
+                if (i < (int)E && j < n) {
+                    const uint32_t g = __ldcg(&ids[start + j]);
+                    s_gid[w][j] = g;
+                    const float4 c = cent[g];
+                    const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                    ccx[i] = c.x; ccy[i] = c.y; ccz[i] = c.z;
+                    acc[0] = fminf(acc[0], b0.x); acc[1] = fminf(acc[1], b0.y); acc[2] = fminf(acc[2], b0.z);
+                    acc[3] = fmaxf(acc[3], b1.x); acc[4] = fmaxf(acc[4], b1.y); acc[5] = fmaxf(acc[5], b1.z);
+                    acc[6] = fminf(acc[6], c.x); acc[7] = fminf(acc[7], c.y); acc[8] = fminf(acc[8], c.z);
+                    acc[9] = fmaxf(acc[9], c.x); acc[10] = fmaxf(acc[10], c.y); acc[11] = fmaxf(acc[11], c.z);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                nlo[k] = o2f(min(__reduce_min_sync(FULL_MASK, f2o(acc[k])), ENC_POS_INIT));
+                nhi[k] = o2f(max(__reduce_max_sync(FULL_MASK, f2o(acc[3 + k])), ENC_NEG_INIT));
+                cmin[k] = o2f(min(__reduce_min_sync(FULL_MASK, f2o(acc[6 + k])), ENC_POS_INIT));
+                cmax[k] = o2f(max(__reduce_max_sync(FULL_MASK, f2o(acc[9 + k])), ENC_NEG_INIT));
+            }
+        }
+        // ---- 2. plane counts ----
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const uint32_t j = i * 32 + lane;
+            if (i < (int)E && j < n) s_pay[w][0][j] = j | (plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax) << 16);
+        }
+        __syncwarp();
+
+        // ---- 3. shuffles ----
+        uint32_t last_up = 0;
+        auto shuffle = [&](int cur, uint32_t a, uint32_t b) -> uint32_t {
+            const uint32_t sh = 16 + 3 * a;
+            uint32_t bal[EPL], LFv[EPL];
+            uint32_t nL = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                bal[i] = 0;
+                LFv[i] = 0;
+                if (i < (int)E) {
+                    const uint32_t j = i * 32 + lane;
+                    const bool L = (j < n) && (((s_pay[w][cur][j] >> sh) & 7u) < b);
+                    bal[i] = __ballot_sync(FULL_MASK, L);
+                    nL += __popc(bal[i]);
+                }
+            }
+            uint32_t running = 0, f = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                if (i >= (int)E) break;
+                const uint32_t j = i * 32 + lane;
+                const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                const uint32_t LF = running + __popc(bal[i] & lt_mask);
+                LFv[i] = LF;
+                bool pred = false;
+                if (j < n) {
+                    const uint32_t RF = j - LF;
+                    uint32_t Lnext;
+                    if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
+                    else Lnext = (i + 1 < (int)E) ? (bal[(i + 1 < EPL) ? i + 1 : i] & 1u) : 0u;
+                    const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
+                    pred = (j + 2 <= n) && (LBB >= RF);
+                    if (Lbit) s_tab[w][n - 1 - (nL - LF - 1)] = (uint16_t)j;
+                    else s_tab[w][RF] = (uint16_t)j;
+                }
+                f += __popc(__ballot_sync(FULL_MASK, pred));
+                running += __popc(bal[i]);
+            }
+            __syncwarp();
+            uint32_t Lf = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                if ((uint32_t)i == (f >> 5)) Lf = (bal[i] >> (f & 31u)) & 1u;
+            const uint32_t pivot = nL - Lf;
+            uint32_t upay = 0;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const uint32_t j = i * 32 + lane;
+                if (i < (int)E && j < n) {
+                    uint32_t pay = s_pay[w][cur][j];
+                    const uint32_t Lbit = (bal[i] >> lane) & 1u;
+                    const uint32_t LF = LFv[i], RF = j - LF;
+                    uint32_t dest;
+                    if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[w][n - RF] - 1u);
+                    else if (j == f) { dest = pivot; pay |= 0x80000000u; upay = pay; }
+                    else dest = Lbit ? (uint32_t)s_tab[w][nL - LF - 1] : j - 1;
+                    s_pay[w][cur ^ 1][dest] = pay;
+                }
+            }
+            __syncwarp();
+            last_up = __shfl_sync(FULL_MASK, upay, f & 31u);  // payload of the unexamined element
+            return pivot;
+        };
+
+        int cur = 0;
+        uint32_t my_u = 0xFFFFFFFFu, my_kb = 0, my_piv = 0;
+        for (uint32_t c = 0; c < 21; ++c) {
+            const uint32_t pivot = shuffle(cur, c / 7, c % 7 + 1);
+            cur ^= 1;
+            if (lane == c) { my_u = last_up & 0xFFFFu; my_kb = (last_up >> 16) & 0x1FFu; my_piv = pivot; }
+        }
+
+        // ---- 4. exact bins over the non-special primitives; lane a*8+k keeps bin (a,k) ----
+        float mybin[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+        {
+            float lo[EPL][3], hi[EPL][3];
+            uint32_t kk[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const uint32_t j = i * 32 + lane;
+                kk[i] = 0xFFFFFFFFu;
+                lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
+                hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
+                if (i < (int)E && j < n) {
+                    const uint32_t pay = s_pay[w][cur][j];
+                    if (!(pay & 0x80000000u)) {
+                        const uint32_t g = s_gid[w][pay & 0xFFFFu];
+                        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                        lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
+                        hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
+                        kk[i] = (pay >> 16) & 0x1FFu;
+                    }
+                }
+            }
+            for (uint32_t a = 0; a < 3; ++a) {
+                for (uint32_t k = 0; k < 8; ++k) {
+                    float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                    bool any = false;
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) {
+                        const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
+                        if (in) {
+                            any = true;
+                            m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
+                            m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                        }
+                    }
+                    if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const uint32_t v = f2o(m[c]);
+                        const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                        if (lane == a * 8 + k) mybin[c] = o2f(r);
+                    }
+                }
+            }
+        }
+        // ---- 5. candidate costs and selection ----
+        float ub[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};  // box of special `lane`
+        if (lane < 21) {
+            const uint32_t g = s_gid[w][my_u];
+            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+            ub[0] = b0.x; ub[1] = b0.y; ub[2] = b0.z; ub[3] = b1.x; ub[4] = b1.y; ub[5] = b1.z;
+        }
+        const uint32_t ca = (lane < 21) ? lane / 7 : 0, cb = lane % 7 + 1;
+        float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+        float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            float v[6];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) v[x] = __shfl_sync(FULL_MASK, mybin[x], ca * 8 + k);
+            if (k < cb) {
+                Lb[0] = fminf(Lb[0], v[0]); Lb[1] = fminf(Lb[1], v[1]); Lb[2] = fminf(Lb[2], v[2]);
+                Lb[3] = fmaxf(Lb[3], v[3]); Lb[4] = fmaxf(Lb[4], v[4]); Lb[5] = fmaxf(Lb[5], v[5]);
+            } else {
+                Rb[0] = fminf(Rb[0], v[0]); Rb[1] = fminf(Rb[1], v[1]); Rb[2] = fminf(Rb[2], v[2]);
+                Rb[3] = fmaxf(Rb[3], v[3]); Rb[4] = fmaxf(Rb[4], v[4]); Rb[5] = fmaxf(Rb[5], v[5]);
+            }
+        }
+        for (uint32_t s2 = 0; s2 < 21; ++s2) {
+            const uint32_t u2 = __shfl_sync(FULL_MASK, my_u, s2), kb2 = __shfl_sync(FULL_MASK, my_kb, s2);
+            float v[6];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) v[x] = __shfl_sync(FULL_MASK, ub[x], s2);
+            const bool left = (u2 != my_u) && (((kb2 >> (3 * ca)) & 7u) < cb);
+            if (left) {
+                Lb[0] = fminf(Lb[0], v[0]); Lb[1] = fminf(Lb[1], v[1]); Lb[2] = fminf(Lb[2], v[2]);
+                Lb[3] = fmaxf(Lb[3], v[3]); Lb[4] = fmaxf(Lb[4], v[4]); Lb[5] = fmaxf(Lb[5], v[5]);
+            } else {
+                Rb[0] = fminf(Rb[0], v[0]); Rb[1] = fminf(Rb[1], v[1]); Rb[2] = fminf(Rb[2], v[2]);
+                Rb[3] = fmaxf(Rb[3], v[3]); Rb[4] = fmaxf(Rb[4], v[4]); Rb[5] = fmaxf(Rb[5], v[5]);
+            }
+        }
+        const float cost = sah_cost(Lb, Rb, my_piv, n - my_piv);
+        const uint32_t key = (lane < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
+        const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
+        if (mk == 0xFFFFFFFFu) {
+            if (lane == 0) {
+                atomicOr(&st->err, DERR_DEGENERATE);
+                atomicSub(&st->w_pending, 1u);
+            }
+            __syncwarp();
+            continue;
+        }
+        const uint32_t win = __ffs(__ballot_sync(FULL_MASK, key == mk)) - 1;
+        const uint32_t p = __shfl_sync(FULL_MASK, my_piv, win);
+        // ---- 6. final shuffle (blas.rs:164), write the order back ----
+        shuffle(cur, win / 7, win % 7 + 1);
+        cur ^= 1;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const uint32_t j = i * 32 + lane;
+            if (i < (int)E && j < n) ids[start + j] = s_gid[w][s_pay[w][cur][j] & 0xFFFFu];
+        }
+        __threadfence();
+        __syncwarp();
+        // ---- 7. record + children ----
+        if (lane == 0) {
+            emit_rec(recs, 2 * (start + p) + 1, nlo, nhi, start, n, leftrun, pstart, pleftrun, tflags);
+            if (p <= 3) A[start] = leftrun + 1;
+            push_child(Q, st, epoch, start, p, leftrun + 1, start, leftrun, 0);
+            push_child(Q, st, epoch, start + p, n - p, 0, start, leftrun, TF_RIGHT);
+            atomicAdd(&st->t2w_done, 1u);
+            __threadfence();
+            atomicSub(&st->w_pending, 1u);
+        }
+        __syncwarp();
     }
 }
 
@@ -632,46 +930,64 @@ struct T1Args {
     const LevelNode* nodes;
     NodeScratch* sc;
     uint32_t n_nodes, n_tiles;
-    uint32_t* ids[2];
-    uint16_t* flags[2];
+    uint32_t* ids0;
+    uint32_t* ids1;
+    uint16_t* fl0;
+    uint16_t* fl1;
     uint32_t* table;
-    uint32_t* tileL;
-    uint32_t* tileLF;
+    uint32_t* tileL;     // [22][tile_stride] per-candidate L count of every tile (current order at that shuffle)
+    uint32_t* tileLF;    // [tile_stride] #L in the node before this tile, for the shuffle in flight
+    uint32_t* tile_node; // [tile_stride] tile -> level node
+    uint32_t tile_stride;
     const float4* cent;
     const float4* box;
     BuildState* st;
+    uint32_t* barrier;   // monotonically increasing arrival counter
 };
 
-__device__ __forceinline__ uint32_t find_node(const LevelNode* nodes, uint32_t n_nodes, uint32_t tile) {
-    uint32_t lo = 0, hi = n_nodes;  // last node with tile_base <= tile
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (nodes[mid].tile_base <= tile) lo = mid; else hi = mid;
+// Grid-wide barrier for the cooperative (co-resident) persistent kernel: one arrival counter that only ever
+// grows, so there is no reset race; generation g completes when it reaches g * gridDim.x.
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gen += 1;
+        const uint32_t target = gen * gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_vol(counter) < target) { }
+        __threadfence();
     }
-    return lo;
+    __syncthreads();
 }
 
 __device__ __forceinline__ void cand_of(const NodeScratch* sc, uint32_t node, int cand, uint32_t& a, uint32_t& b) {
-    const uint32_t c = (cand >= 0) ? (uint32_t)cand : sc[node].best;
+    const uint32_t c = (cand < 21) ? (uint32_t)cand : sc[node].best;
     a = c / 7; b = c % 7 + 1;
 }
 
-__global__ void __launch_bounds__(256) k_t1_init(T1Args g) {
+// L0: per node — scratch init, tile -> node map, zero the per-candidate tile counters of the node's tiles.
+__device__ __forceinline__ void p_t1_init(const T1Args& g) {
     for (uint32_t node = blockIdx.x; node < g.n_nodes; node += gridDim.x) {
         NodeScratch* s = g.sc + node;
+        const LevelNode nd = g.nodes[node];
+        const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
         const uint32_t tid = threadIdx.x;
         if (tid < 12) s->bnd[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
-        if (tid == 12) { s->nL = 0; s->f = 0; s->best = 0xFFFFFFFFu; }
+        if (tid < 22) { s->nL[tid] = 0; s->f[tid] = 0; }
+        if (tid == 22) s->best = 0xFFFFFFFFu;
         if (tid < 144) (&s->bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+        for (uint32_t t = tid; t < nt; t += blockDim.x) g.tile_node[nd.tile_base + t] = node;
+        for (uint32_t k = tid; k < 22 * nt; k += blockDim.x) g.tileL[(size_t)(k / nt) * g.tile_stride + nd.tile_base + (k % nt)] = 0;
     }
 }
 
-__global__ void __launch_bounds__(T1_THREADS) k_t1_bounds(T1Args g) {
+// L1: per tile — vertex box and centroid bounds of the node (blas.rs:87-88,117-123,142).
+__device__ __forceinline__ void p_t1_bounds(const T1Args& g) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_red[T1_THREADS / 32][12];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const uint32_t node = g.tile_node[tile];
         const LevelNode nd = g.nodes[node];
         const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
         float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
@@ -679,7 +995,7 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_bounds(T1Args g) {
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = j0 + i * T1_THREADS + tid;
             if (j < nd.n) {
-                const uint32_t id = g.ids[0][nd.start + j];
+                const uint32_t id = g.ids0[nd.start + j];
                 const float4 c = g.cent[id];
                 const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
                 acc[0] = fminf(acc[0], b0.x); acc[1] = fminf(acc[1], b0.y); acc[2] = fminf(acc[2], b0.z);
@@ -707,43 +1023,29 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_bounds(T1Args g) {
     }
 }
 
-__global__ void __launch_bounds__(T1_THREADS) k_t1_flags(T1Args g) {
+// L2: per tile — plane counts of every primitive, and the tile's L count for candidate 0 (x axis, b = 1).
+__device__ __forceinline__ void p_t1_flags(const T1Args& g) {
     constexpr int EPT = T1_TILE / T1_THREADS;
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_w[T1_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const uint32_t node = g.tile_node[tile];
         const LevelNode nd = g.nodes[node];
         const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
         float cmin[3], cmax[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { cmin[c] = o2f(g.sc[node].bnd[6 + c]); cmax[c] = o2f(g.sc[node].bnd[9 + c]); }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = j0 + i * T1_THREADS + tid;
-            if (j < nd.n) {
-                const float4 c = g.cent[g.ids[0][nd.start + j]];
-                g.flags[0][nd.start + j] = (uint16_t)plane_counts(c.x, c.y, c.z, cmin, cmax);
-            }
-        }
-    }
-}
-
-// Per-tile L count of the current order for one candidate.
-__global__ void __launch_bounds__(T1_THREADS) k_t1_count(T1Args g, int cur, int cand) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
-    __shared__ uint32_t s_w[T1_THREADS / 32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
-        uint32_t a, b;
-        cand_of(g.sc, node, cand, a, b);
         uint32_t cnt = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = j0 + i * T1_THREADS + tid;
-            const bool L = (j < nd.n) && ((((uint32_t)g.flags[cur][nd.start + j] >> (3 * a)) & 7u) < b);
+            bool L = false;
+            if (j < nd.n) {
+                const float4 c = g.cent[g.ids0[nd.start + j]];
+                const uint32_t kb = plane_counts(c.x, c.y, c.z, cmin, cmax);
+                g.fl0[nd.start + j] = (uint16_t)kb;
+                L = (kb & 7u) < 1u;
+            }
             cnt += __popc(__ballot_sync(FULL_MASK, L));
         }
         if (lane == 0) s_w[warp] = cnt;
@@ -751,23 +1053,53 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_count(T1Args g, int cur, int 
         if (tid == 0) {
             uint32_t tot = 0;
             for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) tot += s_w[w2];
-            g.tileL[tile] = tot;
+            g.tileL[tile] = tot;  // candidate 0
         }
         __syncthreads();
     }
 }
 
-// One warp per node: exclusive scan of its tiles' L counts.
-__global__ void __launch_bounds__(256) k_t1_tilescan(T1Args g) {
+// Per-tile L count for the final (winning) candidate, whose identity is only known after select.
+__device__ __forceinline__ void p_t1_count_final(const T1Args& g, const uint16_t* fl) {
+    constexpr int EPT = T1_TILE / T1_THREADS;
+    __shared__ uint32_t s_w[T1_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        const uint32_t node = g.tile_node[tile];
+        const LevelNode nd = g.nodes[node];
+        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        uint32_t a, b;
+        cand_of(g.sc, node, 21, a, b);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + i * T1_THREADS + tid;
+            const bool L = (j < nd.n) && ((((uint32_t)fl[nd.start + j] >> (3 * a)) & 7u) < b);
+            cnt += __popc(__ballot_sync(FULL_MASK, L));
+        }
+        if (lane == 0) s_w[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) tot += s_w[w2];
+            g.tileL[(size_t)21 * g.tile_stride + tile] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// Optional (levels whose nodes span many tiles): one warp per node scans its tiles' L counts for shuffle c.
+__device__ __forceinline__ void p_t1_tilescan(const T1Args& g, int c) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t node = gw; node < g.n_nodes; node += nw) {
         const LevelNode nd = g.nodes[node];
         const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
         uint32_t carry = 0;
         for (uint32_t base = 0; base < nt; base += 32) {
             const uint32_t i = base + lane;
-            const uint32_t v = (i < nt) ? g.tileL[nd.tile_base + i] : 0;
+            const uint32_t v = (i < nt) ? tl[nd.tile_base + i] : 0;
             uint32_t x = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -777,22 +1109,22 @@ __global__ void __launch_bounds__(256) k_t1_tilescan(T1Args g) {
             if (i < nt) g.tileLF[nd.tile_base + i] = carry + x - v;
             carry += __shfl_sync(FULL_MASK, x, 31);
         }
-        if (lane == 0) { g.sc[node].nL = carry; g.sc[node].f = 0; }
+        if (lane == 0) g.sc[node].nL[c] = carry;
     }
 }
 
-// Shared by table and scatter: per-element #L before it (LF) inside the node, via tile prefix + ballots.
-// Element layout inside a tile: j = j0 + warp*256 + i*32 + lane (a warp owns 256 consecutive slots).
+// Ballots + per-element #L-before (LF) of one tile.  Layout: j = j0 + warp*256 + i*32 + lane.
 template <int EPT>
 __device__ __forceinline__ void t1_prefix(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint32_t a,
-                                          uint32_t b, uint32_t tile_lf, uint32_t* s_w, uint32_t* bal,
-                                          uint32_t* LFv) {
+                                          uint32_t b, uint32_t tile_lf, uint32_t* s_w, uint32_t* bal, uint32_t* LFv,
+                                          uint16_t* fw) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cnt = 0;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
         const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
-        const bool L = (j < n) && ((((uint32_t)fl[start + j] >> (3 * a)) & 7u) < b);
+        fw[i] = (j < n) ? fl[start + j] : (uint16_t)0;
+        const bool L = (j < n) && ((((uint32_t)fw[i] >> (3 * a)) & 7u) < b);
         bal[i] = __ballot_sync(FULL_MASK, L);
         cnt += __popc(bal[i]);
     }
@@ -809,22 +1141,48 @@ __device__ __forceinline__ void t1_prefix(const uint16_t* fl, uint32_t start, ui
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(T1_THREADS) k_t1_table(T1Args g, int cur, int cand) {
+// PA(c): per tile — tile prefix, rank->position table (Appendix B), count of front-examined elements.
+__device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_t* fl, bool scanned) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
-    __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_cnt, s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const uint32_t node = g.tile_node[tile];
         const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint32_t lt = tile - nd.tile_base, j0 = lt * T1_TILE;
         uint32_t a, b;
-        cand_of(g.sc, node, cand, a, b);
-        const uint32_t nL = g.sc[node].nL;
-        const uint16_t* fl = g.flags[cur];
+        cand_of(g.sc, node, c, a, b);
+        uint32_t tile_lf, nL;
+        if (scanned) {
+            tile_lf = g.tileLF[tile];
+            nL = g.sc[node].nL[c];
+            if (tid == 0) s_cnt = 0;
+        } else {
+            const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
+            uint32_t pre = 0, tot = 0;
+            for (uint32_t t = tid; t < nt; t += T1_THREADS) {
+                const uint32_t v = tl[nd.tile_base + t];
+                tot += v;
+                if (t < lt) pre += v;
+            }
+            pre = __reduce_add_sync(FULL_MASK, pre);
+            tot = __reduce_add_sync(FULL_MASK, tot);
+            if (lane == 0) { s_pre[warp] = pre; s_tot[warp] = tot; }
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            tile_lf = 0; nL = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) { tile_lf += s_pre[w2]; nL += s_tot[w2]; }
+            if (tid == 0) {
+                g.tileLF[tile] = tile_lf;
+                if (lt == 0) g.sc[node].nL[c] = nL;
+            }
+        }
         uint32_t bal[EPT], LFv[EPT];
-        if (tid == 0) s_cnt = 0;
-        t1_prefix<EPT>(fl, nd.start, nd.n, j0, a, b, g.tileLF[tile], s_w, bal, LFv);
+        uint16_t fw[EPT];
+        t1_prefix<EPT>(fl, nd.start, nd.n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
         uint32_t predc = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -846,55 +1204,77 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_table(T1Args g, int cur, int 
         }
         if (lane == 0 && predc) atomicAdd(&s_cnt, predc);
         __syncthreads();
-        if (tid == 0 && s_cnt) atomicAdd(&g.sc[node].f, s_cnt);
+        if (tid == 0 && s_cnt) atomicAdd(&g.sc[node].f[c], s_cnt);
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(T1_THREADS) k_t1_scatter(T1Args g, int cur, int cand, int cidx) {
+// PB(c): per tile — destinations and scatter into the other buffer; also accumulates, per destination tile,
+// the L count of the NEXT candidate (so shuffle c+1 needs no separate counting pass).
+__device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint32_t* ids_in, const uint16_t* fl,
+                                             uint32_t* ids_out, uint16_t* fl_out) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool count_next = c < 20;  // candidates 1..20 are known in advance; the final one is not
+    const uint32_t na = (uint32_t)(c + 1) / 7, nb = (uint32_t)(c + 1) % 7 + 1;
+    uint32_t* tl_next = g.tileL + (size_t)(c + 1) * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const uint32_t node = g.tile_node[tile];
         const LevelNode nd = g.nodes[node];
         const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
         uint32_t a, b;
-        cand_of(g.sc, node, cand, a, b);
-        const uint32_t nL = g.sc[node].nL, f = g.sc[node].f, n = nd.n;
-        const uint16_t* fl = g.flags[cur];
+        cand_of(g.sc, node, c, a, b);
+        const uint32_t nL = g.sc[node].nL[c], f = g.sc[node].f[c], n = nd.n;
         const uint32_t Lf = ((((uint32_t)fl[nd.start + f] >> (3 * a)) & 7u) < b) ? 1u : 0u;
         const uint32_t pivot = nL - Lf;
         uint32_t bal[EPT], LFv[EPT];
-        t1_prefix<EPT>(fl, nd.start, n, j0, a, b, g.tileLF[tile], s_w, bal, LFv);
+        uint16_t fwv[EPT];
+        t1_prefix<EPT>(fl, nd.start, n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            uint32_t dtile = 0xFFFFFFFFu;
+            bool Lnx = false;
             if (j < n) {
                 const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = LFv[i], RF = j - LF;
-                const uint32_t id = g.ids[cur][nd.start + j];
-                uint32_t fw = fl[nd.start + j];
+                const uint32_t id = ids_in[nd.start + j];
+                uint32_t fw = fwv[i];
                 uint32_t dest;
                 if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : g.table[nd.start + n - RF] - 1u);
                 else if (j == f) {
                     dest = pivot;
                     fw |= 0x8000u;
-                    if (cidx >= 0) { g.sc[node].piv[cidx] = pivot; g.sc[node].uid[cidx] = id; }
+                    if (c < 21) { g.sc[node].piv[c] = pivot; g.sc[node].uid[c] = id; }
                 } else dest = Lbit ? g.table[nd.start + (nL - LF - 1)] : j - 1;
-                g.ids[cur ^ 1][nd.start + dest] = id;
-                g.flags[cur ^ 1][nd.start + dest] = (uint16_t)fw;
+                ids_out[nd.start + dest] = id;
+                fl_out[nd.start + dest] = (uint16_t)fw;
+                dtile = nd.tile_base + dest / T1_TILE;
+                Lnx = ((fw >> (3 * na)) & 7u) < nb;
+            }
+            if (count_next) {
+                // warp-aggregated: destinations of 32 consecutive slots fall into very few tiles
+                uint32_t todo = __ballot_sync(FULL_MASK, dtile != 0xFFFFFFFFu);
+                while (todo) {
+                    const uint32_t leader = __ffs(todo) - 1;
+                    const uint32_t lt = __shfl_sync(FULL_MASK, dtile, leader);
+                    const uint32_t same = __ballot_sync(FULL_MASK, dtile == lt);
+                    const uint32_t cnt = __popc(__ballot_sync(FULL_MASK, dtile == lt && Lnx));
+                    if (lane == leader && cnt) atomicAdd(&tl_next[lt], cnt);
+                    todo &= ~same;
+                }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(T1_THREADS) k_t1_bins(T1Args g, int cur) {
+__device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, const uint16_t* fl) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_bins[3][8][6];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = find_node(g.nodes, g.n_nodes, tile);
+        const uint32_t node = g.tile_node[tile];
         const LevelNode nd = g.nodes[node];
         const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
         if (tid < 144) (&s_bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
@@ -908,9 +1288,9 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_bins(T1Args g, int cur) {
             lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
             hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
             if (j < nd.n) {
-                const uint32_t fw = g.flags[cur][nd.start + j];
+                const uint32_t fw = fl[nd.start + j];
                 if (!(fw & 0x8000u)) {
-                    const uint32_t id = g.ids[cur][nd.start + j];
+                    const uint32_t id = ids[nd.start + j];
                     const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
                     lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
                     hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
@@ -955,7 +1335,7 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_bins(T1Args g, int cur) {
 }
 
 // One warp per node: evaluate the 21 candidates from bins + specials, pick the winner (blas.rs:155-161).
-__global__ void __launch_bounds__(256) k_t1_select(T1Args g) {
+__device__ __forceinline__ void p_t1_select(const T1Args& g) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t node = gw; node < g.n_nodes; node += nw) {
@@ -966,8 +1346,7 @@ __global__ void __launch_bounds__(256) k_t1_select(T1Args g) {
         for (int c = 0; c < 3; ++c) { cmin[c] = o2f(s->bnd[6 + c]); cmax[c] = o2f(s->bnd[9 + c]); }
         const uint32_t c = lane;
         const uint32_t cs = (c < 21) ? c : 0;
-        // lane c also owns special c
-        const uint32_t my_uid = s->uid[cs];
+        const uint32_t my_uid = s->uid[cs];  // lane c also owns special c
         const float4 ce = g.cent[my_uid];
         const float4 b0 = g.box[2 * (size_t)my_uid], b1 = g.box[2 * (size_t)my_uid + 1];
         const uint32_t my_kb = plane_counts(ce.x, ce.y, ce.z, cmin, cmax);
@@ -1011,60 +1390,122 @@ __global__ void __launch_bounds__(256) k_t1_select(T1Args g) {
     }
 }
 
-// One thread per node: record, A counter, children to the next level / T2 queue / T3 list.
-__global__ void __launch_bounds__(256) k_t1_children(T1Args g, LevelNode* next_nodes, uint32_t next_cap, int next_slot,
-                                                     Task* q, uint32_t q_cap, Task* t3, uint32_t t3_cap, uint4* recs,
-                                                     uint32_t* A, uint32_t epoch) {
-    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= g.n_nodes) return;
-    const LevelNode nd = g.nodes[node];
-    const NodeScratch* s = g.sc + node;
-    const uint32_t p = s->piv[s->best];
-    float lo[3], hi[3];
-    for (int c = 0; c < 3; ++c) { lo[c] = o2f(min(s->bnd[c], ENC_POS_INIT)); hi[c] = o2f(max(s->bnd[3 + c], ENC_NEG_INIT)); }
-    if (p == 0 || p >= nd.n) { atomicOr(&g.st->err, DERR_DEGENERATE); return; }
-    emit_rec(recs, 2 * (nd.start + p) + 1, lo, hi, nd.start, nd.n, nd.leftrun, nd.pstart, nd.pleftrun, nd.flags);
-    if (p <= 3) A[nd.start] = nd.leftrun + 1;
-    for (int side = 0; side < 2; ++side) {
-        const uint32_t cs = side ? nd.start + p : nd.start;
-        const uint32_t cn = side ? nd.n - p : p;
-        const uint32_t clr = side ? 0 : nd.leftrun + 1;
-        const uint32_t cfl = side ? TF_RIGHT : 0;
-        if (cn > T2_CAP) {
-            const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
-            if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
-            LevelNode c;
-            c.start = cs; c.n = cn; c.leftrun = clr; c.pstart = nd.start; c.pleftrun = nd.leftrun; c.flags = cfl;
-            c.tile_base = 0; c.pad = 0;
-            next_nodes[idx] = c;
-        } else {
-            push_child(q, q_cap, t3, t3_cap, g.st, epoch, cs, cn, clr, nd.start, nd.leftrun, cfl);
+// One thread per node: record, A counter, children to the next level / block queue / warp queue / T3 list.
+__device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_nodes, uint32_t next_cap, int next_slot,
+                                              const Queues& Q, uint4* recs, uint32_t* A, uint32_t epoch) {
+    for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < g.n_nodes; node += gridDim.x * blockDim.x) {
+        const LevelNode nd = g.nodes[node];
+        const NodeScratch* s = g.sc + node;
+        const uint32_t p = s->piv[s->best];
+        float lo[3], hi[3];
+        for (int c = 0; c < 3; ++c) { lo[c] = o2f(min(s->bnd[c], ENC_POS_INIT)); hi[c] = o2f(max(s->bnd[3 + c], ENC_NEG_INIT)); }
+        if (p == 0 || p >= nd.n) { atomicOr(&g.st->err, DERR_DEGENERATE); continue; }
+        emit_rec(recs, 2 * (nd.start + p) + 1, lo, hi, nd.start, nd.n, nd.leftrun, nd.pstart, nd.pleftrun, nd.flags);
+        if (p <= 3) A[nd.start] = nd.leftrun + 1;
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t cs = side ? nd.start + p : nd.start;
+            const uint32_t cn = side ? nd.n - p : p;
+            const uint32_t clr = side ? 0 : nd.leftrun + 1;
+            const uint32_t cfl = side ? TF_RIGHT : 0;
+            if (cn > T2_CAP) {
+                const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
+                if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
+                LevelNode c;
+                c.start = cs; c.n = cn; c.leftrun = clr; c.pstart = nd.start; c.pleftrun = nd.leftrun; c.flags = cfl;
+                c.tile_base = 0; c.pad = 0;
+                next_nodes[idx] = c;
+            } else {
+                push_child(Q, g.st, epoch, cs, cn, clr, nd.start, nd.leftrun, cfl);
+            }
         }
     }
 }
 
-// Single block: tile_base prefix of the next level's node list.
-__global__ void __launch_bounds__(1024) k_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other) {
+// One block: tile_base prefix of the next level's node list; decides whether the level needs the tile scan.
+__device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other) {
     __shared__ uint32_t s_part[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n = st->lv_count[slot];
-    const uint32_t per = (n + 1023) / 1024;
-    const uint32_t b = tid * per, e = min(n, b + per);
-    uint32_t sum = 0;
-    for (uint32_t i = b; i < e; ++i) sum += (nodes[i].n + T1_TILE - 1) / T1_TILE;
+    __shared__ uint32_t s_max;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t n = ld_vol(&st->lv_count[slot]);
+    const uint32_t per = (n + nt - 1) / nt;
+    const uint32_t b = min(n, tid * per), e = min(n, b + per);
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    uint32_t sum = 0, mx = 0;
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t t = (nodes[i].n + T1_TILE - 1) / T1_TILE;
+        sum += t;
+        mx = max(mx, t);
+    }
     s_part[tid] = sum;
+    if (mx) atomicMax(&s_max, mx);
     __syncthreads();
     if (tid == 0) {
         uint32_t acc = 0;
-        for (int i = 0; i < 1024; ++i) { const uint32_t v = s_part[i]; s_part[i] = acc; acc += v; }
+        for (uint32_t i = 0; i < nt; ++i) { const uint32_t v = s_part[i]; s_part[i] = acc; acc += v; }
         st->lv_tiles[slot] = acc;
+        st->lv_maxtiles[slot] = s_max;
         st->lv_count[other] = 0;
+        st->levels_done += 1;
     }
     __syncthreads();
     uint32_t acc = s_part[tid];
     for (uint32_t i = b; i < e; ++i) {
         nodes[i].tile_base = acc;
         acc += (nodes[i].n + T1_TILE - 1) / T1_TILE;
+    }
+    __syncthreads();
+}
+
+// The whole grid-wide tier as ONE cooperative persistent kernel: every phase boundary is a grid barrier
+// instead of a kernel launch, and the level loop never returns to the host.  ~52 barriers per level.
+__global__ void __launch_bounds__(T1_THREADS) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
+                                                        uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
+    LevelNode* lv[2] = {lv0, lv1};
+    uint32_t gen = 0;
+    int slot = 0;
+    for (uint32_t level = 0; level < max_levels; ++level) {
+        const uint32_t n_nodes = ld_vol(&g.st->lv_count[slot]);
+        const uint32_t n_tiles = ld_vol(&g.st->lv_tiles[slot]);
+        const bool scanned = ld_vol(&g.st->lv_maxtiles[slot]) > 512u;
+        if (n_nodes == 0) break;
+        g.nodes = lv[slot];
+        g.n_nodes = n_nodes;
+        g.n_tiles = n_tiles;
+        p_t1_init(g);
+        grid_barrier(g.barrier, gen);
+        p_t1_bounds(g);
+        grid_barrier(g.barrier, gen);
+        p_t1_flags(g);
+        grid_barrier(g.barrier, gen);
+        for (int c = 0; c < 22; ++c) {
+            const uint32_t* ids_in = (c & 1) ? g.ids1 : g.ids0;
+            uint32_t* ids_out = (c & 1) ? g.ids0 : g.ids1;
+            const uint16_t* fl_in = (c & 1) ? g.fl1 : g.fl0;
+            uint16_t* fl_out = (c & 1) ? g.fl0 : g.fl1;
+            if (c == 21) {
+                p_t1_bins(g, ids_in, fl_in);
+                grid_barrier(g.barrier, gen);
+                p_t1_select(g);
+                grid_barrier(g.barrier, gen);
+                p_t1_count_final(g, fl_in);
+                grid_barrier(g.barrier, gen);
+            }
+            if (scanned) {
+                p_t1_tilescan(g, c);
+                grid_barrier(g.barrier, gen);
+            }
+            p_t1_table(g, c, fl_in, scanned);
+            grid_barrier(g.barrier, gen);
+            p_t1_scatter(g, c, ids_in, fl_in, ids_out, fl_out);
+            grid_barrier(g.barrier, gen);
+        }
+        const int next = slot ^ 1;
+        p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch);
+        grid_barrier(g.barrier, gen);
+        if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot);
+        grid_barrier(g.barrier, gen);
+        slot = next;
     }
 }
 
@@ -1192,8 +1633,8 @@ __global__ void __launch_bounds__(256) k_permute_gather(const uint32_t* __restri
     tmp[3 * (size_t)i + 2] = I[s + 2];
 }
 
-__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_q, Task* first_t3, LevelNode* first_lv,
-                                                    uint32_t N, uint32_t epoch) {
+__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_q, Task* first_qw, Task* first_t3,
+                                                    LevelNode* first_lv, uint32_t N, uint32_t epoch) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     BuildState s{};
     Task root{};
@@ -1205,10 +1646,15 @@ __global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_
         first_lv[0] = l;
         s.lv_count[0] = 1;
         s.lv_tiles[0] = (N + T1_TILE - 1) / T1_TILE;
-    } else if (N > T3_MAX) {
+        s.lv_maxtiles[0] = s.lv_tiles[0];
+    } else if (N > T2W_CAP) {
         first_q[0] = root;
         s.q_tail = 1;
         s.q_pending = 1;
+    } else if (N > T3_MAX) {
+        first_qw[0] = root;
+        s.w_tail = 1;
+        s.w_pending = 1;
     } else {
         first_t3[0] = root;
         s.t3_count = 1;
@@ -1221,6 +1667,18 @@ __global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_
 int blas_t2_occupancy() {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2<T2_CAP, T2_THREADS>, T2_THREADS, 0) != cudaSuccess) occ = 1;
+    return occ < 1 ? 1 : occ;
+}
+
+int blas_t1_coop_occupancy() {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop, T1_THREADS, 0) != cudaSuccess) occ = 1;
+    return occ < 1 ? 1 : occ;
+}
+
+int blas_t2w_occupancy() {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2w<T2W_CAP>, 256, 0) != cudaSuccess) occ = 1;
     return occ < 1 ? 1 : occ;
 }
 
@@ -1252,18 +1710,19 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t N = (uint32_t)n_tris;
     const uint32_t max_large = N / T2_CAP + 2;
     const uint32_t max_tiles = N / T1_TILE + max_large + 2;
-    const uint32_t q_cap = N / 4 + 4096;
+    const uint32_t q_cap = N / 32 + 4096;   // nodes with > T2W_CAP primitives (typically ~N/100)
+    const uint32_t qw_cap = N / 4 + 4096;   // nodes with 33..T2W_CAP primitives (typically ~N/28)
     const uint32_t t3_cap = N + 16;
     const uint32_t scan_n = N + 1;
     const uint32_t scan_blocks = (scan_n + SCAN_TILE - 1) / SCAN_TILE;
 
     // carve the workspace (first pass sizes, second pass assigns)
     float4 *cent = nullptr, *box = nullptr;
-    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr,
+    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr, *tile_node = nullptr, *barrier = nullptr,
              *scan_sums = nullptr, *scan_total = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *q = nullptr, *t3 = nullptr;
+    Task *q = nullptr, *qw = nullptr, *t3 = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -1280,12 +1739,15 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         A = c.take<uint32_t>(scan_n);
         recs = c.take<uint4>(3 * 2 * (size_t)N);
         q = c.take<Task>(q_cap);
+        qw = c.take<Task>(qw_cap);
         t3 = c.take<Task>(t3_cap);
         lv[0] = c.take<LevelNode>(max_large);
         lv[1] = c.take<LevelNode>(max_large);
         sc = c.take<NodeScratch>(max_large);
-        tileL = c.take<uint32_t>(max_tiles);
+        tileL = c.take<uint32_t>(22 * (size_t)max_tiles);
         tileLF = c.take<uint32_t>(max_tiles);
+        tile_node = c.take<uint32_t>(max_tiles);
+        barrier = c.take<uint32_t>(64);
         scan_sums = c.take<uint32_t>(scan_blocks + 1);
         scan_total = c.take<uint32_t>(4);
         if (pass == 0) {
@@ -1293,77 +1755,68 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
             if (rc) return rc;
         }
     }
-    ctx->epoch++;
-    const uint32_t epoch = ctx->epoch;
+    // Task slots are marked ready with a build-unique number so queues never need clearing; the counter is
+    // process-wide because a freed workspace of one context can be handed to another by cudaMalloc.
+    static std::atomic<uint32_t> g_epoch{0x1000};
+    const uint32_t epoch = g_epoch.fetch_add(1) + 1;
+    ctx->epoch = epoch;
     uint32_t launches = 0;
     BvhCudaBuildStats stats{};
 
     CU_CHECK(ctx, cudaMemsetAsync(A, 0, sizeof(uint32_t) * scan_n, stream));
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
-    k_init_state<<<1, 32, 0, stream>>>(st, q, t3, lv[0], N, epoch);
+    const bool prof = ctx->profiling;
+    if (prof) cudaEventRecord(ctx->ev[0], stream);
+    Queues Q{q, qw, t3, q_cap, qw_cap, t3_cap};
+    k_init_state<<<1, 32, 0, stream>>>(st, q, qw, t3, lv[0], N, epoch);
     k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, cent, box, ids0, st);
     launches += 2;
+    if (prof) cudaEventRecord(ctx->ev[1], stream);
 
-    // ---- T1: level-synchronous grid-wide phases ----
+    // ---- T1: grid-wide tier, one cooperative persistent launch ----
     if (N > (uint32_t)T2_CAP) {
-        int slot = 0;
-        uint32_t n_nodes = 1, n_tiles = (N + T1_TILE - 1) / T1_TILE;
-        const uint32_t max_grid = (uint32_t)ctx->sm_count * 16;
-        while (n_nodes > 0) {
-            T1Args g;
-            g.nodes = lv[slot]; g.sc = sc; g.n_nodes = n_nodes; g.n_tiles = n_tiles;
-            g.ids[0] = ids0; g.ids[1] = ids1; g.flags[0] = fl0; g.flags[1] = fl1;
-            g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.cent = cent; g.box = box; g.st = st;
-            const uint32_t grid_t = n_tiles < max_grid ? n_tiles : max_grid;
-            const uint32_t grid_w = (n_nodes + 7) / 8 < max_grid ? (n_nodes + 7) / 8 : max_grid;
-            k_t1_init<<<n_nodes < max_grid ? n_nodes : max_grid, 256, 0, stream>>>(g);
-            k_t1_bounds<<<grid_t, T1_THREADS, 0, stream>>>(g);
-            k_t1_flags<<<grid_t, T1_THREADS, 0, stream>>>(g);
-            launches += 3;
-            int cur = 0;
-            for (int c = 0; c < 22; ++c) {
-                const int cand = (c < 21) ? c : -1;
-                if (c == 21) {
-                    k_t1_bins<<<grid_t, T1_THREADS, 0, stream>>>(g, cur);
-                    k_t1_select<<<grid_w, 256, 0, stream>>>(g);
-                    launches += 2;
-                }
-                k_t1_count<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand);
-                k_t1_tilescan<<<grid_w, 256, 0, stream>>>(g);
-                k_t1_table<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand);
-                k_t1_scatter<<<grid_t, T1_THREADS, 0, stream>>>(g, cur, cand, cand);
-                launches += 4;
-                cur ^= 1;
-            }
-            const int next = slot ^ 1;
-            k_t1_children<<<(n_nodes + 255) / 256, 256, 0, stream>>>(g, lv[next], max_large, next, q, q_cap, t3, t3_cap,
-                                                                       recs, A, epoch);
-            k_t1_nextlevel<<<1, 1024, 0, stream>>>(lv[next], st, next, slot);
-            launches += 2;
-            CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
-            CU_CHECK(ctx, cudaStreamSynchronize(stream));
-            const BuildState* hs = reinterpret_cast<const BuildState*>(ctx->h_pin);
-            stats.grid_levels++;
-            if (hs->err) break;
-            n_nodes = hs->lv_count[next];
-            n_tiles = hs->lv_tiles[next];
-            slot = next;
-            if (stats.grid_levels > 4096) return ctx_fail(ctx, BVH_CUDA_EDEGENERATE, "blas_build: runaway level count");
-        }
+        CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, 256, stream));
+        T1Args g;
+        g.nodes = lv[0]; g.sc = sc; g.n_nodes = 0; g.n_tiles = 0;
+        g.ids0 = ids0; g.ids1 = ids1; g.fl0 = fl0; g.fl1 = fl1;
+        g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.tile_node = tile_node; g.tile_stride = max_tiles;
+        g.cent = cent; g.box = box; g.st = st; g.barrier = barrier;
+        LevelNode* lv0 = lv[0];
+        LevelNode* lv1 = lv[1];
+        uint32_t lv_cap = max_large, ep = epoch, max_levels = 4096;
+        uint4* recs_p = recs;
+        uint32_t* A_p = A;
+        void* args[] = {&g, &lv0, &lv1, &lv_cap, &Q, &recs_p, &A_p, &ep, &max_levels};
+        const uint32_t tiles0 = (N + T1_TILE - 1) / T1_TILE;
+        uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)(ctx->t1_blocks_per_sm > 0 ? ctx->t1_blocks_per_sm : 1);
+        const uint32_t want = tiles0 + 8;  // more blocks than tiles only lengthen the barriers
+        if (grid > want) grid = want;
+        CU_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_t1_coop, dim3(grid), dim3(T1_THREADS), args, 0, stream));
+        launches += 1;
     }
 
+    if (prof) cudaEventRecord(ctx->ev[2], stream);
     // ---- T2: persistent blocks on the device task queue ----
     {
         const int blocks = ctx->sm_count * (ctx->t2_blocks_per_sm > 0 ? ctx->t2_blocks_per_sm : 1);
-        k_t2<T2_CAP, T2_THREADS><<<blocks, T2_THREADS, 0, stream>>>(q, q_cap, t3, t3_cap, ids0, cent, box, recs, A, st, epoch);
+        k_t2<T2_CAP, T2_THREADS><<<blocks, T2_THREADS, 0, stream>>>(Q, ids0, cent, box, recs, A, st, epoch);
         launches++;
     }
+    if (prof) cudaEventRecord(ctx->ev[6], stream);
+    // ---- T2w: persistent warps on the second task queue ----
+    {
+        const int blocks = ctx->sm_count * (ctx->t2w_blocks_per_sm > 0 ? ctx->t2w_blocks_per_sm : 1);
+        k_t2w<T2W_CAP><<<blocks, 256, 0, stream>>>(Q, ids0, cent, box, recs, A, st, epoch);
+        launches++;
+    }
+    if (prof) cudaEventRecord(ctx->ev[3], stream);
     // ---- T3: one warp per small sub-tree ----
     {
         const int blocks = ctx->sm_count * 8;
         k_t3<<<blocks, 256, 0, stream>>>(t3, ids0, cent, box, recs, A, st);
         launches++;
     }
+    if (prof) cudaEventRecord(ctx->ev[4], stream);
     // ---- numbering + emit ----
     k_scan_reduce<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
     k_scan_top<<<1, 1024, 0, stream>>>(scan_sums, scan_blocks, scan_total);
@@ -1374,6 +1827,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     k_permute_gather<<<(N + 255) / 256, 256, 0, stream>>>(d_indices, ids0, N, tmp);
     CU_CHECK(ctx, cudaMemcpyAsync(d_indices, tmp, sizeof(uint32_t) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, stream));
     launches += 5;
+    if (prof) cudaEventRecord(ctx->ev[5], stream);
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaStreamSynchronize(stream));
@@ -1390,9 +1844,20 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.interior_nodes = interior;
     stats.n_nodes = 2 + 2 * interior;
     stats.sum_interior_prims = hs->sum_interior;
+    stats.grid_levels = hs->levels_done;
     stats.block_tasks = hs->t2_done;
+    stats.warp_node_tasks = hs->t2w_done;
     stats.warp_tasks = hs->t3_count;
     stats.kernel_launches = launches;
+    if (prof) {
+        cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&stats.ms_grid, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&stats.ms_block, ctx->ev[2], ctx->ev[6]);
+        cudaEventElapsedTime(&stats.ms_warp_node, ctx->ev[6], ctx->ev[3]);
+        cudaEventElapsedTime(&stats.ms_warp, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&stats.ms_emit, ctx->ev[4], ctx->ev[5]);
+        cudaEventElapsedTime(&stats.ms_total, ctx->ev[0], ctx->ev[5]);
+    }
     ctx->stats = stats;
     if (n_nodes_out) *n_nodes_out = stats.n_nodes;
     if (hs->interior_total != interior) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: internal node count mismatch");

@@ -34,6 +34,14 @@ struct bvh_cuda_ctx {
     size_t last_n = 0;
     uint32_t epoch = 0;
     int t2_blocks_per_sm = 0;
+    int t2w_blocks_per_sm = 0;
+    int t1_blocks_per_sm = 0;
+    // host-API staging arena (grow-only, so repeated host calls do not cudaMalloc)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // optional per-phase timing
+    bool profiling = false;
+    cudaEvent_t ev[8] = {};
 };
 
 struct bvh_cuda_scene {
@@ -45,6 +53,7 @@ struct bvh_cuda_scene {
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what);
 int ctx_cuda_fail(bvh_cuda_ctx* ctx, cudaError_t e, const char* where);
 int ctx_reserve(bvh_cuda_ctx* ctx, size_t bytes);
+int ctx_stage_reserve(bvh_cuda_ctx* ctx, size_t bytes);
 
 #define CU_CHECK(ctx, call)                                          \
     do {                                                             \
