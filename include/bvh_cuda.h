@@ -79,21 +79,21 @@ typedef struct BvhCudaBuildStats {
     uint64_t sum_interior_prims; /* S: sum over interior nodes of their triangle count */
     uint32_t n_nodes;            /* M = 2 + 2 * interior nodes */
     uint32_t interior_nodes;
-    uint32_t grid_levels;        /* levels handled by the grid-wide tier (nodes > 2048 triangles) */
+    uint32_t grid_levels;        /* levels handled by the grid-wide tier (nodes > 16384 triangles) */
+    uint32_t big_block_tasks;    /* nodes handled by one 1024-thread block each (2049..16384) */
     uint32_t block_tasks;        /* nodes handled one block each from the device task queue (257..2048) */
     uint32_t warp_node_tasks;    /* nodes handled one warp each from the second task queue (33..256) */
     uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each */
     uint32_t kernel_launches;    /* kernels launched by this build */
-    uint32_t reserved;
     /* Device time per phase in ms (CUDA events on the build's stream); all zero unless profiling is enabled. */
     float ms_setup;              /* k_setup: centroids, triangle boxes */
     float ms_grid;               /* grid-wide tier, all levels */
-    float ms_block;              /* k_t2: block-per-node task-queue kernel (one launch) */
+    float ms_big_block;          /* k_t2<16384,1024>: big-block task-queue kernel (one launch) */
+    float ms_block;              /* k_t2<2048,256>: block-per-node task-queue kernel (one launch) */
     float ms_warp_node;          /* k_t2w: warp-per-node task-queue kernel (one launch) */
     float ms_warp;               /* k_t3: warp-per-sub-tree kernel (one launch) */
     float ms_emit;               /* numbering scan + node emit + index permutation */
     float ms_total;
-    float reserved_f;
 } BvhCudaBuildStats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */

@@ -30,7 +30,7 @@ def check_blas(name, v, idx):
     same_idx = (gi == oidx).all()
     stats = ctx.last_build_stats()
     print(f"[{name}] n={n} M={len(bvh.nodes)}/{len(onodes)} nodes_ok={same_nodes} idx_ok={same_idx} "
-          f"S={stats['sum_interior_prims']}/{st['sum_interior_prims']} levels={stats['grid_levels']} t2={stats['block_tasks']} t2w={stats['warp_node_tasks']} "
+          f"S={stats['sum_interior_prims']}/{st['sum_interior_prims']} levels={stats['grid_levels']} t2b={stats['big_block_tasks']} t2={stats['block_tasks']} t2w={stats['warp_node_tasks']} "
           f"t3={stats['warp_tasks']} launches={stats['kernel_launches']} e2e={dt*1e3:.2f}ms", flush=True)
     if not (same_nodes and same_idx):
         ok_all = False

@@ -1,0 +1,24 @@
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import voidin_b200 as vb
+from voidin_b200 import scenes as S
+dev = torch.device("cuda", 0)
+ctx = vb.Context(0); ctx.set_profiling(True)
+dv, di = S.dragon_class()
+d_v = torch.from_numpy(dv.reshape(-1)).to(dev); d_i0 = torch.from_numpy(di.view(np.int32)).to(dev)
+n = di.size // 3
+d_nodes = torch.zeros(2 * n * 8, dtype=torch.int32, device=dev)
+buf = (C.c_ulonglong * 32)()
+names = ["init", "bounds", "flags", "bins", "select", "count_final", "tilescan", "table", "scatter", "children", "nextlevel"]
+for k in range(3):
+    d_i = d_i0.clone(); torch.cuda.synchronize()
+    ctx.blas_build_dev(d_v.data_ptr(), dv.shape[0], d_i.data_ptr(), n, d_nodes.data_ptr(), 2 * n, 0)
+    st = ctx.last_build_stats()
+    ctx.lib.bvh_cuda_debug_t1_timing(buf)
+    print(f"build {k}: grid {st['ms_grid']:.3f} ms, levels {st['grid_levels']}")
+    tw = tb = 0
+    for i, nm in enumerate(names):
+        print(f"   {nm:12s} work {buf[2*i]/1e3:9.1f} us   barrier {buf[2*i+1]/1e3:9.1f} us")
+        tw += buf[2*i]; tb += buf[2*i+1]
+    print(f"   total work {tw/1e3:.1f} us, barrier {tb/1e3:.1f} us")

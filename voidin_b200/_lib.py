@@ -40,19 +40,19 @@ class BuildStats(C.Structure):
         ("n_nodes", C.c_uint32),
         ("interior_nodes", C.c_uint32),
         ("grid_levels", C.c_uint32),
+        ("big_block_tasks", C.c_uint32),
         ("block_tasks", C.c_uint32),
         ("warp_node_tasks", C.c_uint32),
         ("warp_tasks", C.c_uint32),
         ("kernel_launches", C.c_uint32),
-        ("reserved", C.c_uint32),
         ("ms_setup", C.c_float),
         ("ms_grid", C.c_float),
+        ("ms_big_block", C.c_float),
         ("ms_block", C.c_float),
         ("ms_warp_node", C.c_float),
         ("ms_warp", C.c_float),
         ("ms_emit", C.c_float),
         ("ms_total", C.c_float),
-        ("reserved_f", C.c_float),
     ]
 
     def as_dict(self):

@@ -8,8 +8,10 @@
 #include <new>
 
 int blas_t2_occupancy();
+int blas_t2b_setup();
 int blas_t2w_occupancy();
 int blas_t1_coop_occupancy();
+int blas_t1_timing(unsigned long long* out32);
 
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what) {
     if (ctx) ctx->err = what ? what : "";
@@ -118,6 +120,7 @@ int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
         return BVH_CUDA_ECUDA;
     }
     ctx->t2_blocks_per_sm = blas_t2_occupancy();
+    if (blas_t2b_setup() < 1) { bvh_cuda_destroy(ctx); return BVH_CUDA_ECUDA; }
     ctx->t2w_blocks_per_sm = blas_t2w_occupancy();
     ctx->t1_blocks_per_sm = blas_t1_coop_occupancy();
     for (auto& e : ctx->ev) cudaEventCreate(&e);
@@ -139,6 +142,9 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Debug only (library built with -DBVH_T1_TIMING): per-phase-kind work / barrier-wait ns of block 0 in the grid tier.
+int bvh_cuda_debug_t1_timing(unsigned long long* out32) { return blas_t1_timing(out32); }
 
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable) {
     if (!ctx) return BVH_CUDA_EINVAL;

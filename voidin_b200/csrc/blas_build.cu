@@ -24,8 +24,10 @@ namespace {
 
 constexpr int T3_MAX = 32;
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
-constexpr int T2_CAP = 2048;
+constexpr int T2_CAP = 2048;    // block-per-node tier: 257..2048 (256 threads)
 constexpr int T2_THREADS = 256;
+constexpr int T2B_CAP = 16384;  // big-block tier: 2049..16384 (1024 threads, one block per SM)
+constexpr int T2B_THREADS = 1024;
 constexpr int T1_TILE = 2048;
 constexpr int T1_THREADS = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
@@ -43,7 +45,8 @@ struct LevelNode {  // 32 B
 
 struct NodeScratch {
     uint32_t bnd[12];  // ordered-uint: vlo[3], vhi[3], cmin[3], cmax[3]
-    uint32_t nL[22], f[22];  // per shuffle: #L in the node, #front-examined
+    uint4 sh[22];      // per shuffle {nL, f, pivot, -}: written by the one thread that owns the boundary element
+    uint32_t nL[22];   // per shuffle #L of the node (tile-scan path only)
     uint32_t best, pad;
     uint32_t piv[21], uid[21];
     uint32_t bins[3][8][6];
@@ -60,6 +63,8 @@ struct BuildState {
     unsigned long long sum_interior;
     uint32_t t2_done;
     uint32_t w_head, w_tail, w_pending;
+    uint32_t b_head, b_tail, b_pending;
+    uint32_t t2b_done;
     uint32_t t2w_done;
     uint32_t levels_done;
     uint32_t pad[2];
@@ -295,19 +300,20 @@ __global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint
 // queue (> 32) or to the T3 list.
 // ------------------------------------------------------------------------------------------------
 struct Queues {
+    Task* qb;   // big-block tasks (T2_CAP < n <= T2B_CAP)
     Task* q;    // block-per-node tasks (T2W_CAP < n <= T2_CAP)
     Task* qw;   // warp-per-node tasks  (T3_MAX < n <= T2W_CAP)
     Task* t3;   // warp-per-sub-tree tasks (n <= T3_MAX)
-    uint32_t q_cap, qw_cap, t3_cap;
+    uint32_t qb_cap, q_cap, qw_cap, t3_cap;
 };
 
 __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint32_t epoch, uint32_t start, uint32_t n,
                                            uint32_t leftrun, uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
     if (n > T3_MAX) {
-        const bool big = n > T2W_CAP;
-        uint32_t* pending = big ? &st->q_pending : &st->w_pending;
-        uint32_t* tail = big ? &st->q_tail : &st->w_tail;
-        const uint32_t cap = big ? Q.q_cap : Q.qw_cap;
+        const int tier = n > T2_CAP ? 2 : (n > T2W_CAP ? 1 : 0);
+        uint32_t* pending = tier == 2 ? &st->b_pending : (tier == 1 ? &st->q_pending : &st->w_pending);
+        uint32_t* tail = tier == 2 ? &st->b_tail : (tier == 1 ? &st->q_tail : &st->w_tail);
+        const uint32_t cap = tier == 2 ? Q.qb_cap : (tier == 1 ? Q.q_cap : Q.qw_cap);
         atomicAdd(pending, 1u);
         const uint32_t idx = atomicAdd(tail, 1u);
         if (idx >= cap) {
@@ -315,7 +321,7 @@ __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint
             atomicSub(pending, 1u);
             return;
         }
-        Task* d = (big ? Q.q : Q.qw) + idx;
+        Task* d = (tier == 2 ? Q.qb : (tier == 1 ? Q.q : Q.qw)) + idx;
         d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
         d->flags = flags; d->pad = 0;
         __threadfence();
@@ -354,17 +360,23 @@ __device__ __forceinline__ bool queue_pop(Task* q, uint32_t cap, uint32_t* head,
     }
 }
 
-template <int CAP, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
-                                                const float4* __restrict__ box, uint4* recs, uint32_t* A,
-                                                BuildState* st, uint32_t epoch) {
+template <int CAP, int THREADS, bool BIG>
+__global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, uint32_t* ids_snap,
+                                                const float4* __restrict__ cent, const float4* __restrict__ box,
+                                                uint4* recs, uint32_t* A, BuildState* st, uint32_t epoch) {
     constexpr int NW = THREADS / 32;
     constexpr int EPT = CAP / THREADS;
-    Task* const q = Q.q;
-    __shared__ uint32_t s_pay[2][CAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
-    __shared__ uint32_t s_gid[CAP];
-    __shared__ uint16_t s_tab[CAP];
-    __shared__ uint16_t s_k[CAP];
+    Task* const q = BIG ? Q.qb : Q.q;
+    const uint32_t q_cap = BIG ? Q.qb_cap : Q.q_cap;
+    uint32_t* const q_head = BIG ? &st->b_head : &st->q_head;
+    uint32_t* const q_tail = BIG ? &st->b_tail : &st->q_tail;
+    uint32_t* const q_pending = BIG ? &st->b_pending : &st->q_pending;
+    // dynamic shared memory: payload ping-pong (bits 0-15 local primitive, 16-24 plane counts, 31 special) and the
+    // rank -> position table.  The local-primitive -> triangle-id map lives in global memory (ids_snap).
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* const s_pay0 = s_dyn;
+    uint32_t* const s_pay1 = s_dyn + CAP;
+    uint16_t* const s_tab = reinterpret_cast<uint16_t*>(s_dyn + 2 * CAP);
     __shared__ uint32_t s_wtot[NW];
     __shared__ uint32_t s_red[NW][12];
     __shared__ uint32_t s_node[12];
@@ -383,7 +395,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         // ---- pop ----
         if (tid == 0) {
             uint32_t idx = 0;
-            const bool have = queue_pop(q, Q.q_cap, &st->q_head, &st->q_tail, &st->q_pending, st, epoch, &idx);
+            const bool have = queue_pop(q, q_cap, q_head, q_tail, q_pending, st, epoch, &idx);
             if (have) {
                 const volatile Task* vq = q + idx;
                 s_task.start = vq->start; s_task.n = vq->n; s_task.leftrun = vq->leftrun;
@@ -400,20 +412,17 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         const uint32_t E = (n + THREADS - 1) / THREADS;
         const uint32_t CHUNK = 32 * E;
 
-        // ---- 1. load, own vertex box, centroid bounds ----
-        float ccx[EPT], ccy[EPT], ccz[EPT];
+        // ---- 1. snapshot the order, own vertex box, centroid bounds ----
         {
             float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-#pragma unroll
+#pragma unroll 4
             for (int i = 0; i < EPT; ++i) {
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
-                ccx[i] = ccy[i] = ccz[i] = 0.0f;
                 if (i < (int)E && j < n) {
                     const uint32_t g = __ldcg(&ids[start + j]);
-                    s_gid[j] = g;
+                    ids_snap[start + j] = g;
                     const float4 c = cent[g];
                     const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-                    ccx[i] = c.x; ccy[i] = c.y; ccz[i] = c.z;
                     acc[0] = fminf(acc[0], b0.x); acc[1] = fminf(acc[1], b0.y); acc[2] = fminf(acc[2], b0.z);
                     acc[3] = fmaxf(acc[3], b1.x); acc[4] = fmaxf(acc[4], b1.y); acc[5] = fmaxf(acc[5], b1.z);
                     acc[6] = fminf(acc[6], c.x); acc[7] = fminf(acc[7], c.y); acc[8] = fminf(acc[8], c.z);
@@ -439,32 +448,34 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         __syncthreads();
 
         // ---- 2. plane counts ----
-        float cmin[3], cmax[3];
+        {
+            float cmin[3], cmax[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { cmin[c] = o2f(s_node[6 + c]); cmax[c] = o2f(s_node[9 + c]); }
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = warp * CHUNK + i * 32 + lane;
-            if (i < (int)E && j < n) {
-                const uint32_t kb = plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax);
-                s_k[j] = (uint16_t)kb;
-                s_pay[0][j] = j | (kb << 16);
+            for (int c = 0; c < 3; ++c) { cmin[c] = o2f(s_node[6 + c]); cmax[c] = o2f(s_node[9 + c]); }
+#pragma unroll 4
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                if (i < (int)E && j < n) {
+                    const float4 c = cent[__ldcg(&ids_snap[start + j])];
+                    s_pay0[j] = j | (plane_counts(c.x, c.y, c.z, cmin, cmax) << 16);
+                }
             }
         }
         __syncthreads();
 
         // ---- 3. shuffles ----
         auto shuffle = [&](int cur, uint32_t a, uint32_t b, int cidx) {
+            const uint32_t* pin = cur ? s_pay1 : s_pay0;
+            uint32_t* pout = cur ? s_pay0 : s_pay1;
             const uint32_t sh = 16 + 3 * a;
-            uint32_t bal[EPT], LFv[EPT];
+            uint32_t bal[EPT];
             uint32_t cnt = 0;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 bal[i] = 0;
-                LFv[i] = 0;
                 if (i < (int)E) {
                     const uint32_t j = warp * CHUNK + i * 32 + lane;
-                    const bool L = (j < n) && (((s_pay[cur][j] >> sh) & 7u) < b);
+                    const bool L = (j < n) && (((pin[j] >> sh) & 7u) < b);
                     bal[i] = __ballot_sync(FULL_MASK, L);
                     cnt += __popc(bal[i]);
                 }
@@ -485,14 +496,13 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
                 const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
-                LFv[i] = LF;
                 bool pred = false;
                 if (j < n) {
                     const uint32_t RF = j - LF;
                     uint32_t Lnext;
                     if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
                     else if (i + 1 < (int)E) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
-                    else Lnext = (j + 1 < n) ? ((((s_pay[cur][j + 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
+                    else Lnext = (j + 1 < n) ? ((((pin[j + 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
                     const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
                     pred = (j + 2 <= n) && (LBB >= RF);
                     if (Lbit) s_tab[n - 1 - (nL - LF - 1)] = (uint16_t)j;
@@ -504,23 +514,27 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
             if (lane == 0 && predc) atomicAdd(&s_f, predc);
             __syncthreads();  // S2
             const uint32_t f = s_f;
-            const uint32_t Lf = (((s_pay[cur][f] >> sh) & 7u) < b) ? 1u : 0u;
+            const uint32_t Lf = (((pin[f] >> sh) & 7u) < b) ? 1u : 0u;
             const uint32_t pivot = nL - Lf;
+            running = wpre;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
+                if (i >= (int)E) break;
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
-                if (i < (int)E && j < n) {
-                    uint32_t pay = s_pay[cur][j];
+                const uint32_t LF = running + __popc(bal[i] & lt_mask);
+                running += __popc(bal[i]);
+                if (j < n) {
+                    uint32_t pay = pin[j];
                     const uint32_t Lbit = (bal[i] >> lane) & 1u;
-                    const uint32_t LF = LFv[i], RF = j - LF;
+                    const uint32_t RF = j - LF;
                     uint32_t dest;
                     if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[n - RF] - 1u);
                     else if (j == f) {
                         dest = pivot;
                         pay |= 0x80000000u;
-                        if (cidx >= 0) { s_u[cidx] = pay & 0xFFFFu; s_piv[cidx] = pivot; }
+                        if (cidx >= 0) { s_u[cidx] = pay & 0xFFFFu; s_uk[cidx] = (pay >> 16) & 0x1FFu; s_piv[cidx] = pivot; }
                     } else dest = Lbit ? (uint32_t)s_tab[nL - LF - 1] : j - 1;
-                    s_pay[cur ^ 1][dest] = pay;
+                    pout[dest] = pay;
                 }
             }
             __syncthreads();  // S3
@@ -530,60 +544,62 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         int cur = 0;
         for (uint32_t c = 0; c < 21; ++c) { shuffle(cur, c / 7, c % 7 + 1, (int)c); cur ^= 1; }
 
-        // ---- 4. exact bins over the non-special primitives ----
+        // ---- 4. exact bins over the non-special primitives (4 slots per thread at a time) ----
         {
-            float lo[EPT][3], hi[EPT][3];
-            uint32_t kk[EPT];
+            const uint32_t* pin = cur ? s_pay1 : s_pay0;
+            for (uint32_t i0 = 0; i0 < E; i0 += 4) {
+                float lo[4][3], hi[4][3];
+                uint32_t kk[4];
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) {
-                const uint32_t j = warp * CHUNK + i * 32 + lane;
-                kk[i] = 0xFFFFFFFFu;
-                lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
-                hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
-                if (i < (int)E && j < n) {
-                    const uint32_t pay = s_pay[cur][j];
-                    if (!(pay & 0x80000000u)) {
-                        const uint32_t g = s_gid[pay & 0xFFFFu];
-                        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-                        lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
-                        hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
-                        kk[i] = (pay >> 16) & 0x1FFu;
-                    }
-                }
-            }
-            for (uint32_t a = 0; a < 3; ++a) {
-                for (uint32_t k = 0; k < 8; ++k) {
-                    float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-                    bool any = false;
-#pragma unroll
-                    for (int i = 0; i < EPT; ++i) {
-                        const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
-                        if (in) {
-                            any = true;
-                            m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
-                            m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                for (int ii = 0; ii < 4; ++ii) {
+                    const uint32_t i = i0 + ii;
+                    const uint32_t j = warp * CHUNK + i * 32 + lane;
+                    kk[ii] = 0xFFFFFFFFu;
+                    lo[ii][0] = lo[ii][1] = lo[ii][2] = 1e30f;
+                    hi[ii][0] = hi[ii][1] = hi[ii][2] = -1e30f;
+                    if (i < E && j < n) {
+                        const uint32_t pay = pin[j];
+                        if (!(pay & 0x80000000u)) {
+                            const uint32_t g = __ldcg(&ids_snap[start + (pay & 0xFFFFu)]);
+                            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                            lo[ii][0] = b0.x; lo[ii][1] = b0.y; lo[ii][2] = b0.z;
+                            hi[ii][0] = b1.x; hi[ii][1] = b1.y; hi[ii][2] = b1.z;
+                            kk[ii] = (pay >> 16) & 0x1FFu;
                         }
                     }
-                    if (!__any_sync(FULL_MASK, any)) continue;
+                }
+                for (uint32_t a = 0; a < 3; ++a) {
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                        bool any = false;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        const uint32_t v = f2o(m[c]);
-                        const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
-                        if (lane == 0) {
-                            if (c < 3) atomicMin(&s_bins[a][k][c], r);
-                            else atomicMax(&s_bins[a][k][c], r);
+                        for (int ii = 0; ii < 4; ++ii) {
+                            const bool in = (kk[ii] != 0xFFFFFFFFu) && (((kk[ii] >> (3 * a)) & 7u) == k);
+                            if (in) {
+                                any = true;
+                                m[0] = fminf(m[0], lo[ii][0]); m[1] = fminf(m[1], lo[ii][1]); m[2] = fminf(m[2], lo[ii][2]);
+                                m[3] = fmaxf(m[3], hi[ii][0]); m[4] = fmaxf(m[4], hi[ii][1]); m[5] = fmaxf(m[5], hi[ii][2]);
+                            }
+                        }
+                        if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) {
+                            const uint32_t v = f2o(m[c]);
+                            const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                            if (lane == 0) {
+                                if (c < 3) atomicMin(&s_bins[a][k][c], r);
+                                else atomicMax(&s_bins[a][k][c], r);
+                            }
                         }
                     }
                 }
             }
         }
         if (tid < 21) {
-            const uint32_t e = s_u[tid];
-            const uint32_t g = s_gid[e];
+            const uint32_t g = __ldcg(&ids_snap[start + s_u[tid]]);
             const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
             s_ubox[tid][0] = b0.x; s_ubox[tid][1] = b0.y; s_ubox[tid][2] = b0.z;
             s_ubox[tid][3] = b1.x; s_ubox[tid][4] = b1.y; s_ubox[tid][5] = b1.z;
-            s_uk[tid] = s_k[e];
         }
         __syncthreads();
 
@@ -623,7 +639,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         if (best == 0xFFFFFFFFu) {
             if (tid == 0) {
                 atomicOr(&st->err, DERR_DEGENERATE);
-                atomicSub(&st->q_pending, 1u);
+                atomicSub(q_pending, 1u);
             }
             __syncthreads();
             continue;
@@ -631,10 +647,13 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
         // ---- 6. final shuffle (blas.rs:164), write the order back ----
         shuffle(cur, best / 7, best % 7 + 1, -1);
         cur ^= 1;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = warp * CHUNK + i * 32 + lane;
-            if (i < (int)E && j < n) ids[start + j] = s_gid[s_pay[cur][j] & 0xFFFFu];
+        {
+            const uint32_t* pin = cur ? s_pay1 : s_pay0;
+#pragma unroll 4
+            for (int i = 0; i < EPT; ++i) {
+                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                if (i < (int)E && j < n) ids[start + j] = __ldcg(&ids_snap[start + (pin[j] & 0xFFFFu)]);
+            }
         }
         __threadfence();
         __syncthreads();
@@ -650,9 +669,9 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, const f
             if (p <= 3) A[start] = t.leftrun + 1;
             push_child(Q, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, 0);
             push_child(Q, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT);
-            atomicAdd(&st->t2_done, 1u);
+            atomicAdd(BIG ? &st->t2b_done : &st->t2_done, 1u);
             __threadfence();
-            atomicSub(&st->q_pending, 1u);
+            atomicSub(q_pending, 1u);
         }
         __syncthreads();
     }
@@ -937,7 +956,7 @@ struct T1Args {
     uint32_t* table;
     uint32_t* tileL;     // [22][tile_stride] per-candidate L count of every tile (current order at that shuffle)
     uint32_t* tileLF;    // [tile_stride] #L in the node before this tile, for the shuffle in flight
-    uint32_t* tile_node; // [tile_stride] tile -> level node
+    uint4* tile_desc;    // [tile_stride] {node, start, n, tile index inside the node}
     uint32_t tile_stride;
     const float4* cent;
     const float4* box;
@@ -947,6 +966,34 @@ struct T1Args {
 
 // Grid-wide barrier for the cooperative (co-resident) persistent kernel: one arrival counter that only ever
 // grows, so there is no reset race; generation g completes when it reaches g * gridDim.x.
+#ifdef BVH_T1_TIMING
+__device__ unsigned long long g_t1_time[32];  // [2*kind] work ns, [2*kind+1] barrier wait ns (block 0)
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define T1_PHASE(kind, call)                                                             \
+    do {                                                                                 \
+        unsigned long long _t0 = gtimer();                                               \
+        call;                                                                            \
+        __syncthreads();                                                                 \
+        unsigned long long _t1 = gtimer();                                               \
+        grid_barrier(g.barrier, gen);                                                    \
+        unsigned long long _t2 = gtimer();                                               \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                       \
+            g_t1_time[2 * (kind)] += _t1 - _t0;                                          \
+            g_t1_time[2 * (kind) + 1] += _t2 - _t1;                                      \
+        }                                                                                \
+    } while (0)
+#else
+#define T1_PHASE(kind, call)          \
+    do {                              \
+        call;                         \
+        grid_barrier(g.barrier, gen); \
+    } while (0)
+#endif
+
 __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -965,7 +1012,7 @@ __device__ __forceinline__ void cand_of(const NodeScratch* sc, uint32_t node, in
     a = c / 7; b = c % 7 + 1;
 }
 
-// L0: per node — scratch init, tile -> node map, zero the per-candidate tile counters of the node's tiles.
+// L0: per node — scratch init, tile descriptors, zero the per-candidate tile counters of the node's tiles.
 __device__ __forceinline__ void p_t1_init(const T1Args& g) {
     for (uint32_t node = blockIdx.x; node < g.n_nodes; node += gridDim.x) {
         NodeScratch* s = g.sc + node;
@@ -973,10 +1020,9 @@ __device__ __forceinline__ void p_t1_init(const T1Args& g) {
         const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
         const uint32_t tid = threadIdx.x;
         if (tid < 12) s->bnd[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
-        if (tid < 22) { s->nL[tid] = 0; s->f[tid] = 0; }
         if (tid == 22) s->best = 0xFFFFFFFFu;
         if (tid < 144) (&s->bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
-        for (uint32_t t = tid; t < nt; t += blockDim.x) g.tile_node[nd.tile_base + t] = node;
+        for (uint32_t t = tid; t < nt; t += blockDim.x) g.tile_desc[nd.tile_base + t] = make_uint4(node, nd.start, nd.n, t);
         for (uint32_t k = tid; k < 22 * nt; k += blockDim.x) g.tileL[(size_t)(k / nt) * g.tile_stride + nd.tile_base + (k % nt)] = 0;
     }
 }
@@ -987,9 +1033,10 @@ __device__ __forceinline__ void p_t1_bounds(const T1Args& g) {
     __shared__ uint32_t s_red[T1_THREADS / 32][12];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x;
+        struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
+        const uint32_t j0 = td.w * T1_TILE;
         float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -1029,9 +1076,10 @@ __device__ __forceinline__ void p_t1_flags(const T1Args& g) {
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x;
+        struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
+        const uint32_t j0 = td.w * T1_TILE;
         float cmin[3], cmax[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { cmin[c] = o2f(g.sc[node].bnd[6 + c]); cmax[c] = o2f(g.sc[node].bnd[9 + c]); }
@@ -1065,9 +1113,10 @@ __device__ __forceinline__ void p_t1_count_final(const T1Args& g, const uint16_t
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x;
+        struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
+        const uint32_t j0 = td.w * T1_TILE;
         uint32_t a, b;
         cand_of(g.sc, node, 21, a, b);
         uint32_t cnt = 0;
@@ -1141,70 +1190,82 @@ __device__ __forceinline__ void t1_prefix(const uint16_t* fl, uint32_t start, ui
     __syncthreads();
 }
 
-// PA(c): per tile — tile prefix, rank->position table (Appendix B), count of front-examined elements.
+// PA(c): per tile — tile prefix, rank->position table (Appendix B), and the boundary element f: the first
+// element that the front cursor does not examine.  "front-examined" is a prefix of the node, so exactly one
+// thread of the whole grid sees the true->false transition; it publishes {nL, f, pivot} for the scatter phase.
 __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_t* fl, bool scanned) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
-    __shared__ uint32_t s_cnt, s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
+    __shared__ uint32_t s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t lt = tile - nd.tile_base, j0 = lt * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x, start = td.y, n = td.z, lt = td.w, tile_base = tile - lt, j0 = lt * T1_TILE;
         uint32_t a, b;
         cand_of(g.sc, node, c, a, b);
+        // flag of the element just before this warp's first slot (needed for the transition test)
+        const uint32_t jw = j0 + warp * (32 * EPT);
+        uint32_t Lprev = 0;
+        if (lane == 0 && jw > 0 && jw <= n) Lprev = ((((uint32_t)fl[start + jw - 1] >> (3 * a)) & 7u) < b) ? 1u : 0u;
         uint32_t tile_lf, nL;
         if (scanned) {
             tile_lf = g.tileLF[tile];
             nL = g.sc[node].nL[c];
-            if (tid == 0) s_cnt = 0;
         } else {
-            const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
+            const uint32_t nt = (n + T1_TILE - 1) / T1_TILE;
             uint32_t pre = 0, tot = 0;
             for (uint32_t t = tid; t < nt; t += T1_THREADS) {
-                const uint32_t v = tl[nd.tile_base + t];
+                const uint32_t v = tl[tile_base + t];
                 tot += v;
                 if (t < lt) pre += v;
             }
             pre = __reduce_add_sync(FULL_MASK, pre);
             tot = __reduce_add_sync(FULL_MASK, tot);
             if (lane == 0) { s_pre[warp] = pre; s_tot[warp] = tot; }
-            if (tid == 0) s_cnt = 0;
             __syncthreads();
             tile_lf = 0; nL = 0;
 #pragma unroll
             for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) { tile_lf += s_pre[w2]; nL += s_tot[w2]; }
-            if (tid == 0) {
-                g.tileLF[tile] = tile_lf;
-                if (lt == 0) g.sc[node].nL[c] = nL;
-            }
+            if (tid == 0) g.tileLF[tile] = tile_lf;
         }
         uint32_t bal[EPT], LFv[EPT];
         uint16_t fw[EPT];
-        t1_prefix<EPT>(fl, nd.start, nd.n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
-        uint32_t predc = 0;
+        t1_prefix<EPT>(fl, start, n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
+        uint32_t prev_pred_bit31 = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            const uint32_t j = jw + i * 32 + lane;
             bool pred = false;
-            if (j < nd.n) {
-                const uint32_t Lbit = (bal[i] >> lane) & 1u;
+            uint32_t Lbit = 0;
+            if (j < n) {
+                Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = LFv[i], RF = j - LF;
                 uint32_t Lnext;
                 if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
                 else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
-                else Lnext = (j + 1 < nd.n) ? (((((uint32_t)fl[nd.start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
+                else Lnext = (j + 1 < n) ? (((((uint32_t)fl[start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
                 const uint32_t LBB = nL - LF - Lbit - Lnext;
-                pred = (j + 2 <= nd.n) && (LBB >= RF);
-                if (Lbit) g.table[nd.start + nd.n - 1 - (nL - LF - 1)] = j;
-                else g.table[nd.start + RF] = j;
+                pred = (j + 2 <= n) && (LBB >= RF);
+                if (Lbit) g.table[start + n - 1 - (nL - LF - 1)] = j;
+                else g.table[start + RF] = j;
             }
-            predc += __popc(__ballot_sync(FULL_MASK, pred));
+            const uint32_t pb = __ballot_sync(FULL_MASK, pred);
+            if (j < n && !pred) {
+                bool prev;
+                if (lane > 0) prev = (pb >> (lane - 1)) & 1u;
+                else if (i > 0) prev = prev_pred_bit31 != 0;
+                else if (j == 0) prev = true;
+                else {
+                    // pred(j-1) from this element's prefix counts: LF(j-1) = LF(j) - L(j-1)
+                    const uint32_t LFp = LFv[i] - Lprev, RFp = (j - 1) - LFp;
+                    const uint32_t LBBp = nL - LFp - Lprev - Lbit;
+                    prev = (j + 1 <= n) && (LBBp >= RFp);
+                }
+                if (prev) g.sc[node].sh[c] = make_uint4(nL, j, nL - Lbit, 0);
+            }
+            prev_pred_bit31 = (pb >> 31) & 1u;
         }
-        if (lane == 0 && predc) atomicAdd(&s_cnt, predc);
-        __syncthreads();
-        if (tid == 0 && s_cnt) atomicAdd(&g.sc[node].f[c], s_cnt);
         __syncthreads();
     }
 }
@@ -1220,14 +1281,14 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
     const uint32_t na = (uint32_t)(c + 1) / 7, nb = (uint32_t)(c + 1) % 7 + 1;
     uint32_t* tl_next = g.tileL + (size_t)(c + 1) * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x;
+        struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
+        const uint32_t j0 = td.w * T1_TILE;
         uint32_t a, b;
         cand_of(g.sc, node, c, a, b);
-        const uint32_t nL = g.sc[node].nL[c], f = g.sc[node].f[c], n = nd.n;
-        const uint32_t Lf = ((((uint32_t)fl[nd.start + f] >> (3 * a)) & 7u) < b) ? 1u : 0u;
-        const uint32_t pivot = nL - Lf;
+        const uint4 sh = g.sc[node].sh[c];
+        const uint32_t nL = sh.x, f = sh.y, pivot = sh.z, n = nd.n;
         uint32_t bal[EPT], LFv[EPT];
         uint16_t fwv[EPT];
         t1_prefix<EPT>(fl, nd.start, n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv);
@@ -1274,9 +1335,10 @@ __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, 
     __shared__ uint32_t s_bins[3][8][6];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-        const uint32_t node = g.tile_node[tile];
-        const LevelNode nd = g.nodes[node];
-        const uint32_t j0 = (tile - nd.tile_base) * T1_TILE;
+        const uint4 td = g.tile_desc[tile];
+        const uint32_t node = td.x;
+        struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
+        const uint32_t j0 = td.w * T1_TILE;
         if (tid < 144) (&s_bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         __syncthreads();
         float lo[EPT][3], hi[EPT][3];
@@ -1407,7 +1469,7 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
             const uint32_t cn = side ? nd.n - p : p;
             const uint32_t clr = side ? 0 : nd.leftrun + 1;
             const uint32_t cfl = side ? TF_RIGHT : 0;
-            if (cn > T2_CAP) {
+            if (cn > T2B_CAP) {
                 const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
                 if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
                 LevelNode c;
@@ -1459,7 +1521,7 @@ __device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st,
 
 // The whole grid-wide tier as ONE cooperative persistent kernel: every phase boundary is a grid barrier
 // instead of a kernel launch, and the level loop never returns to the host.  ~52 barriers per level.
-__global__ void __launch_bounds__(T1_THREADS) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
+__global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
     LevelNode* lv[2] = {lv0, lv1};
     uint32_t gen = 0;
@@ -1472,39 +1534,26 @@ __global__ void __launch_bounds__(T1_THREADS) k_t1_coop(T1Args g, LevelNode* lv0
         g.nodes = lv[slot];
         g.n_nodes = n_nodes;
         g.n_tiles = n_tiles;
-        p_t1_init(g);
-        grid_barrier(g.barrier, gen);
-        p_t1_bounds(g);
-        grid_barrier(g.barrier, gen);
-        p_t1_flags(g);
-        grid_barrier(g.barrier, gen);
+        T1_PHASE(0, p_t1_init(g));
+        T1_PHASE(1, p_t1_bounds(g));
+        T1_PHASE(2, p_t1_flags(g));
         for (int c = 0; c < 22; ++c) {
             const uint32_t* ids_in = (c & 1) ? g.ids1 : g.ids0;
             uint32_t* ids_out = (c & 1) ? g.ids0 : g.ids1;
             const uint16_t* fl_in = (c & 1) ? g.fl1 : g.fl0;
             uint16_t* fl_out = (c & 1) ? g.fl0 : g.fl1;
             if (c == 21) {
-                p_t1_bins(g, ids_in, fl_in);
-                grid_barrier(g.barrier, gen);
-                p_t1_select(g);
-                grid_barrier(g.barrier, gen);
-                p_t1_count_final(g, fl_in);
-                grid_barrier(g.barrier, gen);
+                T1_PHASE(3, p_t1_bins(g, ids_in, fl_in));
+                T1_PHASE(4, p_t1_select(g));
+                T1_PHASE(5, p_t1_count_final(g, fl_in));
             }
-            if (scanned) {
-                p_t1_tilescan(g, c);
-                grid_barrier(g.barrier, gen);
-            }
-            p_t1_table(g, c, fl_in, scanned);
-            grid_barrier(g.barrier, gen);
-            p_t1_scatter(g, c, ids_in, fl_in, ids_out, fl_out);
-            grid_barrier(g.barrier, gen);
+            if (scanned) T1_PHASE(6, p_t1_tilescan(g, c));
+            T1_PHASE(7, p_t1_table(g, c, fl_in, scanned));
+            T1_PHASE(8, p_t1_scatter(g, c, ids_in, fl_in, ids_out, fl_out));
         }
         const int next = slot ^ 1;
-        p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch);
-        grid_barrier(g.barrier, gen);
-        if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot);
-        grid_barrier(g.barrier, gen);
+        T1_PHASE(9, p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch));
+        T1_PHASE(10, if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot));
         slot = next;
     }
 }
@@ -1633,20 +1682,24 @@ __global__ void __launch_bounds__(256) k_permute_gather(const uint32_t* __restri
     tmp[3 * (size_t)i + 2] = I[s + 2];
 }
 
-__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_q, Task* first_qw, Task* first_t3,
-                                                    LevelNode* first_lv, uint32_t N, uint32_t epoch) {
+__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_qb, Task* first_q, Task* first_qw,
+                                                    Task* first_t3, LevelNode* first_lv, uint32_t N, uint32_t epoch) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     BuildState s{};
     Task root{};
     root.start = 0; root.n = N; root.leftrun = 0; root.pstart = 0; root.pleftrun = 0; root.flags = TF_ROOT;
     root.ready = epoch; root.pad = 0;
-    if (N > T2_CAP) {
+    if (N > T2B_CAP) {
         LevelNode l;
         l.start = 0; l.n = N; l.leftrun = 0; l.pstart = 0; l.pleftrun = 0; l.flags = TF_ROOT; l.tile_base = 0; l.pad = 0;
         first_lv[0] = l;
         s.lv_count[0] = 1;
         s.lv_tiles[0] = (N + T1_TILE - 1) / T1_TILE;
         s.lv_maxtiles[0] = s.lv_tiles[0];
+    } else if (N > T2_CAP) {
+        first_qb[0] = root;
+        s.b_tail = 1;
+        s.b_pending = 1;
     } else if (N > T2W_CAP) {
         first_q[0] = root;
         s.q_tail = 1;
@@ -1664,10 +1717,35 @@ __global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_
 
 }  // namespace
 
+constexpr size_t T2_SMEM = (size_t)T2_CAP * 10;    // 2 x u32 payload + u16 table per slot
+constexpr size_t T2B_SMEM = (size_t)T2B_CAP * 10;
+
 int blas_t2_occupancy() {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2<T2_CAP, T2_THREADS>, T2_THREADS, 0) != cudaSuccess) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2<T2_CAP, T2_THREADS, false>, T2_THREADS, T2_SMEM) != cudaSuccess) occ = 1;
     return occ < 1 ? 1 : occ;
+}
+
+int blas_t2b_setup() {
+    if (cudaFuncSetAttribute(k_t2<T2B_CAP, T2B_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2B_SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t2<T2B_CAP, T2B_THREADS, true>, T2B_THREADS, T2B_SMEM) != cudaSuccess) occ = 0;
+    return occ;
+}
+
+int blas_t1_timing(unsigned long long* out32) {
+#ifdef BVH_T1_TIMING
+    unsigned long long z[32] = {};
+    cudaMemcpyFromSymbol(out32, g_t1_time, sizeof(z));
+    cudaMemcpyToSymbol(g_t1_time, z, sizeof(z));
+    return 1;
+#else
+    (void)out32;
+    return 0;
+#endif
 }
 
 int blas_t1_coop_occupancy() {
@@ -1708,9 +1786,10 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     if (nodes_cap < 2 * n_tris)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: nodes_cap must be >= 2*n_tris");
     const uint32_t N = (uint32_t)n_tris;
-    const uint32_t max_large = N / T2_CAP + 2;
+    const uint32_t max_large = N / T2B_CAP + 2;
     const uint32_t max_tiles = N / T1_TILE + max_large + 2;
-    const uint32_t q_cap = N / 32 + 4096;   // nodes with > T2W_CAP primitives (typically ~N/100)
+    const uint32_t qb_cap = N / 256 + 4096; // nodes with 2049..16384 primitives
+    const uint32_t q_cap = N / 32 + 4096;   // nodes with 257..2048 primitives (typically ~N/100)
     const uint32_t qw_cap = N / 4 + 4096;   // nodes with 33..T2W_CAP primitives (typically ~N/28)
     const uint32_t t3_cap = N + 16;
     const uint32_t scan_n = N + 1;
@@ -1718,11 +1797,12 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
 
     // carve the workspace (first pass sizes, second pass assigns)
     float4 *cent = nullptr, *box = nullptr;
-    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr, *tile_node = nullptr, *barrier = nullptr,
+    uint4* tile_desc = nullptr;
+    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr,  *barrier = nullptr,
              *scan_sums = nullptr, *scan_total = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *q = nullptr, *qw = nullptr, *t3 = nullptr;
+    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -1738,6 +1818,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         table = c.take<uint32_t>(N);
         A = c.take<uint32_t>(scan_n);
         recs = c.take<uint4>(3 * 2 * (size_t)N);
+        qb = c.take<Task>(qb_cap);
         q = c.take<Task>(q_cap);
         qw = c.take<Task>(qw_cap);
         t3 = c.take<Task>(t3_cap);
@@ -1746,7 +1827,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         sc = c.take<NodeScratch>(max_large);
         tileL = c.take<uint32_t>(22 * (size_t)max_tiles);
         tileLF = c.take<uint32_t>(max_tiles);
-        tile_node = c.take<uint32_t>(max_tiles);
+        tile_desc = c.take<uint4>(max_tiles);
         barrier = c.take<uint32_t>(64);
         scan_sums = c.take<uint32_t>(scan_blocks + 1);
         scan_total = c.take<uint32_t>(4);
@@ -1767,19 +1848,19 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
     const bool prof = ctx->profiling;
     if (prof) cudaEventRecord(ctx->ev[0], stream);
-    Queues Q{q, qw, t3, q_cap, qw_cap, t3_cap};
-    k_init_state<<<1, 32, 0, stream>>>(st, q, qw, t3, lv[0], N, epoch);
+    Queues Q{qb, q, qw, t3, qb_cap, q_cap, qw_cap, t3_cap};
+    k_init_state<<<1, 32, 0, stream>>>(st, qb, q, qw, t3, lv[0], N, epoch);
     k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, cent, box, ids0, st);
     launches += 2;
     if (prof) cudaEventRecord(ctx->ev[1], stream);
 
     // ---- T1: grid-wide tier, one cooperative persistent launch ----
-    if (N > (uint32_t)T2_CAP) {
+    if (N > (uint32_t)T2B_CAP) {
         CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, 256, stream));
         T1Args g;
         g.nodes = lv[0]; g.sc = sc; g.n_nodes = 0; g.n_tiles = 0;
         g.ids0 = ids0; g.ids1 = ids1; g.fl0 = fl0; g.fl1 = fl1;
-        g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.tile_node = tile_node; g.tile_stride = max_tiles;
+        g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.tile_desc = tile_desc; g.tile_stride = max_tiles;
         g.cent = cent; g.box = box; g.st = st; g.barrier = barrier;
         LevelNode* lv0 = lv[0];
         LevelNode* lv1 = lv[1];
@@ -1799,7 +1880,12 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     // ---- T2: persistent blocks on the device task queue ----
     {
         const int blocks = ctx->sm_count * (ctx->t2_blocks_per_sm > 0 ? ctx->t2_blocks_per_sm : 1);
-        k_t2<T2_CAP, T2_THREADS><<<blocks, T2_THREADS, 0, stream>>>(Q, ids0, cent, box, recs, A, st, epoch);
+        if (N > (uint32_t)T2_CAP) {
+            k_t2<T2B_CAP, T2B_THREADS, true><<<ctx->sm_count, T2B_THREADS, T2B_SMEM, stream>>>(Q, ids0, ids1, cent, box, recs, A, st, epoch);
+            launches++;
+        }
+        if (prof) cudaEventRecord(ctx->ev[7], stream);
+        k_t2<T2_CAP, T2_THREADS, false><<<blocks, T2_THREADS, T2_SMEM, stream>>>(Q, ids0, ids1, cent, box, recs, A, st, epoch);
         launches++;
     }
     if (prof) cudaEventRecord(ctx->ev[6], stream);
@@ -1845,6 +1931,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.n_nodes = 2 + 2 * interior;
     stats.sum_interior_prims = hs->sum_interior;
     stats.grid_levels = hs->levels_done;
+    stats.big_block_tasks = hs->t2b_done;
     stats.block_tasks = hs->t2_done;
     stats.warp_node_tasks = hs->t2w_done;
     stats.warp_tasks = hs->t3_count;
@@ -1852,7 +1939,8 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&stats.ms_grid, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&stats.ms_block, ctx->ev[2], ctx->ev[6]);
+        cudaEventElapsedTime(&stats.ms_big_block, ctx->ev[2], ctx->ev[7]);
+        cudaEventElapsedTime(&stats.ms_block, ctx->ev[7], ctx->ev[6]);
         cudaEventElapsedTime(&stats.ms_warp_node, ctx->ev[6], ctx->ev[3]);
         cudaEventElapsedTime(&stats.ms_warp, ctx->ev[3], ctx->ev[4]);
         cudaEventElapsedTime(&stats.ms_emit, ctx->ev[4], ctx->ev[5]);
