@@ -1838,12 +1838,15 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     }
     // Task slots are marked ready with a build-unique number so queues never need clearing; the counter is
     // process-wide because a freed workspace of one context can be handed to another by cudaMalloc.
-    static std::atomic<uint32_t> g_epoch{0x1000};
-    const uint32_t epoch = g_epoch.fetch_add(1) + 1;
+    static std::atomic<uint32_t> g_epoch{0};
+    const uint32_t epoch = 0x80000000u | (g_epoch.fetch_add(1) + 1);
     ctx->epoch = epoch;
     uint32_t launches = 0;
     BvhCudaBuildStats stats{};
 
+    // The three task queues are contiguous; clearing them makes every `ready` word differ from the epoch even when
+    // the workspace still holds other data of an earlier, differently sized build.
+    CU_CHECK(ctx, cudaMemsetAsync(qb, 0, (size_t)((char*)(qw + qw_cap) - (char*)qb), stream));
     CU_CHECK(ctx, cudaMemsetAsync(A, 0, sizeof(uint32_t) * scan_n, stream));
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
     const bool prof = ctx->profiling;
