@@ -279,13 +279,15 @@ def main():
         d_infos.copy_(torch.from_numpy(infos.view(np.uint8).reshape(-1)), non_blocking=False)
         ctx.tlas_build_dev(d_inst.data_ptr(), 2, d_infos.data_ptr(), 2, d_tlas.data_ptr(), d_kids.data_ptr(), stream)
         if ev: ev[2].record()
-        scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
-                         d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
-                         counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": m0 + m1, "vertices": n_verts,
-                                 "indices": 3 * n_tris})
-        scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
+        if "scene" not in state:
+            state["scene"] = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
+                                      d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
+                                      counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": m0 + m1, "vertices": n_verts,
+                                              "indices": 3 * n_tris}, stream=stream)
+        else:
+            state["scene"].refresh_dev(m0 + m1, stream)  # re-bake the traversal copy of the freshly permuted triangles
+        state["scene"].occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
         if ev: ev[3].record()
-        scene.close()
         state["M"] = m0 + m1
 
     def barrier():
@@ -337,10 +339,23 @@ def main():
     h_occ = torch.empty(n_rays, dtype=torch.uint8).pin_memory()
     import ctypes as C
     lib = ctx.lib
-    host_scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
-                          d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
-                          counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": state["M"], "vertices": n_verts,
-                                  "indices": 3 * n_tris})
+    host_scene = state["scene"]
+    # incoherent variant: the same rays under one fixed random permutation (device-side gather, untimed)
+    gperm = torch.Generator(device="cpu"); gperm.manual_seed(2012 + rank)
+    perm = torch.randperm(n_rays, generator=gperm).to(dev)
+    d_ro_i = d_ro.view(-1, 3)[perm].contiguous().view(-1); d_rd_i = d_rd.view(-1, 3)[perm].contiguous().view(-1)
+    del perm
+    inc = []
+    for k in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); host_scene.occluded_dev(d_ro_i.data_ptr(), d_rd_i.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream); e1.record()
+        torch.cuda.synchronize()
+        if k > 0: inc.append(e0.elapsed_time(e1))
+    inc_t = torch.tensor([float(np.mean(inc))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(inc_t, op=dist.ReduceOp.MAX)
+    inc_ms = float(inc_t.item())
+    del d_ro_i, d_rd_i
     e2e_steps = max(3, min(args.steps, 5))
     eb, er = [], []
     for k in range(e2e_steps + 1):
@@ -401,6 +416,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "rays": {"metric": "shadow_ray_Mrays_per_s", "value": rvalue, "unit": "Mrays/s", "ms": r_ms_step, "occluded_frac": occ_frac,
+                     "order": "surface-raster (G-buffer-like) ray order; incoherent = same rays, one fixed random permutation",
+                     "incoherent": {"value": world * n_rays / (inc_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms": inc_ms},
                      "roofline": ray_roof, "cpu_baseline": cpu_rays,
                      "e2e": {"value": world * n_rays / e2e_r / 1e6, "unit": "Mrays/s", "ms": e2e_r * 1e3,
                              "h2d_bytes_per_step": int(ro.nbytes + rd.nbytes), "d2h_bytes_per_step": int(n_rays),

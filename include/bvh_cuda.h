@@ -147,8 +147,13 @@ typedef struct BvhCudaSceneDesc {
 } BvhCudaSceneDesc;
 /* Copies host buffers to the device. */
 int bvh_cuda_scene_upload(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* host_desc, bvh_cuda_scene** out);
-/* Wraps device buffers that stay owned by the caller (no copy). */
-int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* dev_desc, bvh_cuda_scene** out);
+/* Wraps device buffers that stay owned by the caller (no copy of the six buffers).  Both scene constructors also
+ * "bake" an internal, traversal-friendly copy of the triangles (3 x float4 per pooled triangle, gathered through
+ * indices + vertex_offset exactly as fetch_vertex does, shaders/utils/bvh.wgsl:30-33) on `stream`. */
+int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* dev_desc, void* stream, bvh_cuda_scene** out);
+/* Re-bakes a wrapped scene after its buffers were rewritten in place (e.g. a BLAS rebuilt into the same node /
+ * index buffers); dev_desc may be NULL to keep the pointers, or carry new pointers/counts with the same n_indices. */
+int bvh_cuda_scene_refresh_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, const BvhCudaSceneDesc* dev_desc, void* stream);
 void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene);
 
 /* ---- traversal ----------------------------------------------------------------------------------------- *

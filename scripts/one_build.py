@@ -32,7 +32,11 @@ if n_rays:
     ro, rd = S.gbuffer_shadow_rays(n_rays, S.world_triangles(dv, di, mats[1]), S.rect_light_corners(), seed=12)
     d_ro = torch.from_numpy(ro.reshape(-1)).to(dev); d_rd = torch.from_numpy(rd.reshape(-1)).to(dev)
     d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
-    for k in range(2):
+    for k in range(4):
+        if k == 2:
+            perm = torch.randperm(n_rays).to(dev)
+            d_ro = d_ro.view(-1, 3)[perm].contiguous().view(-1); d_rd = d_rd.view(-1, 3)[perm].contiguous().view(-1)
+            print("-- incoherent (random permutation) --")
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream); e1.record()
         torch.cuda.synchronize()

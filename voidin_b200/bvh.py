@@ -192,7 +192,7 @@ class Scene:
     vertices, indices — uploaded once, then traversed with traverse_tlas semantics (shaders/utils/bvh.wgsl:89)."""
 
     def __init__(self, tlas_nodes, tlas_children, instances, meshes, bvh_nodes, vertices, indices,
-                 ctx: Context | None = None, device_ptrs: bool = False, counts: dict | None = None):
+                 ctx: Context | None = None, device_ptrs: bool = False, counts: dict | None = None, stream: int = 0):
         self._ctx = ctx or default_context()
         d = _lib.SceneDesc()
         if device_ptrs:
@@ -200,7 +200,11 @@ class Scene:
             d.instances, d.meshes, d.bvh_nodes, d.vertices, d.indices = instances, meshes, bvh_nodes, vertices, indices
             d.n_tlas_nodes, d.n_instances, d.n_meshes = counts["tlas_nodes"], counts["instances"], counts["meshes"]
             d.n_bvh_nodes, d.n_vertices, d.n_indices = counts["bvh_nodes"], counts["vertices"], counts["indices"]
-            fn = self._ctx.lib.bvh_cuda_scene_wrap_dev
+            h = C.c_void_p()
+            self._ctx.check(self._ctx.lib.bvh_cuda_scene_wrap_dev(self._ctx.h, C.byref(d), stream, C.byref(h)))
+            self.h = h
+            self._desc = d
+            return
         else:
             keep = [np.ascontiguousarray(tlas_nodes, dtype=TLAS_NODE),
                     None if tlas_children is None else np.ascontiguousarray(tlas_children, dtype=np.uint32),
@@ -219,6 +223,13 @@ class Scene:
         h = C.c_void_p()
         self._ctx.check(fn(self._ctx.h, C.byref(d), C.byref(h)))
         self.h = h
+
+    def refresh_dev(self, n_bvh_nodes: int | None = None, stream: int = 0):
+        """Re-bake a device-wrapped scene after its buffers were rewritten in place."""
+        d = self._desc
+        if n_bvh_nodes is not None:
+            d.n_bvh_nodes = n_bvh_nodes
+        self._ctx.check(self._ctx.lib.bvh_cuda_scene_refresh_dev(self._ctx.h, self.h, C.byref(d), stream))
 
     def close(self):
         if getattr(self, "h", None) and self._ctx.h:

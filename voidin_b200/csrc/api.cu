@@ -281,29 +281,46 @@ int bvh_cuda_scene_upload(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* h, bvh_cuda
     sc->d.bvh_nodes = (const BvhNode*)(b + off[4]);
     sc->d.vertices = (const float*)(b + off[5]);
     sc->d.indices = (const uint32_t*)(b + off[6]);
+    rc = scene_bake_device(ctx, sc, ctx->own_stream);
+    if (rc == BVH_CUDA_OK && cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) rc = ctx_cuda_fail(ctx, cudaGetLastError(), "bake");
+    if (rc) { bvh_cuda_scene_free(ctx, sc); return rc; }
     *out = sc;
     return BVH_CUDA_OK;
 }
 
-int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* d, bvh_cuda_scene** out) {
+int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* d, void* stream, bvh_cuda_scene** out) {
     if (!ctx || !out) return BVH_CUDA_EINVAL;
     *out = nullptr;
     int rc = scene_check(ctx, d);
     if (rc) return rc;
+    DeviceGuard g(ctx->device);
     bvh_cuda_scene* sc = new (std::nothrow) bvh_cuda_scene();
     if (!sc) return BVH_CUDA_ENOMEM;
     sc->d = *d;
     sc->owned = false;
+    rc = scene_bake_device(ctx, sc, (cudaStream_t)stream);
+    if (rc) { bvh_cuda_scene_free(ctx, sc); return rc; }
     *out = sc;
     return BVH_CUDA_OK;
 }
 
+int bvh_cuda_scene_refresh_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, const BvhCudaSceneDesc* d, void* stream) {
+    if (!ctx || !scene) return BVH_CUDA_EINVAL;
+    if (scene->owned) return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene_refresh: only wrapped scenes can be refreshed");
+    DeviceGuard g(ctx->device);
+    if (d) {
+        int rc = scene_check(ctx, d);
+        if (rc) return rc;
+        if (d->n_indices != scene->d.n_indices) return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene_refresh: index count changed");
+        scene->d = *d;
+    }
+    return scene_bake_device(ctx, scene, (cudaStream_t)stream);
+}
+
 void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene) {
     if (!scene) return;
-    if (scene->owned && scene->block) {
-        if (ctx) { DeviceGuard g(ctx->device); cudaFree(scene->block); }
-        else cudaFree(scene->block);
-    }
+    if (ctx) { DeviceGuard g(ctx->device); if (scene->owned && scene->block) cudaFree(scene->block); if (scene->baked) cudaFree(scene->baked); }
+    else { if (scene->owned && scene->block) cudaFree(scene->block); if (scene->baked) cudaFree(scene->baked); }
     delete scene;
 }
 

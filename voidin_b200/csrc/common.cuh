@@ -48,6 +48,8 @@ struct bvh_cuda_scene {
     BvhCudaSceneDesc d{};  // device pointers
     bool owned = false;
     void* block = nullptr;  // single allocation when owned
+    void* baked = nullptr;  // 3 x float4 per pooled triangle (always owned)
+    void* counter = nullptr;  // persistent-warp ray counter (tail of `baked`)
 };
 
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what);
@@ -67,6 +69,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
                       cudaStream_t stream);
 int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
                       size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, cudaStream_t stream);
+int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t stream);
 int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
                       const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d, size_t n_rays,
                       float* d_t, uint32_t* d_tri, cudaStream_t stream);

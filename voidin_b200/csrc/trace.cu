@@ -162,97 +162,173 @@ __device__ __forceinline__ void mat_mul(const float4* m, const float* p, float w
     out[2] = ((c0.z * p[0] + c1.z * p[1]) + c2.z * p[2]) + c3.z * w;
 }
 
+// Bakes the pooled (vertices, indices, vertex_offset) triple of every triangle into 3 x float4 in pooled triangle
+// order, so a leaf test is 3 independent 16-byte loads instead of 3 index loads + 9 dependent scalar loads
+// (same vertex values => same arithmetic as fetch_vertex, bvh.wgsl:30-33).
+__global__ void __launch_bounds__(256) k_bake_tris(BvhCudaSceneDesc sc, float4* tris, uint32_t n_tris) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    // mesh that owns pooled triangle t: last mesh with base_index <= 3t (meshes are pooled in order, mesh/mod.rs:327)
+    uint32_t lo = 0, hi = (uint32_t)sc.n_meshes;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sc.meshes[mid].base_index <= 3 * t) lo = mid; else hi = mid;
+    }
+    const uint32_t voff = (uint32_t)sc.meshes[lo].vertex_offset;
+    const uint32_t* ip = sc.indices + 3 * (size_t)t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* p = sc.vertices + 3 * (size_t)(voff + ip[k]);
+        tris[3 * (size_t)t + k] = make_float4(p[0], p[1], p[2], 0.0f);
+    }
+}
+
+// Stack entries carry what the pop needs (left_first | count << 30), taken from the child node at the time its box
+// is tested, so a node is fetched once (as a child) instead of twice.
+__device__ __forceinline__ uint32_t pack_meta(const NodeW& n) {
+    return (__float_as_uint(n.a.w) & 0x3FFFFFFFu) | (__float_as_uint(n.b.w) << 30);
+}
+
+// Persistent-warp traversal with dynamic ray fetch.  Per-ray work has a heavy tail (mean ~35 node visits, some
+// rays > 1000), so with one ray per thread for the life of a warp only ~4.5 of 32 lanes were busy (ncu r01b).  Here
+// every lane keeps its own ray state and, at the top of each round (a converged point), idle lanes grab the next
+// unprocessed rays from a global counter (one warp-aggregated atomicAdd).  A round advances each live ray to its
+// next leaf ("while-while": TLAS steps until a BLAS is entered, interior nodes until a leaf, then the leaf's
+// triangles).  The per-ray visit order is exactly the reference's; only the lane/ray assignment is dynamic.
 template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float* __restrict__ ro,
-                                                     const float* __restrict__ rd, size_t R, float tmax, float* t_out,
-                                                     uint32_t* tri_out, uint32_t* inst_out, uint8_t* occ_out) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const float eye[3] = {ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]};
-    const float dir[3] = {rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]};
-    const float inv[3] = {__fdiv_rn(1.0f, dir[0]), __fdiv_rn(1.0f, dir[1]), __fdiv_rn(1.0f, dir[2])};
+__global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
+                                                     const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
+                                                     float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out,
+                                                     uint8_t* occ_out, unsigned long long* next_ray) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t tstack[STACK_CAP], bstack[STACK_CAP];
-    int th = 0;
-    tstack[th++] = 0;
-    float dist = tmax;
-    uint32_t tri = BVH_CUDA_NO_HIT, inst = BVH_CUDA_NO_HIT;
-    bool res_hit = false, done = false;
-    while (th > 0 && !done) {
-        const uint32_t ni = tstack[--th];
-        const NodeW node = ld_node(sc.tlas_nodes, ni);
-        const uint32_t left_right = __float_as_uint(node.a.w);
-        if (left_right == 0) {
-            // instance_intersect (bvh.wgsl:78-87)
-            const uint32_t ii = __float_as_uint(node.b.w);
-            const Instance* in = sc.instances + ii;
-            const MeshInfo* mesh = sc.meshes + in->mesh;
-            const uint32_t base_index = mesh->base_index, voff = (uint32_t)mesh->vertex_offset, bvh_index = mesh->bvh_index;
-            float e2[3], d2[3];
-            const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
-            mat_mul(im, eye, 1.0f, e2);
-            mat_mul(im, dir, 0.0f, d2);
-            const float inv2[3] = {__fdiv_rn(1.0f, d2[0]), __fdiv_rn(1.0f, d2[1]), __fdiv_rn(1.0f, d2[2])};
-            // traverse_bvh (bvh.wgsl:35-76)
-            int bh = 0;
-            bstack[bh++] = bvh_index;
-            float hit = dist;
-            while (bh > 0) {
-                const NodeW bn = ld_node(sc.bvh_nodes, bstack[--bh]);
-                const uint32_t left_first = __float_as_uint(bn.a.w), count = __float_as_uint(bn.b.w);
-                if (count > 0) {
-                    for (uint32_t i = 0; i < count; ++i) {
-                        const uint32_t idx = left_first + i;
-                        const uint32_t* ip = sc.indices + base_index + 3 * (size_t)idx;
-                        const float* p0 = sc.vertices + 3 * (size_t)(voff + ip[0]);
-                        const float* p1 = sc.vertices + 3 * (size_t)(voff + ip[1]);
-                        const float* p2 = sc.vertices + 3 * (size_t)(voff + ip[2]);
-                        const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
-                        if (trig_w(e2, d2, v0, v1, v2, &hit)) {
-                            dist = hit; tri = idx; inst = ii; res_hit = true;
-                            if (ANY) { done = true; break; }
-                        }
-                    }
-                    if (ANY && done) break;
+    int th = 0, bh = 0;
+    bool active = false;
+    size_t r = 0;
+    float eye[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
+    float e2[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, inv2[3] = {0, 0, 0};
+    float dist = tmax, hit = tmax;
+    uint32_t tri = BVH_CUDA_NO_HIT, inst = BVH_CUDA_NO_HIT, ii = 0, tri_base = 0, bvh_index = 0;
+    bool res_hit = false;
+    bool exhausted = false;  // warp-uniform: the ray counter ran past R
+
+    for (;;) {
+        // ---- refill idle lanes (converged) ----
+        const uint32_t idle = __ballot_sync(FULL_MASK, !active);
+        if (idle != 0 && !exhausted && (__popc(idle) >= 8 || idle == FULL_MASK)) {
+            const uint32_t n_idle = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, (unsigned long long)n_idle);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (base + n_idle >= R) exhausted = true;
+            const unsigned long long mine = base + __popc(idle & lt_mask);
+            if (!active && mine < R) {
+                r = (size_t)mine;
+                eye[0] = ro[3 * r]; eye[1] = ro[3 * r + 1]; eye[2] = ro[3 * r + 2];
+                dir[0] = rd[3 * r]; dir[1] = rd[3 * r + 1]; dir[2] = rd[3 * r + 2];
+                inv[0] = __fdiv_rn(1.0f, dir[0]); inv[1] = __fdiv_rn(1.0f, dir[1]); inv[2] = __fdiv_rn(1.0f, dir[2]);
+                th = 0; bh = 0;
+                tstack[th++] = 0;
+                dist = tmax; hit = tmax;
+                tri = BVH_CUDA_NO_HIT; inst = BVH_CUDA_NO_HIT;
+                res_hit = false;
+                active = true;
+            }
+        }
+        if (__ballot_sync(FULL_MASK, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one round: advance every live ray to (and through) its next leaf ----
+        if (active) {
+            bool finished = false;
+            // TLAS steps (bvh.wgsl:89-123) until a BLAS is entered or the ray is done
+            while (bh == 0 && !finished) {
+                if (th == 0) { finished = true; break; }
+                const uint32_t ni = tstack[--th];
+                const NodeW node = ld_node(sc.tlas_nodes, ni);
+                const uint32_t left_right = __float_as_uint(node.a.w);
+                if (left_right == 0) {
+                    // instance_intersect (bvh.wgsl:78-87)
+                    ii = __float_as_uint(node.b.w);
+                    const Instance* in = sc.instances + ii;
+                    const MeshInfo* mesh = sc.meshes + in->mesh;
+                    tri_base = mesh->base_index / 3u;
+                    bvh_index = mesh->bvh_index;
+                    const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
+                    mat_mul(im, eye, 1.0f, e2);
+                    mat_mul(im, dir, 0.0f, d2);
+                    inv2[0] = __fdiv_rn(1.0f, d2[0]); inv2[1] = __fdiv_rn(1.0f, d2[1]); inv2[2] = __fdiv_rn(1.0f, d2[2]);
+                    bstack[bh++] = pack_meta(ld_node(sc.bvh_nodes, bvh_index));
+                    hit = dist;
                 } else {
-                    uint32_t min_index = bvh_index + left_first, max_index = bvh_index + left_first + 1;
-                    const NodeW ca = ld_node(sc.bvh_nodes, min_index), cb = ld_node(sc.bvh_nodes, max_index);
-                    float min_dist = aabb_w(e2, inv2, ca.a, ca.b, hit);
-                    float max_dist = aabb_w(e2, inv2, cb.a, cb.b, hit);
+                    uint32_t min_index, max_index;
+                    if (sc.tlas_children) {
+                        const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        min_index = k.x; max_index = k.y;
+                    } else {
+                        min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
+                    }
+                    // The reference's root is merged with itself (tlas.rs:61), so both children can be the same
+                    // node.  Its second traversal can never accept a triangle (same boxes, hit only shrinks,
+                    // acceptance is strict t < hit), so it is skipped: results are identical.
+                    const bool twin = (min_index == max_index);
+                    const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
+                    float min_dist = aabb_w(eye, inv, ca.a, ca.b, dist);
+                    float max_dist = aabb_w(eye, inv, cb.a, cb.b, dist);
                     if (min_dist > max_dist) {
                         const uint32_t ti = min_index; min_index = max_index; max_index = ti;
                         const float td = min_dist; min_dist = max_dist; max_dist = td;
                     }
-                    if (min_dist >= hit) continue;
-                    if (max_dist <= hit && bh < STACK_CAP) bstack[bh++] = max_index;
-                    if (bh < STACK_CAP) bstack[bh++] = min_index;
+                    if (min_dist >= dist) continue;
+                    if (!twin && max_dist < dist && th < STACK_CAP) tstack[th++] = max_index;
+                    if (th < STACK_CAP) tstack[th++] = min_index;
                 }
             }
-        } else {
-            uint32_t min_index, max_index;
-            if (sc.tlas_children) {
-                const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
-                min_index = k.x; max_index = k.y;
-            } else {
-                min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
+            // traverse_bvh (bvh.wgsl:35-76): interior nodes until a leaf
+            uint32_t leaf = 0;
+            while (bh > 0) {
+                const uint32_t m = bstack[--bh];
+                if (m >> 30) { leaf = m; break; }
+                const uint32_t c0 = bvh_index + (m & 0x3FFFFFFFu);
+                const NodeW ca = ld_node(sc.bvh_nodes, c0), cb = ld_node(sc.bvh_nodes, c0 + 1);
+                uint32_t min_meta = pack_meta(ca), max_meta = pack_meta(cb);
+                float min_dist = aabb_w(e2, inv2, ca.a, ca.b, hit);
+                float max_dist = aabb_w(e2, inv2, cb.a, cb.b, hit);
+                if (min_dist > max_dist) {
+                    const uint32_t ti = min_meta; min_meta = max_meta; max_meta = ti;
+                    const float td = min_dist; min_dist = max_dist; max_dist = td;
+                }
+                if (min_dist >= hit) continue;
+                if (max_dist <= hit && bh < STACK_CAP) bstack[bh++] = max_meta;
+                if (bh < STACK_CAP) bstack[bh++] = min_meta;
             }
-            const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
-            float min_dist = aabb_w(eye, inv, ca.a, ca.b, dist);
-            float max_dist = aabb_w(eye, inv, cb.a, cb.b, dist);
-            if (min_dist > max_dist) {
-                const uint32_t ti = min_index; min_index = max_index; max_index = ti;
-                const float td = min_dist; min_dist = max_dist; max_dist = td;
+            if (leaf) {
+                const uint32_t count = leaf >> 30, left_first = leaf & 0x3FFFFFFFu;
+                for (uint32_t i = 0; i < count; ++i) {
+                    const uint32_t idx = left_first + i;
+                    const float4* tp = tris + 3 * (size_t)(tri_base + idx);
+                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    const float v0[3] = {a.x, a.y, a.z}, v1[3] = {b.x, b.y, b.z}, v2[3] = {c.x, c.y, c.z};
+                    if (trig_w(e2, d2, v0, v1, v2, &hit)) {
+                        dist = hit; tri = idx; inst = ii; res_hit = true;
+                        if (ANY) { finished = true; break; }
+                    }
+                }
             }
-            if (min_dist >= dist) continue;
-            if (max_dist < dist && th < STACK_CAP) tstack[th++] = max_index;
-            if (th < STACK_CAP) tstack[th++] = min_index;
+            if (!finished && bh == 0 && th == 0) finished = true;
+            if (finished) {
+                if (ANY) {
+                    occ_out[r] = res_hit ? 1 : 0;
+                } else {
+                    t_out[r] = res_hit ? dist : MAXD;
+                    tri_out[r] = tri;
+                    inst_out[r] = inst;
+                }
+                active = false;
+            }
         }
-    }
-    if (ANY) {
-        occ_out[r] = res_hit ? 1 : 0;
-    } else {
-        t_out[r] = res_hit ? dist : MAXD;
-        tri_out[r] = tri;
-        inst_out[r] = inst;
     }
 }
 
@@ -278,12 +354,35 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     if (!scene || !d_ray_o || !d_ray_d) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null pointer");
     if (any_hit ? !d_occ : (!d_t || !d_tri || !d_inst)) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null output");
     if (n_rays == 0) return BVH_CUDA_OK;
-    const size_t blocks = (n_rays + 127) / 128;
-    if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: too many rays for one call");
+    const float4* tris = reinterpret_cast<const float4*>(scene->baked);
+    if (!tris) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: scene has no baked triangles");
+    // persistent warps: the ray counter lives in the scene (8 bytes), reset per launch
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(scene->counter);
+    CU_CHECK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    size_t want = (n_rays + 127) / 128;
+    const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
     if (any_hit)
-        k_trace_scene<true><<<(unsigned)blocks, 128, 0, stream>>>(scene->d, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ);
+        k_trace_scene<true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
     else
-        k_trace_scene<false><<<(unsigned)blocks, 128, 0, stream>>>(scene->d, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr);
+        k_trace_scene<false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return BVH_CUDA_OK;
+}
+
+// Builds the scene's baked triangle array (device, owned by the scene).  Stream-ordered; the scene's source buffers
+// must not change afterwards.
+int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t stream) {
+    const size_t n_tris = scene->d.n_indices / 3;
+    if (n_tris == 0 || n_tris >= (1ull << 30) || scene->d.n_bvh_nodes >= (1ull << 30))
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene: triangle / node count must be in [1, 2^30)");
+    if (!scene->baked) {
+        cudaError_t e = cudaMalloc(&scene->baked, sizeof(float4) * 3 * n_tris + 256);
+        if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(baked triangles)");
+        scene->counter = (char*)scene->baked + sizeof(float4) * 3 * n_tris;  // 16-byte aligned tail
+    }
+    k_bake_tris<<<(unsigned)((n_tris + 255) / 256), 256, 0, stream>>>(scene->d, reinterpret_cast<float4*>(scene->baked), (uint32_t)n_tris);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return BVH_CUDA_OK;

@@ -330,6 +330,75 @@ def dragon_scene_instances(lift: float = 0.9):
 
 
 def gbuffer_shadow_rays(n: int, dragon_world_tris: np.ndarray, light_corners: np.ndarray, seed: int = 12,
+                        ground_radius: float = 6.0, ground_frac: float = 0.5, coherent: bool = True):
+    """Config 2 rays as a G-buffer would produce them (raytraced_shadows.wgsl:73-99 runs once per pixel and shades
+    what the camera sees: the model and the ground around it).  `1-ground_frac` of the origins are area-uniform
+    points on the model surface emitted in surface-raster order (stratified along the mesh's own triangle order,
+    which follows its (u,v) parametrisation, so consecutive rays start on neighbouring triangles like neighbouring
+    pixels do); the rest are the pixels of a square raster of the ground plane (y = 0, normal +y) of half-width
+    `ground_radius` around the model, row-major.  Origin is pushed 1e-4 along the geometric normal; direction =
+    (uniform random point on the rect light) - origin, NOT normalised, no t-max.
+    coherent=False applies one fixed random permutation (worst case for SIMT traversal; reported separately).
+    Area-weighted sampling over the whole x200 ground quad (40 000 area units against ~12 for the model) would send
+    99.97 % of the rays from empty ground and make the traversal trivial."""
+    rng = np.random.default_rng(seed)
+    n_ground = int(n * ground_frac)
+    n_model = n - n_ground
+    tris = np.asarray(dragon_world_tris, dtype=np.float64)
+    e1 = tris[:, 1] - tris[:, 0]
+    e2 = tris[:, 2] - tris[:, 0]
+    nrm = np.cross(e1, e2)
+    area = 0.5 * np.linalg.norm(nrm, axis=1)
+    cdf = np.cumsum(area)
+    cdf /= cdf[-1]
+    unit = nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-300)
+    lc = np.asarray(light_corners, dtype=np.float64)
+    o = np.empty((n, 3), dtype=F32)
+    d = np.empty((n, 3), dtype=F32)
+    chunk = 1 << 22
+    for b0 in range(0, n_model, chunk):
+        m = min(chunk, n_model - b0)
+        strat = (np.arange(b0, b0 + m) + rng.random(m)) / n_model  # stratified: monotone in ray index
+        t = np.minimum(np.searchsorted(cdf, strat), len(cdf) - 1)
+        r1 = np.sqrt(rng.random(m))
+        r2 = rng.random(m)
+        p = tris[t, 0] + e1[t] * (r1 * (1 - r2))[:, None] + e2[t] * (r1 * r2)[:, None]
+        o32 = (p + 1e-4 * unit[t]).astype(F32)
+        tgt = lc[0] + (lc[1] - lc[0]) * rng.random(m)[:, None] + (lc[3] - lc[0]) * rng.random(m)[:, None]
+        o[b0:b0 + m] = o32
+        d[b0:b0 + m] = (tgt - o32.astype(np.float64)).astype(F32)
+    side = int(np.ceil(np.sqrt(max(n_ground, 1))))
+    for b0 in range(0, n_ground, chunk):
+        m = min(chunk, n_ground - b0)
+        k = np.arange(b0, b0 + m)
+        px = (k % side + rng.random(m)) / side
+        pz = (k // side + rng.random(m)) / side
+        p = np.stack([(2 * px - 1) * ground_radius, np.full(m, 1e-4), (2 * pz - 1) * ground_radius], axis=1)
+        o32 = p.astype(F32)
+        tgt = lc[0] + (lc[1] - lc[0]) * rng.random(m)[:, None] + (lc[3] - lc[0]) * rng.random(m)[:, None]
+        o[n_model + b0:n_model + b0 + m] = o32
+        d[n_model + b0:n_model + b0 + m] = (tgt - o32.astype(np.float64)).astype(F32)
+    if not coherent:
+        perm = np.random.default_rng(seed + 2000).permutation(n)
+        o, d = o[perm], d[perm]
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+def world_triangles(vertices, indices, transform=None) -> np.ndarray:
+    v = np.asarray(vertices, dtype=np.float64)
+    if transform is not None:
+        t = np.asarray(transform, dtype=np.float64)
+        v = v @ t[:3, :3].T + t[:3, 3]
+    return v[np.asarray(indices, dtype=np.int64).reshape(-1, 3)]
+
+
+def dragon_scene_instances(lift: float = 0.9):
+    """Config 2 scene: mesh 0 = ground plane scaled x200 (raytraced_shadows.rs:36-40), mesh 1 = the dragon-class
+    mesh lifted so that it rests on the ground.  Returns row-major transforms and mesh ids for make_instances."""
+    return np.stack([mat_scale(200.0), mat_translation([0.0, lift, 0.0])]), np.array([0, 1])
+
+
+def gbuffer_shadow_rays(n: int, dragon_world_tris: np.ndarray, light_corners: np.ndarray, seed: int = 12,
                         ground_radius: float = 6.0, ground_frac: float = 0.5):
     """Config 2 rays as a G-buffer would produce them (raytraced_shadows.wgsl:73-99 shades what the camera sees:
     the model and the ground around it): `1-ground_frac` of the origins are uniform points on the dragon-class
