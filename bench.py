@@ -197,6 +197,125 @@ def cpu_baseline_leg(dv, di, pv, pi, inst):
     return build, rays, per_ray, {"S": st["sum_interior_prims"], "M": int(len(dn))}
 
 
+def run_scene1024(args, rank, local_rank, world):
+    """BASELINE config 5: `--meshes` distinct synthetic meshes; BLAS builds sharded over the ranks (LPT), ONE all-gather
+    of {vertices | permuted indices | nodes} slabs over NCCL so every GPU holds the pooled scene, TLAS per rank, then
+    any-hit shadow rays sharded by contiguous ranges (no collective)."""
+    import torch
+    import torch.distributed as dist
+
+    import voidin_b200 as vb
+    from voidin_b200 import multi_gpu as MG
+    from voidin_b200 import scenes as S
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = vb.Context(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_meshes, vside = args.meshes, args.mesh_res
+    uside = 2 * vside
+    tri_counts = [2 * uside * vside - uside] * n_meshes
+    vert_counts = [(uside + 1) * (vside + 1)] * n_meshes
+    plan = MG.lpt_assignment(tri_counts, world)
+    mine, bounds_local = {}, np.zeros((n_meshes, 2, 3), dtype=np.float32)
+    for mid in plan[rank]:
+        v, idx = S.displaced_sphere(vside, uside, 5000 + mid)
+        bounds_local[mid, 0], bounds_local[mid, 1] = v.min(0), v.max(0)
+        mine[mid] = (torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(idx.view(np.int32)).to(dev))
+    b_t = torch.from_numpy(bounds_local).to(dev)
+    if world > 1:
+        dist.all_reduce(b_t, op=dist.ReduceOp.SUM)  # every mesh is owned by exactly one rank
+    bounds = b_t.cpu().numpy()
+    side = int(np.ceil(np.sqrt(n_meshes)))
+    mats = np.stack([S.mat_translation([3.0 * (k % side), 0.0, 3.0 * (k // side)]) for k in range(n_meshes)])
+    inst = S.make_instances(mats, np.arange(n_meshes))
+    d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
+    d_tlas = torch.zeros((2 * n_meshes + 1) * 8, dtype=torch.int32, device=dev)
+    d_kids = torch.zeros((2 * n_meshes + 1) * 2, dtype=torch.int32, device=dev)
+    # rays of this rank's contiguous shard, generated on the device from the global ray index
+    n_total = args.rays * world if args.rays != N_RAYS else (1 << 26) * world
+    rb, re_ = MG.ray_range(rank, world, n_total)
+    gi = torch.arange(rb, re_, device=dev, dtype=torch.int64)
+
+    def u01(salt):
+        x = (gi * 6364136223846793005 + (salt * 1442695040888963407) % (1 << 62)) & 0x7FFFFFFFFFFFFFFF
+        x = ((x >> 29) ^ x) * 0x2545F4914F6CDD1D & 0x7FFFFFFFFFFFFFFF
+        return ((x >> 11) & 0xFFFFFF).to(torch.float32) / 16777216.0
+
+    ext = 3.0 * side
+    o = torch.stack([u01(15) * (ext + 6) - 4.5, torch.full_like(u01(1), -1.6), u01(16) * (ext + 6) - 4.5], dim=1)
+    tgt = torch.stack([ext / 2 - 1.5 + (u01(17) - 0.5) * 20, torch.full_like(u01(1), 30.0), ext / 2 - 1.5 + (u01(18) - 0.5) * 20], dim=1)
+    d_ro = o.contiguous().view(-1)
+    d_rd = (tgt - o).contiguous().view(-1)
+    n_rays = re_ - rb
+    del gi, o, tgt
+    d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
+    build_fn = MG.cuda_build_fn(ctx, stream)
+    state = {}
+
+    def step(ev=None):
+        if ev: ev[0].record()
+        tm = {}
+        sc = MG.build_sharded(mine, n_meshes, vert_counts, tri_counts, bounds, build_fn, rank, world, timings=tm)
+        if ev: ev[1].record()
+        d_infos = torch.from_numpy(sc.mesh_info.view(np.uint8).reshape(-1)).to(dev)
+        ctx.tlas_build_dev(d_inst.data_ptr(), n_meshes, d_infos.data_ptr(), n_meshes, d_tlas.data_ptr(), d_kids.data_ptr(), stream)
+        if ev: ev[2].record()
+        scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), sc.bvh_nodes.data_ptr(),
+                         sc.vertices.data_ptr(), sc.indices.data_ptr(), ctx, device_ptrs=True,
+                         counts={"tlas_nodes": 2 * n_meshes + 1, "instances": n_meshes, "meshes": n_meshes,
+                                 "bvh_nodes": sum(sc.n_nodes), "vertices": sum(vert_counts), "indices": 3 * sum(tri_counts)}, stream=stream)
+        scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
+        if ev: ev[3].record()
+        torch.cuda.synchronize()
+        state["tm"] = tm
+        state["gather_ms"] = tm["after_build"].elapsed_time(tm["after_gather"]) if "after_build" in tm else 0.0
+        scene.close()
+        state["sc"] = None
+        del sc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    barrier()
+    steps = max(1, min(args.steps, 5))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    gms = []
+    l0 = ctx.launch_count
+    for k in range(steps):
+        barrier()
+        step(evs[k])
+        gms.append(state["gather_ms"])
+    barrier()
+    launches = ctx.launch_count - l0
+    tot = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in evs), sum(e[1].elapsed_time(e[2]) for e in evs),
+                        sum(e[2].elapsed_time(e[3]) for e in evs), sum(gms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    b_ms, t_ms, r_ms, g_ms = [float(x) / steps for x in tot.tolist()]
+    occ = float(d_occ.float().mean().item())
+    if rank == 0:
+        total_tris = sum(tri_counts)
+        print(json.dumps({
+            "metric": "multi_mesh_blas_build_Mtris_per_s", "value": total_tris / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "n_gpus": world,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": b_ms + t_ms + r_ms, "higher_is_better": True,
+            "scaling": "strong (build: fixed 1024-mesh scene sharded over ranks) / weak (rays: fixed rays per GPU)", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config5: {n_meshes} meshes x {tri_counts[0]} tris, BLAS builds sharded (LPT) + one NCCL all-gather, {n_total} any-hit rays ray-sharded",
+                       "tris": total_tris, "rays_total": n_total},
+            "phase_ms": {"build_plus_gather": b_ms, "gather_and_assemble": g_ms, "tlas": t_ms, "trace_incl_scene_bake": r_ms},
+            "rays": {"metric": "shadow_ray_Mrays_per_s", "value": n_total / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s", "occluded_frac": occ},
+            "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +324,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="dragon", choices=["dragon", "scene1024"],
+                    help="dragon = BASELINE config 2 (default, the bench line the driver reads); scene1024 = config 5")
+    ap.add_argument("--meshes", type=int, default=1024)
+    ap.add_argument("--mesh-res", type=int, default=181, help="scene1024: vside of each displaced sphere (181 -> 130682 tris)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -214,6 +337,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "scene1024":
+        run_scene1024(args, rank, local_rank, world)
         return
 
     import torch
