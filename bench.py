@@ -253,12 +253,13 @@ def run_scene1024(args, rank, local_rank, world):
     del gi, o, tgt
     d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
     build_fn = MG.cuda_build_fn(ctx, stream)
+    build_batch_fn = MG.cuda_build_batch_fn(ctx, stream)
     state = {}
 
     def step(ev=None):
         if ev: ev[0].record()
         tm = {}
-        sc = MG.build_sharded(mine, n_meshes, vert_counts, tri_counts, bounds, build_fn, rank, world, timings=tm)
+        sc = MG.build_sharded(mine, n_meshes, vert_counts, tri_counts, bounds, build_fn, rank, world, timings=tm, build_batch_fn=build_batch_fn)
         if ev: ev[1].record()
         d_infos = torch.from_numpy(sc.mesh_info.view(np.uint8).reshape(-1)).to(dev)
         ctx.tlas_build_dev(d_inst.data_ptr(), n_meshes, d_infos.data_ptr(), n_meshes, d_tlas.data_ptr(), d_kids.data_ptr(), stream)

@@ -121,6 +121,16 @@ int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_verti
 int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
                             size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
                             void* stream);
+/* MeshPool::add for a whole pooled scene in one call (crates/pools/src/mesh/mod.rs:309-351): every mesh's BLAS is built
+ * in the same passes (a forest build: one root per mesh), which is far cheaper than n_meshes separate builds.
+ * d_vertices / d_indices: pooled buffers; indices are mesh-local vertex ids (the shader adds vertex_offset,
+ * shaders/utils/bvh.wgsl:31) and are permuted in place, mesh by mesh.  d_mesh_info[m] (device, in/out): the caller fills
+ * vertex_offset, base_index, index_count (meshes back to back in order: base_index[0]=0, base_index[m+1] =
+ * base_index[m]+index_count[m]) and min/max; the call fills bvh_index.  d_nodes_out: pooled nodes (mesh m at
+ * bvh_index[m], numbered from 0 inside the mesh), capacity >= 2*n_indices/3; *n_nodes_out = total nodes (host). */
+int bvh_cuda_blas_build_batch_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                                  size_t n_indices, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out,
+                                  size_t nodes_cap, uint32_t* n_nodes_out, void* stream);
 /* Optional: final triangle_indices of the last build (original triangle id per slot), n_tris entries, device->host. */
 int bvh_cuda_blas_last_order(bvh_cuda_ctx* ctx, uint32_t* order_out, size_t n_tris);
 int bvh_cuda_blas_last_stats(const bvh_cuda_ctx* ctx, BvhCudaBuildStats* out);

@@ -202,3 +202,56 @@ def test_trace_empty_and_degenerate_rays(ctx, oracle):
     t, tri, ins = scene.traverse_tlas(ro, rd)
     ot, otri, oins, _, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd)
     assert (tri == otri).all() and (ins == oins).all() and (t == ot).all()
+
+
+def test_blas_batch_forest_build_equals_per_mesh_builds(ctx, oracle):
+    """bvh_cuda_blas_build_batch_dev (MeshPool::add x n in one forest build) must give, mesh by mesh, exactly the nodes
+    and permuted indices of separate builds, pooled with the reference's offsets (mesh/mod.rs:310-331)."""
+    import torch
+    from voidin_b200 import multi_gpu as MG
+
+    meshes = [S.make_plane_mesh(), S.soup(3, 1, 0.05), S.make_uv_sphere(1.0, 1), S.soup(40_000, 2, 0.02), S.soup(300, 3, 0.05),
+              S.make_uv_sphere(1.0, 10), S.soup(2500, 4, 0.05), S.soup(1, 5, 0.05), S.displaced_sphere(36, 72, 9), S.soup(33, 6, 0.05)]
+    dev = torch.device("cuda", 0)
+    tm = [(torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(i.view(np.int32)).to(dev)) for v, i in meshes]
+    outs = MG.cuda_build_batch_fn(ctx)(tm)
+    st = ctx.last_build_stats()
+    total = 0
+    for (v, idx), (nodes, perm) in zip(meshes, outs):
+        rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+        assert rc == 0
+        assert nodes.cpu().numpy().tobytes() == onodes.tobytes()
+        assert (perm.cpu().numpy().view(np.uint32) == oidx).all()
+        total += len(onodes)
+    assert st["n_nodes"] == total
+    # and through the sharded-scene assembly on one rank
+    tri = [i.size // 3 for _, i in meshes]
+    vc = [v.shape[0] for v, _ in meshes]
+    bounds = np.stack([np.stack([v.min(0), v.max(0)]) for v, _ in meshes])
+    sc = MG.build_sharded({k: tm[k] for k in range(len(tm))}, len(tm), vc, tri, bounds, None, 0, 1,
+                          build_batch_fn=MG.cuda_build_batch_fn(ctx))
+    pool = S.MeshPool(lambda v, i: (lambda r: (r[1], r[2]))(oracle.blas_build(v, i)))
+    for v, idx in meshes:
+        pool.add(v, idx)
+    verts, inds, nodes, infos = pool.pooled()
+    assert sc.bvh_nodes.cpu().numpy().tobytes() == nodes.tobytes() and sc.mesh_info.tobytes() == infos.tobytes()
+    assert (sc.indices.cpu().numpy().view(np.uint32) == inds).all()
+
+
+def test_blas_batch_rejects_bad_mesh_table(ctx):
+    import torch
+    from voidin_b200.types import MESH_INFO
+
+    dev = torch.device("cuda", 0)
+    v, idx = S.soup(100, 1, 0.05)
+    info = np.zeros(2, dtype=MESH_INFO)
+    info["index_count"] = [150, 150]
+    info["base_index"] = [0, 151]  # not back to back
+    info["vertex_offset"] = [0, 0]
+    d_info = torch.from_numpy(info.view(np.uint8).reshape(-1)).to(dev)
+    d_v = torch.from_numpy(v.reshape(-1)).to(dev)
+    d_i = torch.from_numpy(idx.view(np.int32)).to(dev)
+    nodes = torch.empty(2 * 100 * 8, dtype=torch.int32, device=dev)
+    with pytest.raises(vb.BvhCudaError) as e:
+        ctx.blas_build_batch_dev(d_v.data_ptr(), 300, d_i.data_ptr(), 300, d_info.data_ptr(), 2, nodes.data_ptr(), 200)
+    assert e.value.code == vb.types.EINVAL

@@ -18,6 +18,7 @@ SYMBOLS = [
     "bvh_cuda_set_profiling",
     "bvh_cuda_blas_build",
     "bvh_cuda_blas_build_dev",
+    "bvh_cuda_blas_build_batch_dev",
     "bvh_cuda_blas_last_order",
     "bvh_cuda_blas_last_stats",
     "bvh_cuda_tlas_build",
@@ -104,6 +105,7 @@ def load() -> C.CDLL:
     lib.bvh_cuda_set_profiling.argtypes = [vp, C.c_int]
     lib.bvh_cuda_blas_build.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p]
     lib.bvh_cuda_blas_build_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p, vp]
+    lib.bvh_cuda_blas_build_batch_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, u32p, vp]
     lib.bvh_cuda_blas_last_order.argtypes = [vp, vp, sz]
     lib.bvh_cuda_blas_last_stats.argtypes = [vp, C.POINTER(BuildStats)]
     lib.bvh_cuda_tlas_build.argtypes = [vp, vp, sz, vp, sz, vp, vp]

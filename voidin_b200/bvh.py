@@ -77,6 +77,14 @@ class Context:
                                                     nodes_cap, C.byref(m), stream))
         return int(m.value)
 
+    def blas_build_batch_dev(self, d_vertices: int, n_vertices: int, d_indices: int, n_indices: int, d_mesh_info: int,
+                             n_meshes: int, d_nodes: int, nodes_cap: int, stream: int = 0) -> int:
+        """Forest build of a pooled scene (MeshPool::add x n_meshes); fills MeshInfo.bvh_index on the device."""
+        m = C.c_uint32(0)
+        self.check(self.lib.bvh_cuda_blas_build_batch_dev(self.h, d_vertices, n_vertices, d_indices, n_indices, d_mesh_info,
+                                                          n_meshes, d_nodes, nodes_cap, C.byref(m), stream))
+        return int(m.value)
+
     def tlas_build_dev(self, d_instances: int, n_inst: int, d_meshes: int, n_mesh: int, d_nodes: int,
                        d_children: int, stream: int = 0):
         self.check(self.lib.bvh_cuda_tlas_build_dev(self.h, d_instances, n_inst, d_meshes, n_mesh, d_nodes,

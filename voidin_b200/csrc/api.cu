@@ -157,8 +157,18 @@ int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n
                             size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out, void* stream) {
     if (!ctx) return BVH_CUDA_EINVAL;
     DeviceGuard g(ctx->device);
-    return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_tris, d_nodes_out, nodes_cap, n_nodes_out,
+    return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_tris, nullptr, 1, d_nodes_out, nodes_cap, n_nodes_out,
                              (cudaStream_t)stream);
+}
+
+int bvh_cuda_blas_build_batch_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                                  size_t n_indices, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out,
+                                  size_t nodes_cap, uint32_t* n_nodes_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!d_mesh_info || n_indices % 3 != 0) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build_batch: null mesh table or n_indices % 3 != 0");
+    DeviceGuard g(ctx->device);
+    return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_indices / 3, d_mesh_info, n_meshes, d_nodes_out, nodes_cap,
+                             n_nodes_out, (cudaStream_t)stream);
 }
 
 int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_vertices, uint32_t* indices, size_t n_tris,
@@ -180,7 +190,7 @@ int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_verti
     CU_CHECK(ctx, cudaMemcpyAsync(dv, vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
     CU_CHECK(ctx, cudaMemcpyAsync(di, indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
     uint32_t m = 0;
-    rc = blas_build_device(ctx, dv, n_vertices, di, n_tris, dn, 2 * n_tris, &m, s);
+    rc = blas_build_device(ctx, dv, n_vertices, di, n_tris, nullptr, 1, dn, 2 * n_tris, &m, s);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CU_CHECK(ctx, cudaMemcpyAsync(nodes_out, dn, sizeof(BvhNode) * m, cudaMemcpyDeviceToHost, s));
     CU_CHECK(ctx, cudaMemcpyAsync(indices, di, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyDeviceToHost, s));

@@ -34,6 +34,7 @@ constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 #define TF_RIGHT 1u
 #define TF_ROOT 2u
+#define TF_MESH_SHIFT 2  // task / record flags: bit0 right child, bit1 root, bits 2.. mesh id (batched builds)
 
 struct Task {  // 32 B
     uint32_t start, n, leftrun, pstart, pleftrun, flags, ready, pad;
@@ -111,19 +112,33 @@ __device__ __forceinline__ float sah_cost(const float* L, const float* R, uint32
 // K1 setup: centroid ((v0+v1)+v2)/3 (blas.rs:70-81), per-triangle AABB folded from +-1e30 (blas.rs:185-186),
 // identity triangle_indices (blas.rs:83), index validation.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mesh_of_tri(const uint32_t* __restrict__ tbase, uint32_t n_meshes, uint32_t tri) {
+    uint32_t lo = 0, hi = n_meshes;  // last mesh with tbase <= tri
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tbase[mid] <= tri) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint32_t nV,
-                                               const uint32_t* __restrict__ I, uint32_t N, float4* cent,
-                                               float4* box, uint32_t* ids, BuildState* st) {
+                                               const uint32_t* __restrict__ I, uint32_t N,
+                                               const uint32_t* __restrict__ tbase, const uint32_t* __restrict__ voff,
+                                               uint32_t n_meshes, float4* cent, float4* box, uint32_t* ids,
+                                               BuildState* st) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const uint32_t vo = (n_meshes > 1) ? voff[mesh_of_tri(tbase, n_meshes, i)] : voff[0];
     uint32_t i0 = I[3 * (size_t)i], i1 = I[3 * (size_t)i + 1], i2 = I[3 * (size_t)i + 2];
-    if (i0 >= nV || i1 >= nV || i2 >= nV) {
+    const uint32_t lim = vo < nV ? nV - vo : 0u;
+    if (i0 >= lim || i1 >= lim || i2 >= lim) {
         atomicOr(&st->err, DERR_BAD_INDEX);
         i0 = i1 = i2 = 0;
     }
-    const float* a = V + 3 * (size_t)i0;
-    const float* b = V + 3 * (size_t)i1;
-    const float* c = V + 3 * (size_t)i2;
+    const uint32_t vb = lim ? vo : 0u;
+    const float* a = V + 3 * (size_t)(vb + i0);
+    const float* b = V + 3 * (size_t)(vb + i1);
+    const float* c = V + 3 * (size_t)(vb + i2);
     float lo[3], hi[3], ce[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint
                         stk_c = leftrun;
                     }
                     sp++;
-                    pstart = abs_start; pleftrun = leftrun; leftrun = leftrun + 1; n = p; fl = 0;
+                    pstart = abs_start; pleftrun = leftrun; leftrun = leftrun + 1; n = p; fl = t.flags & ~3u;
                     descend = true;
                 }
             }
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint
             const uint32_t a = __shfl_sync(FULL_MASK, stk_a, sp);
             pstart = __shfl_sync(FULL_MASK, stk_b, sp);
             pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
-            s = a & 0xFFu; n = a >> 8; leftrun = 0; fl = TF_RIGHT;
+            s = a & 0xFFu; n = a >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
         }
         if (lane < t.n) ids[t.start + lane] = s_gid[w][pay & 31u];
     }
@@ -667,8 +682,8 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, uint32_
             }
             emit_rec(recs, 2 * (start + p) + 1, lo, hi, start, n, t.leftrun, t.pstart, t.pleftrun, t.flags);
             if (p <= 3) A[start] = t.leftrun + 1;
-            push_child(Q, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, 0);
-            push_child(Q, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT);
+            push_child(Q, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, t.flags & ~3u);
+            push_child(Q, st, epoch, start + p, n - p, 0, start, t.leftrun, TF_RIGHT | (t.flags & ~3u));
             atomicAdd(BIG ? &st->t2b_done : &st->t2_done, 1u);
             __threadfence();
             atomicSub(q_pending, 1u);
@@ -932,8 +947,8 @@ __global__ void __launch_bounds__(256) k_t2w(Queues Q, uint32_t* ids, const floa
         if (lane == 0) {
             emit_rec(recs, 2 * (start + p) + 1, nlo, nhi, start, n, leftrun, pstart, pleftrun, tflags);
             if (p <= 3) A[start] = leftrun + 1;
-            push_child(Q, st, epoch, start, p, leftrun + 1, start, leftrun, 0);
-            push_child(Q, st, epoch, start + p, n - p, 0, start, leftrun, TF_RIGHT);
+            push_child(Q, st, epoch, start, p, leftrun + 1, start, leftrun, tflags & ~3u);
+            push_child(Q, st, epoch, start + p, n - p, 0, start, leftrun, TF_RIGHT | (tflags & ~3u));
             atomicAdd(&st->t2w_done, 1u);
             __threadfence();
             atomicSub(&st->w_pending, 1u);
@@ -1468,7 +1483,7 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
             const uint32_t cs = side ? nd.start + p : nd.start;
             const uint32_t cn = side ? nd.n - p : p;
             const uint32_t clr = side ? 0 : nd.leftrun + 1;
-            const uint32_t cfl = side ? TF_RIGHT : 0;
+            const uint32_t cfl = (side ? TF_RIGHT : 0u) | (nd.flags & ~3u);
             if (cn > T2B_CAP) {
                 const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
                 if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
@@ -1484,7 +1499,7 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
 }
 
 // One block: tile_base prefix of the next level's node list; decides whether the level needs the tile scan.
-__device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other) {
+__device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other, bool count_level = true) {
     __shared__ uint32_t s_part[1024];
     __shared__ uint32_t s_max;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -1508,7 +1523,7 @@ __device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st,
         st->lv_tiles[slot] = acc;
         st->lv_maxtiles[slot] = s_max;
         st->lv_count[other] = 0;
-        st->levels_done += 1;
+        if (count_level) st->levels_done += 1;
     }
     __syncthreads();
     uint32_t acc = s_part[tid];
@@ -1518,6 +1533,9 @@ __device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st,
     }
     __syncthreads();
 }
+
+// Tile prefix of the root level (one block).
+__global__ void __launch_bounds__(1024) k_t1_level0(LevelNode* nodes, BuildState* st) { p_t1_nextlevel(nodes, st, 0, 1, false); }
 
 // The whole grid-wide tier as ONE cooperative persistent kernel: every phase boundary is a grid barrier
 // instead of a kernel launch, and the level loop never returns to the host.  ~52 barriers per level.
@@ -1635,29 +1653,33 @@ __global__ void __launch_bounds__(1024) k_scan_apply(uint32_t* x, uint32_t n, co
 // Emit: records -> BvhNode[] in DFS pre-order pair numbering (blas.rs:90,110-112,125-126).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_emit(const uint4* __restrict__ recs, uint32_t n_slots,
-                                              const uint32_t* __restrict__ P, BvhNode* nodes, uint32_t nodes_cap,
+                                              const uint32_t* __restrict__ P, const uint32_t* __restrict__ tbase,
+                                              const uint32_t* __restrict__ node_base, BvhNode* nodes, uint32_t nodes_cap,
                                               BuildState* st) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long s_add = 0;
     uint32_t i_add = 0;
-    if (slot == 0 && nodes_cap > 1) {
-        uint4* z = reinterpret_cast<uint4*>(nodes + 1);  // node 1 is never used (blas.rs:90)
-        z[0] = make_uint4(0, 0, 0, 0);
-        z[1] = make_uint4(0, 0, 0, 0);
-    }
     if (slot < n_slots) {
         const uint4 r1 = recs[3 * (size_t)slot + 1];
         if (r1.w != 0) {
             const uint4 r0 = recs[3 * (size_t)slot], r2 = recs[3 * (size_t)slot + 2];
             const uint32_t start = r0.w, count = r1.w;
-            const uint32_t pos = (r2.w & TF_ROOT) ? 0u : 2u + 2u * (P[r2.y] + r2.z) + (r2.w & TF_RIGHT);
+            const uint32_t mesh = r2.w >> TF_MESH_SHIFT;
+            const uint32_t mb = tbase[mesh], Pb = P[mb], nb = node_base[mesh];  // numbering restarts per mesh
+            const bool root = (r2.w & TF_ROOT) != 0;
+            const uint32_t pos = nb + (root ? 0u : 2u + 2u * (P[r2.y] - Pb + r2.z) + (r2.w & TF_RIGHT));
             uint32_t lf, cn;
-            if (count > 3) { lf = 2u + 2u * (P[start] + r2.x); cn = 0; s_add = count; i_add = 1; }
-            else { lf = start; cn = count; }
-            if (pos < nodes_cap) {
+            if (count > 3) { lf = 2u + 2u * (P[start] - Pb + r2.x); cn = 0; s_add = count; i_add = 1; }
+            else { lf = start - mb; cn = count; }
+            if (pos < nodes_cap && nb + 1 < nodes_cap) {
                 uint4* o = reinterpret_cast<uint4*>(nodes + pos);
                 o[0] = make_uint4(r0.x, r0.y, r0.z, lf);
                 o[1] = make_uint4(r1.x, r1.y, r1.z, cn);
+                if (root) {  // node 1 of every mesh is never used (blas.rs:90)
+                    uint4* z = reinterpret_cast<uint4*>(nodes + nb + 1);
+                    z[0] = make_uint4(0, 0, 0, 0);
+                    z[1] = make_uint4(0, 0, 0, 0);
+                }
             } else atomicOr(&st->err, DERR_QUEUE);
         }
     }
@@ -1671,6 +1693,20 @@ __global__ void __launch_bounds__(256) k_emit(const uint4* __restrict__ recs, ui
     if (threadIdx.x == 0 && s_i) { atomicAdd(&st->sum_interior, s_s); atomicAdd(&st->interior_total, s_i); }
 }
 
+// Per-mesh node counts M_m = 2 + 2 * interior_m (blas.rs:93) from the scanned A, written where the scan kernels
+// will turn them into node_base; also validates nothing.
+__global__ void __launch_bounds__(256) k_mesh_counts(const uint32_t* __restrict__ P, const uint32_t* __restrict__ tbase,
+                                                     uint32_t n_meshes, uint32_t* node_base) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n_meshes) node_base[m] = 2u + 2u * (P[tbase[m + 1]] - P[tbase[m]]);
+    if (m == n_meshes) node_base[m] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_write_bvh_index(MeshInfo* infos, const uint32_t* __restrict__ node_base, uint32_t n_meshes) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n_meshes) infos[m].bvh_index = node_base[m];
+}
+
 // indices[i] <- indices_in[order[i]]  (blas.rs:95-100)
 __global__ void __launch_bounds__(256) k_permute_gather(const uint32_t* __restrict__ I, const uint32_t* __restrict__ order,
                                                         uint32_t N, uint32_t* tmp) {
@@ -1682,37 +1718,47 @@ __global__ void __launch_bounds__(256) k_permute_gather(const uint32_t* __restri
     tmp[3 * (size_t)i + 2] = I[s + 2];
 }
 
-__global__ void __launch_bounds__(256) k_init_state(BuildState* st, Task* first_qb, Task* first_q, Task* first_qw,
-                                                    Task* first_t3, LevelNode* first_lv, uint32_t N, uint32_t epoch) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    BuildState s{};
-    Task root{};
-    root.start = 0; root.n = N; root.leftrun = 0; root.pstart = 0; root.pleftrun = 0; root.flags = TF_ROOT;
-    root.ready = epoch; root.pad = 0;
-    if (N > T2B_CAP) {
+__global__ void k_init_state(BuildState* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { BuildState s{}; *st = s; }
+}
+
+// Mesh table of a batched build: triangle base and vertex offset per mesh from the caller's MeshInfo array (the
+// meshes must be pooled back to back in order, as MeshPool::add lays them out, mesh/mod.rs:310-331).
+__global__ void __launch_bounds__(256) k_mesh_table(const MeshInfo* __restrict__ infos, uint32_t n_meshes, uint32_t n_indices,
+                                                    uint32_t* tbase, uint32_t* voff, BuildState* st) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > n_meshes) return;
+    if (m == n_meshes) { tbase[m] = n_indices / 3; return; }
+    const MeshInfo mi = infos[m];
+    const uint32_t next = (m + 1 < n_meshes) ? infos[m + 1].base_index : n_indices;
+    if (mi.base_index % 3 != 0 || mi.index_count % 3 != 0 || mi.index_count == 0 || mi.base_index + mi.index_count != next ||
+        (m == 0 && mi.base_index != 0) || mi.vertex_offset < 0)
+        atomicOr(&st->err, DERR_BAD_INDEX);
+    tbase[m] = mi.base_index / 3;
+    voff[m] = (uint32_t)mi.vertex_offset;
+}
+
+__global__ void k_single_mesh_table(uint32_t N, uint32_t* tbase, uint32_t* voff) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { tbase[0] = 0; tbase[1] = N; voff[0] = 0; }
+}
+
+// One root per mesh, routed to the tier of its size.
+__global__ void __launch_bounds__(256) k_roots(const uint32_t* __restrict__ tbase, uint32_t n_meshes, Queues Q, LevelNode* lv0,
+                                               uint32_t lv_cap, BuildState* st, uint32_t epoch) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_meshes) return;
+    const uint32_t start = tbase[m], n = tbase[m + 1] - tbase[m];
+    const uint32_t flags = TF_ROOT | (m << TF_MESH_SHIFT);
+    if (n == 0) { atomicOr(&st->err, DERR_BAD_INDEX); return; }
+    if (n > T2B_CAP) {
+        const uint32_t idx = atomicAdd(&st->lv_count[0], 1u);
+        if (idx >= lv_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
         LevelNode l;
-        l.start = 0; l.n = N; l.leftrun = 0; l.pstart = 0; l.pleftrun = 0; l.flags = TF_ROOT; l.tile_base = 0; l.pad = 0;
-        first_lv[0] = l;
-        s.lv_count[0] = 1;
-        s.lv_tiles[0] = (N + T1_TILE - 1) / T1_TILE;
-        s.lv_maxtiles[0] = s.lv_tiles[0];
-    } else if (N > T2_CAP) {
-        first_qb[0] = root;
-        s.b_tail = 1;
-        s.b_pending = 1;
-    } else if (N > T2W_CAP) {
-        first_q[0] = root;
-        s.q_tail = 1;
-        s.q_pending = 1;
-    } else if (N > T3_MAX) {
-        first_qw[0] = root;
-        s.w_tail = 1;
-        s.w_pending = 1;
+        l.start = start; l.n = n; l.leftrun = 0; l.pstart = start; l.pleftrun = 0; l.flags = flags; l.tile_base = 0; l.pad = 0;
+        lv0[idx] = l;
     } else {
-        first_t3[0] = root;
-        s.t3_count = 1;
+        push_child(Q, st, epoch, start, n, 0, start, 0, flags);
     }
-    *st = s;
 }
 
 }  // namespace
@@ -1777,29 +1823,32 @@ struct Carver {
 }  // namespace
 
 int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
-                      size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
-                      cudaStream_t stream) {
-    if (!d_vertices || !d_indices || !d_nodes_out || n_tris == 0 || n_vertices == 0)
+                      size_t n_tris, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out, size_t nodes_cap,
+                      uint32_t* n_nodes_out, cudaStream_t stream) {
+    if (!d_vertices || !d_indices || !d_nodes_out || n_tris == 0 || n_vertices == 0 || n_meshes == 0)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: empty mesh or null pointer");
-    if (n_tris > 0x7FFFFFFFull / 2 || n_vertices > 0xFFFFFFFFull)
+    if (n_tris > 0x7FFFFFFFull / 2 || n_vertices > 0xFFFFFFFFull || n_meshes > (1ull << 29) || n_meshes > n_tris)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: mesh too large (2*n_tris must fit in 31 bits)");
     if (nodes_cap < 2 * n_tris)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: nodes_cap must be >= 2*n_tris");
     const uint32_t N = (uint32_t)n_tris;
+    const uint32_t NM = (uint32_t)n_meshes;
     const uint32_t max_large = N / T2B_CAP + 2;
     const uint32_t max_tiles = N / T1_TILE + max_large + 2;
-    const uint32_t qb_cap = N / 256 + 4096; // nodes with 2049..16384 primitives
-    const uint32_t q_cap = N / 32 + 4096;   // nodes with 257..2048 primitives (typically ~N/100)
-    const uint32_t qw_cap = N / 4 + 4096;   // nodes with 33..T2W_CAP primitives (typically ~N/28)
-    const uint32_t t3_cap = N + 16;
+    const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
+    const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
+    const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
+    const uint32_t t3_cap = N + NM + 16;
     const uint32_t scan_n = N + 1;
     const uint32_t scan_blocks = (scan_n + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t mscan_n = NM + 1;
+    const uint32_t mscan_blocks = (mscan_n + SCAN_TILE - 1) / SCAN_TILE;
 
     // carve the workspace (first pass sizes, second pass assigns)
     float4 *cent = nullptr, *box = nullptr;
     uint4* tile_desc = nullptr;
-    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr,  *barrier = nullptr,
-             *scan_sums = nullptr, *scan_total = nullptr;
+    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr, *barrier = nullptr,
+             *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
     Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr;
@@ -1831,13 +1880,17 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         barrier = c.take<uint32_t>(64);
         scan_sums = c.take<uint32_t>(scan_blocks + 1);
         scan_total = c.take<uint32_t>(4);
+        tbase = c.take<uint32_t>(NM + 1);
+        voff = c.take<uint32_t>(NM + 1);
+        node_base = c.take<uint32_t>(mscan_n);
+        mscan_sums = c.take<uint32_t>(mscan_blocks + 1);
         if (pass == 0) {
             int rc = ctx_reserve(ctx, c.off + 256);
             if (rc) return rc;
         }
     }
-    // Task slots are marked ready with a build-unique number so queues never need clearing; the counter is
-    // process-wide because a freed workspace of one context can be handed to another by cudaMalloc.
+    // Task slots are marked ready with a build-unique number; the counter is process-wide because a freed workspace
+    // of one context can be handed to another by cudaMalloc.
     static std::atomic<uint32_t> g_epoch{0};
     const uint32_t epoch = 0x80000000u | (g_epoch.fetch_add(1) + 1);
     ctx->epoch = epoch;
@@ -1852,12 +1905,16 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const bool prof = ctx->profiling;
     if (prof) cudaEventRecord(ctx->ev[0], stream);
     Queues Q{qb, q, qw, t3, qb_cap, q_cap, qw_cap, t3_cap};
-    k_init_state<<<1, 32, 0, stream>>>(st, qb, q, qw, t3, lv[0], N, epoch);
-    k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, cent, box, ids0, st);
-    launches += 2;
+    k_init_state<<<1, 32, 0, stream>>>(st);
+    if (d_mesh_info) k_mesh_table<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(d_mesh_info, NM, 3 * N, tbase, voff, st);
+    else k_single_mesh_table<<<1, 32, 0, stream>>>(N, tbase, voff);
+    k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, tbase, voff, NM, cent, box, ids0, st);
+    k_roots<<<(NM + 255) / 256, 256, 0, stream>>>(tbase, NM, Q, lv[0], max_large, st, epoch);
+    k_t1_level0<<<1, 1024, 0, stream>>>(lv[0], st);
+    launches += 5;
     if (prof) cudaEventRecord(ctx->ev[1], stream);
 
-    // ---- T1: grid-wide tier, one cooperative persistent launch ----
+    // ---- T1: grid-wide tier, one cooperative persistent launch (exits at once when no node is that large) ----
     if (N > (uint32_t)T2B_CAP) {
         CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, 256, stream));
         T1Args g;
@@ -1880,7 +1937,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     }
 
     if (prof) cudaEventRecord(ctx->ev[2], stream);
-    // ---- T2: persistent blocks on the device task queue ----
+    // ---- T2: persistent blocks on the device task queues ----
     {
         const int blocks = ctx->sm_count * (ctx->t2_blocks_per_sm > 0 ? ctx->t2_blocks_per_sm : 1);
         if (N > (uint32_t)T2_CAP) {
@@ -1892,7 +1949,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         launches++;
     }
     if (prof) cudaEventRecord(ctx->ev[6], stream);
-    // ---- T2w: persistent warps on the second task queue ----
+    // ---- T2w: persistent warps on the third task queue ----
     {
         const int blocks = ctx->sm_count * (ctx->t2w_blocks_per_sm > 0 ? ctx->t2w_blocks_per_sm : 1);
         k_t2w<T2W_CAP><<<blocks, 256, 0, stream>>>(Q, ids0, cent, box, recs, A, st, epoch);
@@ -1910,28 +1967,35 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     k_scan_reduce<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
     k_scan_top<<<1, 1024, 0, stream>>>(scan_sums, scan_blocks, scan_total);
     k_scan_apply<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
-    k_emit<<<(2 * N + 255) / 256, 256, 0, stream>>>(recs, 2 * N, A, d_nodes_out, (uint32_t)(nodes_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : nodes_cap), st);
+    // per-mesh node bases (pooled bvh_index, mesh/mod.rs:322-325): exclusive scan of M_m over the meshes
+    k_mesh_counts<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(A, tbase, NM, node_base);
+    k_scan_reduce<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
+    k_scan_top<<<1, 1024, 0, stream>>>(mscan_sums, mscan_blocks, scan_total + 1);
+    k_scan_apply<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
+    k_emit<<<(2 * N + 255) / 256, 256, 0, stream>>>(recs, 2 * N, A, tbase, node_base, d_nodes_out,
+                                                    (uint32_t)(nodes_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : nodes_cap), st);
+    if (d_mesh_info) { k_write_bvh_index<<<(NM + 255) / 256, 256, 0, stream>>>(d_mesh_info, node_base, NM); launches++; }
     // permute the caller's index buffer in place (box[] is dead by now and is reused as the staging copy)
     uint32_t* tmp = reinterpret_cast<uint32_t*>(box);
     k_permute_gather<<<(N + 255) / 256, 256, 0, stream>>>(d_indices, ids0, N, tmp);
     CU_CHECK(ctx, cudaMemcpyAsync(d_indices, tmp, sizeof(uint32_t) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, stream));
-    launches += 5;
+    launches += 9;
     if (prof) cudaEventRecord(ctx->ev[5], stream);
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
-    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaStreamSynchronize(stream));
     CU_CHECK(ctx, cudaGetLastError());
     const BuildState* hs = reinterpret_cast<const BuildState*>(ctx->h_pin);
     ctx->launches += launches;
     ctx->d_last_order = ids0;
     ctx->last_n = N;
-    if (hs->err & DERR_BAD_INDEX) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: vertex index out of range");
+    if (hs->err & DERR_BAD_INDEX) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: vertex index out of range or inconsistent mesh table");
     if (hs->err & DERR_DEGENERATE)
         return ctx_fail(ctx, BVH_CUDA_EDEGENERATE, "blas_build: a node with >3 triangles has no finite-cost split (the reference would not terminate)");
     if (hs->err) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: device task queue overflow or stall");
     const uint32_t interior = ctx->h_pin[64];
     stats.interior_nodes = interior;
-    stats.n_nodes = 2 + 2 * interior;
+    stats.n_nodes = ctx->h_pin[65];  // sum over meshes of 2 + 2 * interior_m
     stats.sum_interior_prims = hs->sum_interior;
     stats.grid_levels = hs->levels_done;
     stats.big_block_tasks = hs->t2b_done;
@@ -1952,5 +2016,6 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     ctx->stats = stats;
     if (n_nodes_out) *n_nodes_out = stats.n_nodes;
     if (hs->interior_total != interior) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: internal node count mismatch");
+    if (stats.n_nodes != 2 * NM + 2 * interior) return ctx_fail(ctx, BVH_CUDA_ECUDA, "blas_build: per-mesh node count mismatch");
     return BVH_CUDA_OK;
 }

@@ -65,8 +65,8 @@ int ctx_stage_reserve(bvh_cuda_ctx* ctx, size_t bytes);
 
 // implemented in blas_build.cu / tlas.cu / trace.cu
 int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
-                      size_t n_tris, BvhNode* d_nodes_out, size_t nodes_cap, uint32_t* n_nodes_out,
-                      cudaStream_t stream);
+                      size_t n_tris, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out, size_t nodes_cap,
+                      uint32_t* n_nodes_out, cudaStream_t stream);
 int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
                       size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, cudaStream_t stream);
 int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t stream);

@@ -56,7 +56,7 @@ class PooledScene:
 def build_sharded(meshes_of_rank: dict[int, tuple[torch.Tensor, torch.Tensor]], n_meshes: int,
                   vert_counts: Sequence[int], tri_counts: Sequence[int], mesh_bounds: np.ndarray,
                   build_fn: Callable[[torch.Tensor, torch.Tensor], tuple[torch.Tensor, torch.Tensor]],
-                  rank: int, world: int, group=None, timings: dict | None = None) -> PooledScene:
+                  rank: int, world: int, group=None, timings: dict | None = None, build_batch_fn=None) -> PooledScene:
     """meshes_of_rank: mesh id -> (vertices float32 [V*3], indices int32 [3N]) for the ids lpt_assignment gives this
     rank.  vert_counts / tri_counts / mesh_bounds ([n_meshes,2,3] min/max over all positions, mesh/mod.rs:22-27) are
     known to every rank.  build_fn(vertices, indices) -> (nodes int32 [M*8], permuted indices int32 [3N])."""
@@ -67,10 +67,16 @@ def build_sharded(meshes_of_rank: dict[int, tuple[torch.Tensor, torch.Tensor]], 
 
     # ---- local builds ----
     built = {}
-    for mid in mine:
-        v, idx = meshes_of_rank[mid]
-        nodes, perm = build_fn(v, idx)
-        built[mid] = (v.reshape(-1), perm.reshape(-1), nodes.reshape(-1))
+    if build_batch_fn is not None and mine:
+        # one forest build for all local meshes (bvh_cuda_blas_build_batch_dev)
+        outs = build_batch_fn([meshes_of_rank[mid] for mid in mine])
+        for mid, (nodes, perm) in zip(mine, outs):
+            built[mid] = (meshes_of_rank[mid][0].reshape(-1), perm.reshape(-1), nodes.reshape(-1))
+    else:
+        for mid in mine:
+            v, idx = meshes_of_rank[mid]
+            nodes, perm = build_fn(v, idx)
+            built[mid] = (v.reshape(-1), perm.reshape(-1), nodes.reshape(-1))
     counts = torch.zeros(n_meshes, dtype=torch.int64, device=dev)
     for mid in mine:
         counts[mid] = built[mid][2].numel() // 8
@@ -137,5 +143,36 @@ def cuda_build_fn(ctx, stream: int = 0):
         nodes = torch.empty(2 * n * 8, dtype=torch.int32, device=v.device)
         m = ctx.blas_build_dev(v.data_ptr(), v.numel() // 3, work.data_ptr(), n, nodes.data_ptr(), 2 * n, stream)
         return nodes[: m * 8], work
+
+    return fn
+
+
+def cuda_build_batch_fn(ctx, stream: int = 0):
+    """build_batch_fn for CUDA tensors: pools the given meshes (vertex_offset / base_index prefix sums, as
+    MeshPool::add does), runs ONE forest build and splits the pooled outputs back per mesh."""
+
+    def fn(meshes):
+        dev = meshes[0][0].device
+        vcount = [m[0].numel() // 3 for m in meshes]
+        icount = [m[1].numel() for m in meshes]
+        info = np.zeros(len(meshes), dtype=MESH_INFO)
+        info["index_count"] = icount
+        info["vertex_offset"] = np.concatenate([[0], np.cumsum(vcount)[:-1]])
+        info["base_index"] = np.concatenate([[0], np.cumsum(icount)[:-1]])
+        d_info = torch.from_numpy(info.view(np.uint8).reshape(-1)).to(dev)
+        verts = torch.cat([m[0].reshape(-1) for m in meshes])
+        inds = torch.cat([m[1].reshape(-1) for m in meshes])  # fresh buffer: permuted in place
+        n_tris = inds.numel() // 3
+        nodes = torch.empty(2 * n_tris * 8, dtype=torch.int32, device=dev)
+        ctx.blas_build_batch_dev(verts.data_ptr(), verts.numel() // 3, inds.data_ptr(), inds.numel(), d_info.data_ptr(),
+                                 len(meshes), nodes.data_ptr(), 2 * n_tris, stream)
+        bvh_index = d_info.cpu().numpy().view(MESH_INFO)["bvh_index"].astype(np.int64)
+        total = int(ctx.last_build_stats()["n_nodes"])
+        ends = np.concatenate([bvh_index[1:], [total]])
+        out = []
+        for k in range(len(meshes)):
+            b0 = int(info["base_index"][k])
+            out.append((nodes[8 * int(bvh_index[k]): 8 * int(ends[k])], inds[b0: b0 + icount[k]]))
+        return out
 
     return fn
