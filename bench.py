@@ -220,16 +220,21 @@ def run_scene1024(args, rank, local_rank, world):
     vert_counts = [(uside + 1) * (vside + 1)] * n_meshes
     plan = MG.lpt_assignment(tri_counts, world)
     mine, bounds_local = {}, np.zeros((n_meshes, 2, 3), dtype=np.float32)
+    side = int(np.ceil(np.sqrt(n_meshes)))
     for mid in plan[rank]:
         v, idx = S.displaced_sphere(vside, uside, 5000 + mid)
+        # Each mesh is authored at its lattice cell (spacing 3) and instanced with the identity.  Tlas::build seeds every
+        # leaf box with the UNTRANSFORMED local mesh box (tlas.rs:39), so translating centred meshes by their instance
+        # transform instead would stretch every leaf box from the origin to the instance and make the TLAS useless
+        # (measured with the oracle: ~200 instance entries per ray on this scene).
+        v = (v + np.array([3.0 * (mid % side), 0.0, 3.0 * (mid // side)], dtype=np.float32)).astype(np.float32)
         bounds_local[mid, 0], bounds_local[mid, 1] = v.min(0), v.max(0)
         mine[mid] = (torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(idx.view(np.int32)).to(dev))
     b_t = torch.from_numpy(bounds_local).to(dev)
     if world > 1:
         dist.all_reduce(b_t, op=dist.ReduceOp.SUM)  # every mesh is owned by exactly one rank
     bounds = b_t.cpu().numpy()
-    side = int(np.ceil(np.sqrt(n_meshes)))
-    mats = np.stack([S.mat_translation([3.0 * (k % side), 0.0, 3.0 * (k // side)]) for k in range(n_meshes)])
+    mats = np.stack([np.eye(4)] * n_meshes)
     inst = S.make_instances(mats, np.arange(n_meshes))
     d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
     d_tlas = torch.zeros((2 * n_meshes + 1) * 8, dtype=torch.int32, device=dev)

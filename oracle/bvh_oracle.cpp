@@ -531,6 +531,7 @@ struct ModelBuilder {
 // Traversal
 // ---------------------------------------------------------------------------------------------
 constexpr int STACK_CAP = 64;  // reference: 32 (blas.rs:299) / 24 (stack.wgsl:1); overflow there is UB
+constexpr int TLAS_STACK_CAP = 256;  // the reference's agglomerative TLAS can be deep (88 levels on a 32x32 lattice)
 
 struct RDist {  // Dist enum, intersection.rs:22-26 with derive(PartialOrd): Hit(_) < Miss
     bool hit;
@@ -725,7 +726,7 @@ inline V3 mat_mul(const float* m, V3 p, float w) {
 inline void traverse_tlas_w(const Scene& sc, V3 eye, V3 dir, float tmax, bool any_hit, float* t_out,
                             uint32_t* tri_out, uint32_t* inst_out, bool* hit_out, OracleRayStats* st) {
     V3 inv = {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
-    uint32_t stack[STACK_CAP];
+    uint32_t stack[TLAS_STACK_CAP];
     int head = 0;
     stack[head++] = 0;
     float dist = tmax;
@@ -764,8 +765,8 @@ inline void traverse_tlas_w(const Scene& sc, V3 eye, V3 dir, float tmax, bool an
                 std::swap(min_dist, max_dist);
             }
             if (min_dist >= dist) continue;
-            if (max_dist < dist && head < STACK_CAP) stack[head++] = max_index;
-            if (head < STACK_CAP) stack[head++] = min_index;
+            if (max_dist < dist && head < TLAS_STACK_CAP) stack[head++] = max_index;
+            if (head < TLAS_STACK_CAP) stack[head++] = min_index;
             if (st && (uint64_t)head > st->max_stack) st->max_stack = head;
         }
     }

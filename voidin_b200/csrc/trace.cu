@@ -13,7 +13,8 @@
 
 namespace {
 
-constexpr int STACK_CAP = 64;
+constexpr int STACK_CAP = 64;        // BLAS stack (reference: 32 in blas.rs:299, 24 in stack.wgsl:1)
+constexpr int TLAS_STACK_CAP = 256;  // the reference's agglomerative TLAS can be deep (88 levels on a 32x32 lattice)
 constexpr float MAXD = 1e30f;
 
 struct NodeW {  // BvhNode / TlasNode as two float4
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                                                      uint8_t* occ_out, unsigned long long* next_ray) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t tstack[STACK_CAP], bstack[STACK_CAP];
+    uint32_t tstack[TLAS_STACK_CAP], bstack[STACK_CAP];
     int th = 0, bh = 0;
     bool active = false;
     size_t r = 0;
@@ -282,8 +283,8 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                         const float td = min_dist; min_dist = max_dist; max_dist = td;
                     }
                     if (min_dist >= dist) continue;
-                    if (!twin && max_dist < dist && th < STACK_CAP) tstack[th++] = max_index;
-                    if (th < STACK_CAP) tstack[th++] = min_index;
+                    if (!twin && max_dist < dist && th < TLAS_STACK_CAP) tstack[th++] = max_index;
+                    if (th < TLAS_STACK_CAP) tstack[th++] = min_index;
                 }
             }
             // traverse_bvh (bvh.wgsl:35-76): interior nodes until a leaf
