@@ -67,12 +67,16 @@ def ray_bytes(counters_per_ray, out_bytes):
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up until after the timed region;
+    the summary uses the samples whose arrival time falls inside the timed window (falls back to all samples taken
+    while the GPU was busy when the window is shorter than the sampling period)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.rows, self.proc = [], None
+        self.t0 = self.t1 = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -81,34 +85,41 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        parsed = []
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                parsed.append((ts, float(f[0]), float(f[1]), float(f[2]), [nme for k, nme in enumerate(names) if f[3 + k].lower().startswith("active")]))
             except ValueError:
                 continue
-            for k, nme in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        if not sm:
+        if not parsed:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(pw)}
+        inwin = [p for p in parsed if self.t0 is not None and self.t0 - 0.05 <= p[0] <= self.t1 + 0.1]
+        src = "timed window"
+        if not inwin:
+            pmax = max(p[3] for p in parsed)
+            inwin = [p for p in parsed if p[3] > 0.6 * pmax] or parsed
+            src = "whole run, busy samples (timed window shorter than the sampling period)"
+        reasons = sorted({r for p in inwin for r in p[4]})
+        return {"sm_mhz": float(np.median([p[1] for p in inwin])), "sm_max_mhz": float(max(p[2] for p in parsed)), "reasons": reasons,
+                "samples": len(inwin), "samples_total": len(parsed), "power_w_max": max(p[3] for p in inwin), "source": src}
 
 
 def run_reference(args, rank, world):
@@ -433,12 +444,12 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cpu_build, cpu_rays, per_ray, _ = cpu_baseline_leg(dv, di, pv, pi, inst)
 
+    sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step_dev()
     barrier()
 
     # ---- device-resident timing ----
-    sampler = ClockSampler(local_rank)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     launches0 = ctx.launch_count
     barrier()
@@ -451,7 +462,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop()
+    sampler.window(t_wall0, t_wall0 + t_wall)
     b_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
     t_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
     r_ms = np.array([e[2].elapsed_time(e[3]) for e in evs])
@@ -507,6 +518,7 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_b, e2e_r = [float(x) for x in e2e_t.tolist()]
     m_dragon = int(m.value)
+    clocks = sampler.stop()
 
     if rank == 0:
         peak, peak_src = peaks()
