@@ -68,7 +68,8 @@ struct BuildState {
     uint32_t t2b_done;
     uint32_t t2w_done;
     uint32_t levels_done;
-    uint32_t pad[2];
+    uint32_t t3_inline;
+    uint32_t pad[1];
 };
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -156,9 +157,167 @@ __global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint
 // ------------------------------------------------------------------------------------------------
 // T3: one warp builds a whole sub-tree of <= 32 primitives.  Lane j owns slot j of the range.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint32_t* ids,
-                                            const float4* __restrict__ cent, const float4* __restrict__ box,
-                                            uint4* recs, uint32_t* A, BuildState* st) {
+// Shared-memory scratch of one warp for a <=32-primitive sub-tree.
+struct T3Smem {
+    float (*box)[32];   // [6][32]
+    float (*cent)[32];  // [3][32]
+    uint32_t* gid;      // [32]
+    uint8_t* tab;       // [32]
+    uint16_t* pay;      // [32]
+};
+
+// One warp builds the whole sub-tree of task `t` (<= 32 primitives).  Lane j owns slot j of the range.
+__device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint32_t lane, uint32_t* ids,
+                                           const float4* __restrict__ cent, const float4* __restrict__ box, uint4* recs,
+                                           uint32_t* A, BuildState* st) {
+    float (*sm_box)[32] = sm.box;
+    float (*sm_cent)[32] = sm.cent;
+    uint32_t* sm_gid = sm.gid;
+    uint8_t* sm_tab = sm.tab;
+    uint16_t* sm_pay = sm.pay;
+    __syncwarp();
+    if (lane < t.n) {
+        const uint32_t g = __ldcg(&ids[t.start + lane]);
+        const float4 c = cent[g];
+        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+        sm_box[0][lane] = b0.x; sm_box[1][lane] = b0.y; sm_box[2][lane] = b0.z;
+        sm_box[3][lane] = b1.x; sm_box[4][lane] = b1.y; sm_box[5][lane] = b1.z;
+        sm_cent[0][lane] = c.x; sm_cent[1][lane] = c.y; sm_cent[2][lane] = c.z;
+        sm_gid[lane] = g;
+    }
+    __syncwarp();
+    uint32_t pay = lane;  // bits 0-4: local primitive, 5-13: plane counts of the current node
+    uint32_t s = 0, n = t.n, leftrun = t.leftrun, pstart = t.pstart, pleftrun = t.pleftrun, fl = t.flags;
+    uint32_t stk_a = 0, stk_b = 0, stk_c = 0;  // lane i holds stack entry i
+    int sp = 0;
+
+    for (;;) {
+        const bool active = lane >= s && lane < s + n;
+        const uint32_t e = pay & 31u;
+        const uint32_t abs_start = t.start + s;
+        // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
+        float lo[3], hi[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t mn = active ? f2o(sm_box[c][e]) : ENC_POS_INIT;
+            uint32_t mx = active ? f2o(sm_box[3 + c][e]) : ENC_NEG_INIT;
+            mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
+            mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
+            lo[c] = o2f(mn);
+            hi[c] = o2f(mx);
+        }
+        bool descend = false;
+        if (n <= 3) {  // leaf (blas.rs:106-109)
+            if (lane == 0) emit_rec(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
+        } else {
+            // centroid bounds (blas.rs:142)
+            float cmin[3], cmax[3], cc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                cc[c] = active ? sm_cent[c][e] : 0.0f;
+                uint32_t mn = active ? f2o(cc[c]) : ENC_POS_INIT;
+                uint32_t mx = active ? f2o(cc[c]) : ENC_NEG_INIT;
+                mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
+                mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
+                cmin[c] = o2f(mn);
+                cmax[c] = o2f(mx);
+            }
+            pay = e | (plane_counts(cc[0], cc[1], cc[2], cmin, cmax) << 5);
+
+            const uint32_t j = lane - s;
+            const uint32_t nmask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            // closed form of partition_shuffle (blas.rs:168-182) on the current order
+            auto do_shuffle = [&](uint32_t a, uint32_t b) -> uint32_t {
+                const bool L = active && (((pay >> (5 + 3 * a)) & 7u) < b);
+                const uint32_t Lm = __ballot_sync(FULL_MASK, L) >> s;
+                const uint32_t Rm = ~Lm & nmask;
+                const uint32_t below = active ? ((1u << j) - 1u) : 0u;
+                const uint32_t RF = __popc(Rm & below), LF = j - RF;
+                const uint32_t nL = __popc(Lm);
+                const uint32_t LBB = (j + 2 < 32) ? __popc(Lm >> (j + 2)) : 0u;
+                const bool pred = active && (j + 2 <= n) && (LBB >= RF);
+                const uint32_t f = __popc(__ballot_sync(FULL_MASK, pred));
+                const uint32_t pivot = nL - ((Lm >> f) & 1u);
+                const uint32_t LB = nL - LF - (L ? 1u : 0u);
+                if (active) {
+                    if (L) sm_tab[n - 1 - LB] = (uint8_t)j;
+                    else sm_tab[RF] = (uint8_t)j;
+                }
+                __syncwarp();
+                if (active) {
+                    uint32_t dest;
+                    if (j < f) dest = L ? j : (RF == 0 ? n - 1 : (uint32_t)sm_tab[n - RF] - 1u);
+                    else if (j == f) dest = pivot;
+                    else dest = L ? (uint32_t)sm_tab[LB] : j - 1;
+                    sm_pay[dest] = (uint16_t)pay;
+                }
+                __syncwarp();
+                if (active) pay = sm_pay[j];
+                return pivot;
+            };
+
+            uint32_t my_u = 0xFFu, my_piv = 0;
+            for (uint32_t c = 0; c < 21; ++c) {
+                const uint32_t pivot = do_shuffle(c / 7, c % 7 + 1);
+                const uint32_t up = __shfl_sync(FULL_MASK, pay, s + pivot);
+                if (lane == c) { my_u = up & 31u; my_piv = pivot; }
+            }
+            // candidate `lane` (< 21): exact boxes of {L}\{u} and {R}+{u} (blas.rs:149-155)
+            const uint32_t ca = (lane < 21) ? lane / 7 : 0, cb = lane % 7 + 1;
+            float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+            float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+            for (uint32_t tt = 0; tt < n; ++tt) {
+                const uint32_t p = __shfl_sync(FULL_MASK, pay, s + tt);
+                const uint32_t et = p & 31u;
+                const bool left = (((p >> (5 + 3 * ca)) & 7u) < cb) && (et != my_u);
+                const float x0 = sm_box[0][et], x1 = sm_box[1][et], x2 = sm_box[2][et];
+                const float x3 = sm_box[3][et], x4 = sm_box[4][et], x5 = sm_box[5][et];
+                if (left) {
+                    Lb[0] = fminf(Lb[0], x0); Lb[1] = fminf(Lb[1], x1); Lb[2] = fminf(Lb[2], x2);
+                    Lb[3] = fmaxf(Lb[3], x3); Lb[4] = fmaxf(Lb[4], x4); Lb[5] = fmaxf(Lb[5], x5);
+                } else {
+                    Rb[0] = fminf(Rb[0], x0); Rb[1] = fminf(Rb[1], x1); Rb[2] = fminf(Rb[2], x2);
+                    Rb[3] = fmaxf(Rb[3], x3); Rb[4] = fmaxf(Rb[4], x4); Rb[5] = fmaxf(Rb[5], x5);
+                }
+            }
+            const float cost = sah_cost(Lb, Rb, my_piv, n - my_piv);
+            // strict <, first candidate wins, NaN/inf never win (blas.rs:140,156)
+            const uint32_t key = (lane < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
+            const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
+            if (mk == 0xFFFFFFFFu) {
+                if (lane == 0) atomicOr(&st->err, DERR_DEGENERATE);
+            } else {
+                const uint32_t win = __ffs(__ballot_sync(FULL_MASK, key == mk)) - 1;
+                const uint32_t p = __shfl_sync(FULL_MASK, my_piv, win);  // recorded pivot (blas.rs:159,165)
+                do_shuffle(win / 7, win % 7 + 1);                       // blas.rs:164
+                if (lane == 0) {
+                    emit_rec(recs, 2 * (abs_start + p) + 1, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
+                    if (p <= 3) A[abs_start] = leftrun + 1;
+                }
+                if ((int)lane == sp) {
+                    stk_a = (s + p) | ((n - p) << 8);
+                    stk_b = abs_start;
+                    stk_c = leftrun;
+                }
+                sp++;
+                pstart = abs_start; pleftrun = leftrun; leftrun = leftrun + 1; n = p; fl = t.flags & ~3u;
+                descend = true;
+            }
+        }
+        if (descend) continue;
+        if (sp == 0) break;
+        sp--;
+        const uint32_t a = __shfl_sync(FULL_MASK, stk_a, sp);
+        pstart = __shfl_sync(FULL_MASK, stk_b, sp);
+        pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
+        s = a & 0xFFu; n = a >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
+    }
+    if (lane < t.n) ids[t.start + lane] = sm_gid[pay & 31u];
+}
+
+__global__ void __launch_bounds__(256, 4) k_t3(const Task* __restrict__ tasks, uint32_t* ids,
+                                               const float4* __restrict__ cent, const float4* __restrict__ box,
+                                               uint4* recs, uint32_t* A, BuildState* st) {
     __shared__ float s_box[8][6][32];
     __shared__ float s_cent[8][3][32];
     __shared__ uint32_t s_gid[8][32];
@@ -166,147 +325,10 @@ __global__ void __launch_bounds__(256) k_t3(const Task* __restrict__ tasks, uint
     __shared__ uint16_t s_pay[8][32];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t n_tasks = st->t3_count;
-
+    const T3Smem sm{s_box[w], s_cent[w], s_gid[w], s_tab[w], s_pay[w]};
     for (uint32_t ti = blockIdx.x * 8 + w; ti < n_tasks; ti += gridDim.x * 8) {
         const Task t = tasks[ti];
-        __syncwarp();
-        if (lane < t.n) {
-            const uint32_t g = __ldcg(&ids[t.start + lane]);
-            const float4 c = cent[g];
-            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-            s_box[w][0][lane] = b0.x; s_box[w][1][lane] = b0.y; s_box[w][2][lane] = b0.z;
-            s_box[w][3][lane] = b1.x; s_box[w][4][lane] = b1.y; s_box[w][5][lane] = b1.z;
-            s_cent[w][0][lane] = c.x; s_cent[w][1][lane] = c.y; s_cent[w][2][lane] = c.z;
-            s_gid[w][lane] = g;
-        }
-        __syncwarp();
-        uint32_t pay = lane;  // bits 0-4: local primitive, 5-13: plane counts of the current node
-        uint32_t s = 0, n = t.n, leftrun = t.leftrun, pstart = t.pstart, pleftrun = t.pleftrun, fl = t.flags;
-        uint32_t stk_a = 0, stk_b = 0, stk_c = 0;  // lane i holds stack entry i
-        int sp = 0;
-
-        for (;;) {
-            const bool active = lane >= s && lane < s + n;
-            const uint32_t e = pay & 31u;
-            const uint32_t abs_start = t.start + s;
-            // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
-            float lo[3], hi[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint32_t mn = active ? f2o(s_box[w][c][e]) : ENC_POS_INIT;
-                uint32_t mx = active ? f2o(s_box[w][3 + c][e]) : ENC_NEG_INIT;
-                mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
-                mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
-                lo[c] = o2f(mn);
-                hi[c] = o2f(mx);
-            }
-            bool descend = false;
-            if (n <= 3) {  // leaf (blas.rs:106-109)
-                if (lane == 0) emit_rec(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
-            } else {
-                // centroid bounds (blas.rs:142)
-                float cmin[3], cmax[3], cc[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    cc[c] = active ? s_cent[w][c][e] : 0.0f;
-                    uint32_t mn = active ? f2o(cc[c]) : ENC_POS_INIT;
-                    uint32_t mx = active ? f2o(cc[c]) : ENC_NEG_INIT;
-                    mn = min(__reduce_min_sync(FULL_MASK, mn), ENC_POS_INIT);
-                    mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
-                    cmin[c] = o2f(mn);
-                    cmax[c] = o2f(mx);
-                }
-                pay = e | (plane_counts(cc[0], cc[1], cc[2], cmin, cmax) << 5);
-
-                const uint32_t j = lane - s;
-                const uint32_t nmask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
-                // closed form of partition_shuffle (blas.rs:168-182) on the current order
-                auto do_shuffle = [&](uint32_t a, uint32_t b) -> uint32_t {
-                    const bool L = active && (((pay >> (5 + 3 * a)) & 7u) < b);
-                    const uint32_t Lm = __ballot_sync(FULL_MASK, L) >> s;
-                    const uint32_t Rm = ~Lm & nmask;
-                    const uint32_t below = active ? ((1u << j) - 1u) : 0u;
-                    const uint32_t RF = __popc(Rm & below), LF = j - RF;
-                    const uint32_t nL = __popc(Lm);
-                    const uint32_t LBB = (j + 2 < 32) ? __popc(Lm >> (j + 2)) : 0u;
-                    const bool pred = active && (j + 2 <= n) && (LBB >= RF);
-                    const uint32_t f = __popc(__ballot_sync(FULL_MASK, pred));
-                    const uint32_t pivot = nL - ((Lm >> f) & 1u);
-                    const uint32_t LB = nL - LF - (L ? 1u : 0u);
-                    if (active) {
-                        if (L) s_tab[w][n - 1 - LB] = (uint8_t)j;
-                        else s_tab[w][RF] = (uint8_t)j;
-                    }
-                    __syncwarp();
-                    if (active) {
-                        uint32_t dest;
-                        if (j < f) dest = L ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[w][n - RF] - 1u);
-                        else if (j == f) dest = pivot;
-                        else dest = L ? (uint32_t)s_tab[w][LB] : j - 1;
-                        s_pay[w][dest] = (uint16_t)pay;
-                    }
-                    __syncwarp();
-                    if (active) pay = s_pay[w][j];
-                    return pivot;
-                };
-
-                uint32_t my_u = 0xFFu, my_piv = 0;
-                for (uint32_t c = 0; c < 21; ++c) {
-                    const uint32_t pivot = do_shuffle(c / 7, c % 7 + 1);
-                    const uint32_t up = __shfl_sync(FULL_MASK, pay, s + pivot);
-                    if (lane == c) { my_u = up & 31u; my_piv = pivot; }
-                }
-                // candidate `lane` (< 21): exact boxes of {L}\{u} and {R}+{u} (blas.rs:149-155)
-                const uint32_t ca = (lane < 21) ? lane / 7 : 0, cb = lane % 7 + 1;
-                float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-                float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-                for (uint32_t tt = 0; tt < n; ++tt) {
-                    const uint32_t p = __shfl_sync(FULL_MASK, pay, s + tt);
-                    const uint32_t et = p & 31u;
-                    const bool left = (((p >> (5 + 3 * ca)) & 7u) < cb) && (et != my_u);
-                    const float x0 = s_box[w][0][et], x1 = s_box[w][1][et], x2 = s_box[w][2][et];
-                    const float x3 = s_box[w][3][et], x4 = s_box[w][4][et], x5 = s_box[w][5][et];
-                    if (left) {
-                        Lb[0] = fminf(Lb[0], x0); Lb[1] = fminf(Lb[1], x1); Lb[2] = fminf(Lb[2], x2);
-                        Lb[3] = fmaxf(Lb[3], x3); Lb[4] = fmaxf(Lb[4], x4); Lb[5] = fmaxf(Lb[5], x5);
-                    } else {
-                        Rb[0] = fminf(Rb[0], x0); Rb[1] = fminf(Rb[1], x1); Rb[2] = fminf(Rb[2], x2);
-                        Rb[3] = fmaxf(Rb[3], x3); Rb[4] = fmaxf(Rb[4], x4); Rb[5] = fmaxf(Rb[5], x5);
-                    }
-                }
-                const float cost = sah_cost(Lb, Rb, my_piv, n - my_piv);
-                // strict <, first candidate wins, NaN/inf never win (blas.rs:140,156)
-                const uint32_t key = (lane < 21 && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
-                const uint32_t mk = __reduce_min_sync(FULL_MASK, key);
-                if (mk == 0xFFFFFFFFu) {
-                    if (lane == 0) atomicOr(&st->err, DERR_DEGENERATE);
-                } else {
-                    const uint32_t win = __ffs(__ballot_sync(FULL_MASK, key == mk)) - 1;
-                    const uint32_t p = __shfl_sync(FULL_MASK, my_piv, win);  // recorded pivot (blas.rs:159,165)
-                    do_shuffle(win / 7, win % 7 + 1);                       // blas.rs:164
-                    if (lane == 0) {
-                        emit_rec(recs, 2 * (abs_start + p) + 1, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
-                        if (p <= 3) A[abs_start] = leftrun + 1;
-                    }
-                    if ((int)lane == sp) {
-                        stk_a = (s + p) | ((n - p) << 8);
-                        stk_b = abs_start;
-                        stk_c = leftrun;
-                    }
-                    sp++;
-                    pstart = abs_start; pleftrun = leftrun; leftrun = leftrun + 1; n = p; fl = t.flags & ~3u;
-                    descend = true;
-                }
-            }
-            if (descend) continue;
-            if (sp == 0) break;
-            sp--;
-            const uint32_t a = __shfl_sync(FULL_MASK, stk_a, sp);
-            pstart = __shfl_sync(FULL_MASK, stk_b, sp);
-            pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
-            s = a & 0xFFu; n = a >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
-        }
-        if (lane < t.n) ids[t.start + lane] = s_gid[w][pay & 31u];
+        t3_subtree(t, sm, lane, ids, cent, box, recs, A, st);
     }
 }
 
@@ -698,7 +720,7 @@ __global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, uint32_
 // (lane a*8+k owns bin (a,k); lane c owns candidate c and special c).  No block barriers.
 // ------------------------------------------------------------------------------------------------
 template <int WCAP>
-__global__ void __launch_bounds__(256) k_t2w(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
+__global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
                                              const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st,
                                              uint32_t epoch) {
     constexpr int EPL = WCAP / 32;
@@ -706,8 +728,15 @@ __global__ void __launch_bounds__(256) k_t2w(Queues Q, uint32_t* ids, const floa
     __shared__ uint32_t s_pay[NWB][2][WCAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
     __shared__ uint32_t s_gid[NWB][WCAP];
     __shared__ uint16_t s_tab[NWB][WCAP];
+    // scratch for children of <= 32 primitives, which this warp finishes itself (no hand-off to k_t3)
+    __shared__ float s3_box[NWB][6][32];
+    __shared__ float s3_cent[NWB][3][32];
+    __shared__ uint32_t s3_gid[NWB][32];
+    __shared__ uint8_t s3_tab[NWB][32];
+    __shared__ uint16_t s3_pay[NWB][32];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const T3Smem sm3{s3_box[w], s3_cent[w], s3_gid[w], s3_tab[w], s3_pay[w]};
 
     for (;;) {
         // ---- pop (lane 0) ----
@@ -944,14 +973,32 @@ __global__ void __launch_bounds__(256) k_t2w(Queues Q, uint32_t* ids, const floa
         __threadfence();
         __syncwarp();
         // ---- 7. record + children ----
+        // (finishing <=32-primitive children inline on this warp was measured slower than handing them to k_t3:
+        //  3.30 ms vs 2.43 ms for the two tiers on the dragon-class mesh, so the hand-off stays)
+        const bool small_l = false, small_r = false;
         if (lane == 0) {
             emit_rec(recs, 2 * (start + p) + 1, nlo, nhi, start, n, leftrun, pstart, pleftrun, tflags);
             if (p <= 3) A[start] = leftrun + 1;
-            push_child(Q, st, epoch, start, p, leftrun + 1, start, leftrun, tflags & ~3u);
-            push_child(Q, st, epoch, start + p, n - p, 0, start, leftrun, TF_RIGHT | (tflags & ~3u));
+            if (!small_l) push_child(Q, st, epoch, start, p, leftrun + 1, start, leftrun, tflags & ~3u);
+            if (!small_r) push_child(Q, st, epoch, start + p, n - p, 0, start, leftrun, TF_RIGHT | (tflags & ~3u));
             atomicAdd(&st->t2w_done, 1u);
+            if (small_l || small_r) atomicAdd(&st->t3_inline, (small_l ? 1u : 0u) + (small_r ? 1u : 0u));
             __threadfence();
             atomicSub(&st->w_pending, 1u);
+        }
+        __syncwarp();
+        // children of <= 32 primitives: finish the whole sub-tree right here
+        if (small_l) {
+            Task c;
+            c.start = start; c.n = p; c.leftrun = leftrun + 1; c.pstart = start; c.pleftrun = leftrun; c.flags = tflags & ~3u;
+            c.ready = 0; c.pad = 0;
+            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st);
+        }
+        if (small_r) {
+            Task c;
+            c.start = start + p; c.n = n - p; c.leftrun = 0; c.pstart = start; c.pleftrun = leftrun; c.flags = TF_RIGHT | (tflags & ~3u);
+            c.ready = 0; c.pad = 0;
+            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st);
         }
         __syncwarp();
     }
@@ -2001,7 +2048,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.big_block_tasks = hs->t2b_done;
     stats.block_tasks = hs->t2_done;
     stats.warp_node_tasks = hs->t2w_done;
-    stats.warp_tasks = hs->t3_count;
+    stats.warp_tasks = hs->t3_count + hs->t3_inline;
     stats.kernel_launches = launches;
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
