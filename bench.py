@@ -208,6 +208,111 @@ def cpu_baseline_leg(dv, di, pv, pi, inst):
     return build, rays, per_ray, {"S": st["sum_interior_prims"], "M": int(len(dn))}
 
 
+def run_small_configs(args, local_rank):
+    """BASELINE config 1 (bunny-class BLAS + 1 Mi closest-hit rays, Rust semantics = Bvh::traverse_iter) and config 3
+    (TLAS over many randomly transformed instances of three meshes + two-level closest-hit).  Single GPU, one JSON line.
+    Secondary workloads: not the line the driver reads."""
+    import torch
+
+    import voidin_b200 as vb
+    from voidin_b200 import scenes as S
+    from voidin_b200.types import MESH_INFO
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = vb.Context(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = max(1, args.steps)
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts))
+
+    def up(a, dt):
+        return torch.from_numpy(np.ascontiguousarray(a).view(dt).reshape(-1)).to(dev)
+
+    out = {"n_gpus": 1, "data": "synthetic", "dtype": "f32", "steps": steps}
+    if args.workload == "bunny":
+        v, idx = S.bunny_class()
+        n = idx.size // 3
+        d_v, d_i0 = up(v, np.float32), up(idx, np.int32)
+        d_i = d_i0.clone()
+        d_nodes = torch.zeros(2 * n * 8, dtype=torch.int32, device=dev)
+        m = [0]
+
+        def build():
+            d_i.copy_(d_i0)
+            m[0] = ctx.blas_build_dev(d_v.data_ptr(), v.shape[0], d_i.data_ptr(), n, d_nodes.data_ptr(), 2 * n, stream)
+
+        b_ms = timed(build, steps)
+        n_rays = 1 << 20 if args.rays == N_RAYS else args.rays
+        ro, rd = S.rays_toward_box(n_rays, v.min(0), v.max(0), seed=11)
+        d_ro, d_rd = up(ro, np.float32), up(rd, np.float32)
+        d_t = torch.empty(n_rays, dtype=torch.float32, device=dev)
+        d_tri = torch.empty(n_rays, dtype=torch.int32, device=dev)
+        r_ms = timed(lambda: ctx.trace_blas_dev(d_nodes.data_ptr(), d_v.data_ptr(), d_i.data_ptr(), d_ro.data_ptr(), d_rd.data_ptr(),
+                                                n_rays, d_t.data_ptr(), d_tri.data_ptr(), stream), steps)
+        out.update({"metric": "bunny_blas_build_Mtris_per_s", "value": n / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": b_ms + r_ms,
+                    "config": {"workload": f"config1: bunny_class BLAS ({n} tris) + {n_rays} closest-hit rays, Bvh::traverse_iter semantics"},
+                    "phase_ms": {"build": b_ms, "trace": r_ms},
+                    "rays": {"metric": "closest_hit_Mrays_per_s", "value": n_rays / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                             "hit_frac": float((d_tri != -1).float().mean().item())}})
+    else:
+        meshes = [S.bunny_class(), S.dragon_class(), S.displaced_sphere(62, 124, 3)]  # third = DamagedHelmet-sized stand-in
+        n_inst = args.instances
+        tm = [(up(v, np.float32), up(i, np.int32)) for v, i in meshes]
+        info = np.zeros(len(meshes), dtype=MESH_INFO)
+        info["index_count"] = [i.size for _, i in meshes]
+        info["vertex_offset"] = np.concatenate([[0], np.cumsum([v.shape[0] for v, _ in meshes])[:-1]])
+        info["base_index"] = np.concatenate([[0], np.cumsum(info["index_count"])[:-1]])
+        info["min"] = [v.min(0) for v, _ in meshes]
+        info["max"] = [v.max(0) for v, _ in meshes]
+        d_info = up(info, np.uint8)
+        d_verts = torch.cat([a for a, _ in tm])
+        d_inds0 = torch.cat([b for _, b in tm])
+        d_inds = d_inds0.clone()
+        n_tris = d_inds.numel() // 3
+        d_nodes = torch.zeros(2 * n_tris * 8, dtype=torch.int32, device=dev)
+        mm = [0]
+
+        def build():
+            d_inds.copy_(d_inds0)
+            mm[0] = ctx.blas_build_batch_dev(d_verts.data_ptr(), d_verts.numel() // 3, d_inds.data_ptr(), d_inds.numel(), d_info.data_ptr(),
+                                             len(meshes), d_nodes.data_ptr(), 2 * n_tris, stream)
+
+        b_ms = timed(build, steps)
+        inst = S.random_instances(n_inst, len(meshes), seed=3, extent=500.0)
+        d_inst = up(inst, np.uint8)
+        d_tlas = torch.zeros((2 * n_inst + 1) * 8, dtype=torch.int32, device=dev)
+        d_kids = torch.zeros((2 * n_inst + 1) * 2, dtype=torch.int32, device=dev)
+        t_ms = timed(lambda: ctx.tlas_build_dev(d_inst.data_ptr(), n_inst, d_info.data_ptr(), len(meshes), d_tlas.data_ptr(), d_kids.data_ptr(), stream), 1)
+        scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_info.data_ptr(), d_nodes.data_ptr(), d_verts.data_ptr(),
+                         d_inds.data_ptr(), ctx, device_ptrs=True,
+                         counts={"tlas_nodes": 2 * n_inst + 1, "instances": n_inst, "meshes": len(meshes), "bvh_nodes": mm[0],
+                                 "vertices": d_verts.numel() // 3, "indices": d_inds.numel()}, stream=stream)
+        n_rays = 1 << 20 if args.rays == N_RAYS else args.rays
+        ro, rd = S.rays_sphere_to_cube(n_rays, 1200.0, 500.0, seed=13)
+        d_ro, d_rd = up(ro, np.float32), up(rd, np.float32)
+        d_t = torch.empty(n_rays, dtype=torch.float32, device=dev)
+        d_tri = torch.empty(n_rays, dtype=torch.int32, device=dev)
+        d_ins = torch.empty(n_rays, dtype=torch.int32, device=dev)
+        r_ms = timed(lambda: scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr(),
+                                                     1e30, stream), max(1, min(steps, 3)))
+        out.update({"metric": "tlas_build_ms", "value": t_ms, "unit": "ms", "higher_is_better": False, "ms_per_step": b_ms + t_ms + r_ms,
+                    "config": {"workload": f"config3: TLAS over {n_inst} random instances of 3 meshes ({n_tris} tris, forest BLAS build) + {n_rays} two-level closest-hit rays",
+                               "note": "Tlas::build seeds every leaf box with the untransformed local mesh box (tlas.rs:39), so instances far from the origin get boxes stretched to the origin and most rays enter a large share of them: reference behaviour, reproduced bit-exactly"},
+                    "phase_ms": {"blas_forest_build": b_ms, "tlas_build": t_ms, "trace": r_ms},
+                    "blas": {"value": n_tris / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s"},
+                    "rays": {"metric": "closest_hit_Mrays_per_s", "value": n_rays / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                             "hit_frac": float((d_tri != -1).float().mean().item())}})
+    print(json.dumps(out), flush=True)
+
+
 def run_scene1024(args, rank, local_rank, world):
     """BASELINE config 5: `--meshes` distinct synthetic meshes; BLAS builds sharded over the ranks (LPT), ONE all-gather
     of {vertices | permuted indices | nodes} slabs over NCCL so every GPU holds the pooled scene, TLAS per rank, then
@@ -341,9 +446,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="dragon", choices=["dragon", "scene1024"],
+    ap.add_argument("--workload", default="dragon", choices=["dragon", "scene1024", "bunny", "instances"],
                     help="dragon = BASELINE config 2 (default, the bench line the driver reads); scene1024 = config 5")
     ap.add_argument("--meshes", type=int, default=1024)
+    ap.add_argument("--instances", type=int, default=32767, help="instances workload (config 3): instance count")
     ap.add_argument("--mesh-res", type=int, default=181, help="scene1024: vside of each displaced sphere (181 -> 130682 tris)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -357,6 +463,9 @@ def main():
         return
     if args.workload == "scene1024":
         run_scene1024(args, rank, local_rank, world)
+        return
+    if args.workload in ("bunny", "instances"):
+        run_small_configs(args, local_rank)
         return
 
     import torch

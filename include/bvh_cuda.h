@@ -181,6 +181,19 @@ int bvh_cuda_trace_blas_dev(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const flo
                             const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d,
                             size_t n_rays, float* d_t_out, uint32_t* d_tri_out, void* stream);
 
+/* Bvh::traverse (crates/bvh/src/blas.rs:211-245), the recursive variant (unused by the reference: commented out at
+ * src/bin/bvh_cpu.rs:86): starts at node_idx with distance bound t0; hit_out[r] = 1 means Hit(t_out[r]) — which the
+ * reference returns as soon as the start node's box is hit, with t_out = t0 when no triangle is closer — 0 means Miss.
+ * The reference takes Vec4 / UVec4 slices and truncates them; pass the same Vec3 / UVec3 data here. */
+int bvh_cuda_trace_blas_recursive(bvh_cuda_ctx* ctx, const BvhNode* nodes, size_t n_nodes, const float* vertices,
+                                  size_t n_vertices, const uint32_t* indices, size_t n_tris, const float* ray_o,
+                                  const float* ray_d, size_t n_rays, uint32_t node_idx, float t0, float* t_out,
+                                  uint8_t* hit_out);
+int bvh_cuda_trace_blas_recursive_dev(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
+                                      const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d,
+                                      size_t n_rays, uint32_t node_idx, float t0, float* d_t_out, uint8_t* d_hit_out,
+                                      void* stream);
+
 /* traverse_tlas (shaders/utils/bvh.wgsl:89-123) with the WGSL tests (shaders/utils/intersections.wgsl:13-45):
  * reciprocal slabs, back-face culling, 0 < t < hit, near child first.  tmax: initial res.dist (reference: 1e30). */
 int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o,
@@ -197,6 +210,21 @@ int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
 int bvh_cuda_trace_any_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
                            const float* d_ray_d, size_t n_rays, float tmax, uint8_t* d_occluded_out,
                            void* stream);
+
+/* ---- ray generation: the step right before traversal ------------------------------------------------------ *
+ * Primary rays, one per pixel, from camera.clip_to_world (column-major 4x4, host pointer): src/bin/bvh_cpu.rs:72-84,
+ * the CPU twin of src/bin/bvh_trace.wgsl:224-233.  Pixel i: x = (i % W)/W, y = (i / H)/H (sic, bvh_cpu.rs:75),
+ * eye = (M*(x',y',1,1)).xyz / w, dir = normalize((M*(x',y',0,1)).xyz). */
+int bvh_cuda_gen_primary_rays_dev(bvh_cuda_ctx* ctx, const float* clip_to_world, uint32_t width, uint32_t height,
+                                  float* d_ray_o, float* d_ray_d, void* stream);
+/* Point-light shadow rays from G-buffer world positions / normals (3 floats each, device):
+ * ray_new(pos + nor * 0.0001, light.position - pos), src/bin/raytraced_shadows.wgsl:93-99.  light_pos: host, 3 floats. */
+int bvh_cuda_gen_shadow_rays_dev(bvh_cuda_ctx* ctx, const float* d_pos, const float* d_nor, size_t n, const float* light_pos,
+                                 float* d_ray_o, float* d_ray_d, void* stream);
+/* Rect-area-light shadow rays: same origin, direction toward p0 + (p1-p0)*u + (p3-p0)*v with the corner order of
+ * AreaLight::from_transform (crates/pools/src/light.rs:28-52); d_uv: 2 floats per ray; corners: host, 12 floats. */
+int bvh_cuda_gen_area_shadow_rays_dev(bvh_cuda_ctx* ctx, const float* d_pos, const float* d_nor, const float* d_uv, size_t n,
+                                      const float* corners, float* d_ray_o, float* d_ray_d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -621,6 +621,29 @@ inline void traverse_iter_rs(const BvhNode* nodes, const float* vertices, const 
     if (st && hit) st->hits++;
 }
 
+// blas.rs:211-245 (Bvh::traverse, the recursive variant; unused by the reference itself, bvh_cpu.rs:86).  The Vec4/UVec4
+// inputs are the Vec3/UVec3 data plus an ignored lane (`truncate()`).  Returns Hit(t) as soon as the node's box is
+// hit, with t left at the caller's value when no triangle is closer.
+inline RDist traverse_rec_rs(const BvhNode* nodes, const float* vertices, const uint32_t* indices, V3 o, V3 d,
+                             size_t node_idx, float t) {
+    const BvhNode& node = nodes[node_idx];
+    if (!intersect_aabb_rs(o, d, ld3(node.min), ld3(node.max), t).hit) return {false, 0.0f};
+    if (node.count > 0) {
+        for (uint32_t i = 0; i < node.count; ++i) {
+            const uint32_t* idx = indices + 3 * (size_t)(node.left_first + i);
+            RDist r = intersect_tri_rs(o, d, ld3(vertices + 3 * (size_t)idx[0]), ld3(vertices + 3 * (size_t)idx[1]),
+                                       ld3(vertices + 3 * (size_t)idx[2]));
+            if (r.hit) t = fmin_rs(t, r.t);
+        }
+        return {true, t};
+    }
+    RDist l = traverse_rec_rs(nodes, vertices, indices, o, d, node.left_first, t);
+    if (l.hit) t = fmin_rs(t, l.t);
+    RDist r = traverse_rec_rs(nodes, vertices, indices, o, d, (size_t)node.left_first + 1, t);
+    if (r.hit) t = fmin_rs(t, r.t);
+    return {true, t};
+}
+
 // WGSL min/max: IEEE minNum/maxNum (what fminf/fmaxf and the CUDA intrinsics implement)
 inline float wmin(float a, float b) { return std::fmin(a, b); }
 inline float wmax(float a, float b) { return std::fmax(a, b); }
@@ -974,6 +997,18 @@ int oracle_trace_blas(const BvhNode* nodes, const float* vertices, const uint32_
     return ORACLE_OK;
 }
 
+// Bvh::traverse over R rays (blas.rs:211-245): hit_out[r] = 1 for Hit(t_out[r]), 0 for Miss.
+int oracle_trace_blas_recursive(const BvhNode* nodes, const float* vertices, const uint32_t* indices, const float* ray_o,
+                                const float* ray_d, size_t n_rays, uint32_t node_idx, float t0, float* t_out,
+                                uint8_t* hit_out) {
+    for (size_t r = 0; r < n_rays; ++r) {
+        RDist d = traverse_rec_rs(nodes, vertices, indices, ld3(ray_o + 3 * r), ld3(ray_d + 3 * r), node_idx, t0);
+        hit_out[r] = d.hit ? 1 : 0;
+        t_out[r] = d.hit ? d.t : MAX_DIST;
+    }
+    return ORACLE_OK;
+}
+
 // traverse_tlas over R rays (bvh.wgsl:89-123).  any_hit != 0: occluded_out[r] = traverse_tlas(ray).hit
 // computed with early exit (raytraced_shadows.wgsl:98-102); t/tri/inst outputs may be NULL then.
 int oracle_trace_scene(const TlasNode* tlas, const uint32_t* tlas_children, const Instance* instances,
@@ -1017,6 +1052,36 @@ int oracle_brute_force(const float* vertices, const uint32_t* indices, size_t n_
         }
         t_out[r] = best;
     }
+    return ORACLE_OK;
+}
+
+// Primary rays (src/bin/bvh_cpu.rs:72-84).  clip_to_world column-major.
+int oracle_gen_primary_rays(const float* m, uint32_t width, uint32_t height, float* ro, float* rd) {
+    auto mv = [&](float x, float y, float z, float w, float* o) {
+        for (int r = 0; r < 4; ++r) o[r] = ((m[r] * x + m[4 + r] * y) + m[8 + r] * z) + m[12 + r] * w;
+    };
+    for (size_t i = 0; i < (size_t)width * height; ++i) {
+        float x = (float)(i % width) / (float)width;
+        float y = (float)(i / height) / (float)height;  // sic: bvh_cpu.rs:75 divides by HEIGHT
+        x = (x - 0.5f) * 2.0f;
+        y = (y - 0.5f) * -2.0f;
+        float vp[4], vt[4];
+        mv(x, y, 1.0f, 1.0f, vp);
+        mv(x, y, 0.0f, 1.0f, vt);
+        ro[3 * i] = vp[0] / vp[3]; ro[3 * i + 1] = vp[1] / vp[3]; ro[3 * i + 2] = vp[2] / vp[3];
+        const float rl = 1.0f / std::sqrt((vt[0] * vt[0] + vt[1] * vt[1]) + vt[2] * vt[2]);  // glam normalize = v * length_recip
+        rd[3 * i] = vt[0] * rl; rd[3 * i + 1] = vt[1] * rl; rd[3 * i + 2] = vt[2] * rl;
+    }
+    return ORACLE_OK;
+}
+
+// raytraced_shadows.wgsl:93-99: ray_new(pos + nor * 0.0001, light.position - pos)
+int oracle_gen_shadow_rays(const float* pos, const float* nor, size_t n, const float* light, float* ro, float* rd) {
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            ro[3 * i + k] = pos[3 * i + k] + nor[3 * i + k] * 0.0001f;
+            rd[3 * i + k] = light[k] - pos[3 * i + k];
+        }
     return ORACLE_OK;
 }
 

@@ -128,6 +128,20 @@ def trace_blas(nodes, vertices, perm_indices, ray_o, ray_d, threads: int = 1):
     return t, tri, st.as_dict()
 
 
+def trace_blas_recursive(nodes, vertices, perm_indices, ray_o, ray_d, node_idx: int = 0, t0: float = 1e30):
+    """Bvh::traverse per ray (blas.rs:211-245).  Returns (hit[bool], t)."""
+    o, d = _f32(ray_o).reshape(-1, 3), _f32(ray_d).reshape(-1, 3)
+    r = o.shape[0]
+    t = np.empty(r, dtype=np.float32)
+    hit = np.empty(r, dtype=np.uint8)
+    v = _f32(vertices)
+    idx = np.ascontiguousarray(perm_indices, dtype=np.uint32)
+    nd = np.ascontiguousarray(nodes)
+    lib().oracle_trace_blas_recursive(_p(nd), _p(v), _p(idx), _p(o), _p(d), C.c_size_t(r), C.c_uint32(node_idx), C.c_float(t0),
+                                      _p(t), _p(hit))
+    return hit.astype(bool), t
+
+
 def trace_scene(tlas, children, instances, meshes, bvh_nodes, vertices, indices, ray_o, ray_d, tmax=1e30,
                 any_hit: bool = False, threads: int = 1):
     """traverse_tlas per ray (bvh.wgsl:89-123).  Returns (t, tri, inst, occluded, stats)."""
@@ -160,3 +174,19 @@ def brute_force(vertices, indices, ray_o, ray_d, mode: int):
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+def gen_primary_rays(clip_to_world, width: int, height: int):
+    m = _f32(clip_to_world).reshape(16)
+    ro = np.empty((width * height, 3), dtype=np.float32)
+    rd = np.empty((width * height, 3), dtype=np.float32)
+    lib().oracle_gen_primary_rays(_p(m), C.c_uint32(width), C.c_uint32(height), _p(ro), _p(rd))
+    return ro, rd
+
+
+def gen_shadow_rays(pos, nor, light):
+    p, n = _f32(pos).reshape(-1, 3), _f32(nor).reshape(-1, 3)
+    l = _f32(light).reshape(3)
+    ro, rd = np.empty_like(p), np.empty_like(p)
+    lib().oracle_gen_shadow_rays(_p(p), _p(n), C.c_size_t(p.shape[0]), _p(l), _p(ro), _p(rd))
+    return ro, rd

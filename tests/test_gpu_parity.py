@@ -255,3 +255,58 @@ def test_blas_batch_rejects_bad_mesh_table(ctx):
     with pytest.raises(vb.BvhCudaError) as e:
         ctx.blas_build_batch_dev(d_v.data_ptr(), 300, d_i.data_ptr(), 300, d_info.data_ptr(), 2, nodes.data_ptr(), 200)
     assert e.value.code == vb.types.EINVAL
+
+
+def test_trace_blas_recursive_variant(ctx, oracle):
+    """Bvh::traverse (blas.rs:211-245): Hit(t) once the start node's box is hit (t = t0 when no triangle is closer)."""
+    v, idx = S.displaced_sphere(36, 72, 9)
+    bvh, gi = gpu_build(ctx, v, idx)
+    ro, rd = S.rays_toward_box(50_000, v.min(0) * 1.5, v.max(0) * 1.5, seed=21)
+    for node_idx, t0 in [(0, 1e30), (0, 3.0), (2, 1e30)]:
+        hit, t = bvh.traverse_batch(v, gi, ro, rd, node_idx, t0)
+        ohit, ot = oracle.trace_blas_recursive(bvh.nodes, v, gi, ro, rd, node_idx, t0)
+        assert (hit == ohit).all() and np.allclose(t, ot, rtol=T_RTOL, atol=0.0) and (t == ot).all()
+    # closest distance agrees with traverse_iter wherever a triangle is hit
+    hit, t = bvh.traverse_batch(v, gi, ro, rd)
+    ti, tri = bvh.traverse_iter_batch(v, gi, ro, rd)
+    has = tri != 0xFFFFFFFF
+    assert (t[has] == ti[has]).all() and hit[has].all()
+    assert bvh.traverse(v, gi, vb.Ray.new(ro[0], rd[0])) == (vb.Hit(t[0]) if hit[0] else vb.MISS)
+
+
+def test_ray_generation_bit_exact(ctx, oracle):
+    """Primary rays from clip_to_world (bvh_cpu.rs:72-84) and G-buffer shadow rays (raytraced_shadows.wgsl:93-99)."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    # a perspective * look-at camera, inverted in float64 and rounded (the reference's proj_view.inverse() is an input here)
+    f, aspect, zn, zf = 1.0 / np.tan(0.4), 1.0, 0.1, 100.0
+    proj = np.array([[f / aspect, 0, 0, 0], [0, f, 0, 0], [0, 0, zf / (zn - zf), zn * zf / (zn - zf)], [0, 0, -1, 0]])
+    eye, tgt, up = np.array([3.0, 2.0, 5.0]), np.array([0.0, 0.5, 0.0]), np.array([0.0, 1.0, 0.0])
+    fw = (tgt - eye) / np.linalg.norm(tgt - eye); rt = np.cross(fw, up); rt /= np.linalg.norm(rt); u2 = np.cross(rt, fw)
+    view = np.eye(4); view[0, :3], view[1, :3], view[2, :3] = rt, u2, -fw; view[:3, 3] = -view[:3, :3] @ eye
+    c2w = np.linalg.inv(proj @ view).astype(np.float32).T.reshape(-1)  # column-major
+    for w, h in [(640, 640), (320, 200)]:
+        d_ro = torch.empty(w * h * 3, dtype=torch.float32, device=dev)
+        d_rd = torch.empty(w * h * 3, dtype=torch.float32, device=dev)
+        vb.gen_primary_rays_dev(ctx, c2w, w, h, d_ro.data_ptr(), d_rd.data_ptr())
+        oro, ord_ = oracle.gen_primary_rays(c2w, w, h)
+        assert (d_ro.cpu().numpy().reshape(-1, 3) == oro).all() and (d_rd.cpu().numpy().reshape(-1, 3) == ord_).all()
+    rng = np.random.default_rng(5)
+    pos = rng.normal(size=(100_000, 3)).astype(np.float32) * 5
+    nor = rng.normal(size=(100_000, 3)).astype(np.float32)
+    nor /= np.linalg.norm(nor, axis=1, keepdims=True)
+    light = np.array([-3.0, 8.5, 10.0], dtype=np.float32)  # raytraced_shadows.rs:33
+    d_p, d_n = torch.from_numpy(pos.reshape(-1)).to(dev), torch.from_numpy(nor.reshape(-1)).to(dev)
+    d_ro, d_rd = torch.empty_like(d_p), torch.empty_like(d_p)
+    vb.gen_shadow_rays_dev(ctx, d_p.data_ptr(), d_n.data_ptr(), pos.shape[0], light, d_ro.data_ptr(), d_rd.data_ptr())
+    oro, ord_ = oracle.gen_shadow_rays(pos, nor, light)
+    assert (d_ro.cpu().numpy().reshape(-1, 3) == oro).all() and (d_rd.cpu().numpy().reshape(-1, 3) == ord_).all()
+    # area light: every direction ends on the rect
+    corners = S.rect_light_corners().astype(np.float32)
+    uv = rng.random((pos.shape[0], 2)).astype(np.float32)
+    d_uv = torch.from_numpy(uv.reshape(-1)).to(dev)
+    vb.gen_area_shadow_rays_dev(ctx, d_p.data_ptr(), d_n.data_ptr(), d_uv.data_ptr(), pos.shape[0], corners, d_ro.data_ptr(), d_rd.data_ptr())
+    end = d_ro.cpu().numpy().reshape(-1, 3).astype(np.float64) + d_rd.cpu().numpy().reshape(-1, 3).astype(np.float64)
+    expect = corners[0] + (corners[1] - corners[0]) * uv[:, :1] + (corners[3] - corners[0]) * uv[:, 1:]
+    assert np.abs(end - expect).max() < 1e-4

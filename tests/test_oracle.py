@@ -143,6 +143,19 @@ def test_traversal_equals_brute_force(oracle):
     assert (t3 == t2).all() and (tri3 == tri2).all() and (ins3 == ins2).all()
 
 
+def test_recursive_traverse_matches_iterative(oracle):
+    v, idx = S.displaced_sphere(36, 72, 9)
+    rc, nodes, perm, _, _ = oracle.blas_build(v, idx)
+    ro, rd = S.rays_toward_box(3000, v.min(0) * 1.5, v.max(0) * 1.5, seed=21)
+    hit, t = oracle.trace_blas_recursive(nodes, v, perm, ro, rd)
+    ti, tri, _ = oracle.trace_blas(nodes, v, perm, ro, rd)
+    has = tri != 0xFFFFFFFF
+    assert has.sum() > 300 and (t[has] == ti[has]).all() and hit[has].all()
+    # box hit without a triangle hit: Hit(t0), the quirk of blas.rs:235,244
+    only_box = hit & ~has
+    assert only_box.sum() > 0 and (t[only_box] == np.float32(1e30)).all()
+
+
 def test_golden_hashes(oracle):
     """Regression pin of the oracle's own outputs (tests/golden/make_golden.py wrote them; the reference has no
     golden vectors of its own — 'parity unpinned', see oracle/bvh_oracle.cpp header)."""

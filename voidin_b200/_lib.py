@@ -29,10 +29,15 @@ SYMBOLS = [
     "bvh_cuda_scene_free",
     "bvh_cuda_trace_blas",
     "bvh_cuda_trace_blas_dev",
+    "bvh_cuda_trace_blas_recursive",
+    "bvh_cuda_trace_blas_recursive_dev",
     "bvh_cuda_trace_closest",
     "bvh_cuda_trace_closest_dev",
     "bvh_cuda_trace_any",
     "bvh_cuda_trace_any_dev",
+    "bvh_cuda_gen_primary_rays_dev",
+    "bvh_cuda_gen_shadow_rays_dev",
+    "bvh_cuda_gen_area_shadow_rays_dev",
 ]
 
 
@@ -117,10 +122,15 @@ def load() -> C.CDLL:
     lib.bvh_cuda_scene_free.restype = None
     lib.bvh_cuda_trace_blas.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, sz, vp, vp]
     lib.bvh_cuda_trace_blas_dev.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp]
+    lib.bvh_cuda_trace_blas_recursive.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, sz, C.c_uint32, C.c_float, vp, vp]
+    lib.bvh_cuda_trace_blas_recursive_dev.argtypes = [vp, vp, vp, vp, vp, vp, sz, C.c_uint32, C.c_float, vp, vp, vp]
     lib.bvh_cuda_trace_closest.argtypes = [vp, vp, vp, vp, sz, C.c_float, vp, vp, vp]
     lib.bvh_cuda_trace_closest_dev.argtypes = [vp, vp, vp, vp, sz, C.c_float, vp, vp, vp, vp]
     lib.bvh_cuda_trace_any.argtypes = [vp, vp, vp, vp, sz, C.c_float, vp]
     lib.bvh_cuda_trace_any_dev.argtypes = [vp, vp, vp, vp, sz, C.c_float, vp, vp]
+    lib.bvh_cuda_gen_primary_rays_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
+    lib.bvh_cuda_gen_shadow_rays_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+    lib.bvh_cuda_gen_area_shadow_rays_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here means the header and the library disagree
     _lib = lib

@@ -95,6 +95,23 @@ class Context:
                                                     d_tri, stream))
 
 
+def gen_primary_rays_dev(ctx: Context, clip_to_world, width: int, height: int, d_ro: int, d_rd: int, stream: int = 0):
+    """Primary rays per pixel (src/bin/bvh_cpu.rs:72-84).  clip_to_world: 16 floats, column-major (glam Mat4)."""
+    m = np.ascontiguousarray(clip_to_world, dtype=np.float32).reshape(16)
+    ctx.check(ctx.lib.bvh_cuda_gen_primary_rays_dev(ctx.h, _vp(m), width, height, d_ro, d_rd, stream))
+
+
+def gen_shadow_rays_dev(ctx: Context, d_pos: int, d_nor: int, n: int, light_pos, d_ro: int, d_rd: int, stream: int = 0):
+    """ray_new(pos + nor*1e-4, light.position - pos) (src/bin/raytraced_shadows.wgsl:93-99)."""
+    l = np.ascontiguousarray(light_pos, dtype=np.float32).reshape(3)
+    ctx.check(ctx.lib.bvh_cuda_gen_shadow_rays_dev(ctx.h, d_pos, d_nor, n, _vp(l), d_ro, d_rd, stream))
+
+
+def gen_area_shadow_rays_dev(ctx: Context, d_pos: int, d_nor: int, d_uv: int, n: int, corners, d_ro: int, d_rd: int, stream: int = 0):
+    c = np.ascontiguousarray(corners, dtype=np.float32).reshape(12)
+    ctx.check(ctx.lib.bvh_cuda_gen_area_shadow_rays_dev(ctx.h, d_pos, d_nor, d_uv, n, _vp(c), d_ro, d_rd, stream))
+
+
 _default_ctx: Context | None = None
 
 
@@ -140,6 +157,24 @@ class Bvh:  # blas.rs:206-208
         ctx.check(ctx.lib.bvh_cuda_trace_blas(ctx.h, _vp(nodes), nodes.shape[0], _vp(v), v.shape[0], _vp(idx),
                                               idx.size // 3, _vp(o), _vp(d), o.shape[0], _vp(t), _vp(tri)))
         return t, tri
+
+    def traverse_batch(self, vertices, indices, ray_o, ray_d, node_idx: int = 0, t: float = 1e30):
+        """Bvh::traverse (recursive variant, blas.rs:211-245) for an array of rays.  Returns (hit[bool], t)."""
+        ctx = self._ctx
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        o = np.ascontiguousarray(ray_o, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(ray_d, dtype=np.float32).reshape(-1, 3)
+        tt = np.empty(o.shape[0], dtype=np.float32)
+        hit = np.empty(o.shape[0], dtype=np.uint8)
+        nodes = np.ascontiguousarray(self.nodes)
+        ctx.check(ctx.lib.bvh_cuda_trace_blas_recursive(ctx.h, _vp(nodes), nodes.shape[0], _vp(v), v.shape[0], _vp(idx), idx.size // 3,
+                                                        _vp(o), _vp(d), o.shape[0], node_idx, t, _vp(tt), _vp(hit)))
+        return hit.astype(bool), tt
+
+    def traverse(self, vertices, indices, ray: Ray, node_idx: int = 0, t: float = 1e30):
+        hit, tt = self.traverse_batch(vertices, indices, ray.orig[None, :], ray.dir[None, :], node_idx, t)
+        return Hit(tt[0]) if hit[0] else MISS
 
     def traverse_iter(self, vertices, indices, ray: Ray):
         t, _ = self.traverse_iter_batch(vertices, indices, ray.orig[None, :], ray.dir[None, :])

@@ -374,6 +374,44 @@ int bvh_cuda_trace_blas(bvh_cuda_ctx* ctx, const BvhNode* nodes, size_t n_nodes,
     return BVH_CUDA_OK;
 }
 
+int bvh_cuda_trace_blas_recursive_dev(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
+                                      const float* d_ray_o, const float* d_ray_d, size_t n_rays, uint32_t node_idx, float t0,
+                                      float* d_t_out, uint8_t* d_hit_out, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return trace_blas_rec_device(ctx, d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, node_idx, t0, d_t_out, d_hit_out,
+                                 (cudaStream_t)stream);
+}
+
+int bvh_cuda_trace_blas_recursive(bvh_cuda_ctx* ctx, const BvhNode* nodes, size_t n_nodes, const float* vertices, size_t n_vertices,
+                                  const uint32_t* indices, size_t n_tris, const float* ray_o, const float* ray_d, size_t n_rays,
+                                  uint32_t node_idx, float t0, float* t_out, uint8_t* hit_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!nodes || !vertices || !indices || !ray_o || !ray_d || !t_out || !hit_out || n_nodes == 0 || node_idx >= n_nodes)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas_recursive: null pointer or node_idx out of range");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->own_stream;
+    Stage st(ctx);
+    const int in = st.add(sizeof(BvhNode) * n_nodes), iv = st.add(sizeof(float) * 3 * n_vertices), ii = st.add(sizeof(uint32_t) * 3 * n_tris),
+              io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays), it = st.add(sizeof(float) * n_rays),
+              ih = st.add(n_rays);
+    int rc = st.commit();
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(st.ptr<void>(in), nodes, sizeof(BvhNode) * n_nodes, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(st.ptr<void>(iv), vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(st.ptr<void>(ii), indices, sizeof(uint32_t) * 3 * n_tris, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(st.ptr<void>(io), ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(st.ptr<void>(id), ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
+    rc = trace_blas_rec_device(ctx, st.ptr<BvhNode>(in), st.ptr<float>(iv), st.ptr<uint32_t>(ii), st.ptr<float>(io), st.ptr<float>(id),
+                               n_rays, node_idx, t0, st.ptr<float>(it), st.ptr<uint8_t>(ih), s);
+    if (rc) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(t_out, st.ptr<void>(it), sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaMemcpyAsync(hit_out, st.ptr<void>(ih), n_rays, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(ctx, cudaStreamSynchronize(s));
+    return BVH_CUDA_OK;
+}
+
 int bvh_cuda_trace_closest_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o, const float* d_ray_d,
                                size_t n_rays, float tmax, float* d_t_out, uint32_t* d_tri_out, uint32_t* d_inst_out, void* stream) {
     if (!ctx) return BVH_CUDA_EINVAL;

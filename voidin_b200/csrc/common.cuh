@@ -73,6 +73,9 @@ int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t str
 int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
                       const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d, size_t n_rays,
                       float* d_t, uint32_t* d_tri, cudaStream_t stream);
+int trace_blas_rec_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
+                          const float* d_ray_o, const float* d_ray_d, size_t n_rays, uint32_t node_idx, float t0, float* d_t,
+                          uint8_t* d_hit, cudaStream_t stream);
 int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
                        const float* d_ray_d, size_t n_rays, float tmax, int any_hit, float* d_t, uint32_t* d_tri,
                        uint32_t* d_inst, uint8_t* d_occ, cudaStream_t stream);

@@ -126,6 +126,45 @@ __global__ void __launch_bounds__(128) k_trace_blas(const BvhNode* __restrict__ 
     tri_out[r] = tri;
 }
 
+// Bvh::traverse (blas.rs:211-245), the recursive variant, as an explicit DFS: left before right, each node's box is
+// tested against the running t when it is visited, Miss only if the start node's box is missed.
+__global__ void __launch_bounds__(128) k_trace_blas_rec(const BvhNode* __restrict__ nodes, const float* __restrict__ V,
+                                                        const uint32_t* __restrict__ I, const float* __restrict__ ro,
+                                                        const float* __restrict__ rd, size_t R, uint32_t node_idx, float t0,
+                                                        float* t_out, uint8_t* hit_out) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float o[3] = {ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]};
+    const float d[3] = {rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]};
+    uint32_t stack[STACK_CAP];
+    int head = 0;
+    stack[head++] = node_idx;
+    float t = t0;
+    bool root_hit = false, first = true;
+    while (head > 0) {
+        const NodeW node = ld_node(nodes, stack[--head]);
+        const bool bh = aabb_rs(o, d, node.a, node.b, t).hit;
+        if (first) { root_hit = bh; first = false; }
+        if (!bh) continue;
+        const uint32_t left_first = __float_as_uint(node.a.w), count = __float_as_uint(node.b.w);
+        if (count > 0) {
+            for (uint32_t i = 0; i < count; ++i) {
+                const uint32_t* idx = I + 3 * (size_t)(left_first + i);
+                const float* p0 = V + 3 * (size_t)idx[0];
+                const float* p1 = V + 3 * (size_t)idx[1];
+                const float* p2 = V + 3 * (size_t)idx[2];
+                const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+                const RDist h = tri_rs(o, d, v0, v1, v2);
+                if (h.hit && h.t < t) t = h.t;  // t.min(dist)
+            }
+        } else {
+            if (head + 2 <= STACK_CAP) { stack[head++] = left_first + 1; stack[head++] = left_first; }
+        }
+    }
+    hit_out[r] = root_hit ? 1 : 0;
+    t_out[r] = root_hit ? t : MAXD;
+}
+
 // ---- WGSL-mode tests --------------------------------------------------------------------------------
 // intersections.wgsl:13-23
 __device__ __forceinline__ float aabb_w(const float* eye, const float* inv, const float4& mn, const float4& mx, float t) {
@@ -344,6 +383,20 @@ int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_
     const size_t blocks = (n_rays + 127) / 128;
     if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: too many rays for one call");
     k_trace_blas<<<(unsigned)blocks, 128, 0, stream>>>(d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, d_t, d_tri);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return BVH_CUDA_OK;
+}
+
+int trace_blas_rec_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
+                          const float* d_ray_o, const float* d_ray_d, size_t n_rays, uint32_t node_idx, float t0, float* d_t,
+                          uint8_t* d_hit, cudaStream_t stream) {
+    if (!d_nodes || !d_vertices || !d_indices || !d_ray_o || !d_ray_d || !d_t || !d_hit)
+        return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas_recursive: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    const size_t blocks = (n_rays + 127) / 128;
+    if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas_recursive: too many rays for one call");
+    k_trace_blas_rec<<<(unsigned)blocks, 128, 0, stream>>>(d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, node_idx, t0, d_t, d_hit);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return BVH_CUDA_OK;
