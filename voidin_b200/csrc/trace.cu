@@ -14,6 +14,11 @@
 namespace {
 
 constexpr int STACK_CAP = 64;        // BLAS stack (reference: 32 in blas.rs:299, 24 in stack.wgsl:1)
+// Lanes that must be waiting before the (more expensive, less frequent) triangle / TLAS paths run in an iteration.
+// Measured on the dragon-class scene: thresholds of 10 ("postponed leaves") were 14 % SLOWER than 1, because lanes
+// parked on a pending leaf thin out the pop path, which is where most instructions are.
+constexpr uint32_t TRI_VOTE = 1;
+constexpr uint32_t TLAS_VOTE = 1;
 constexpr int TLAS_STACK_CAP = 256;  // the reference's agglomerative TLAS can be deep (88 levels on a 32x32 lattice)
 constexpr float MAXD = 1e30f;
 
@@ -229,12 +234,15 @@ __device__ __forceinline__ uint32_t pack_meta(const NodeW& n) {
     return (__float_as_uint(n.a.w) & 0x3FFFFFFFu) | (__float_as_uint(n.b.w) << 30);
 }
 
-// Persistent-warp traversal with dynamic ray fetch.  Per-ray work has a heavy tail (mean ~35 node visits, some
-// rays > 1000), so with one ray per thread for the life of a warp only ~4.5 of 32 lanes were busy (ncu r01b).  Here
-// every lane keeps its own ray state and, at the top of each round (a converged point), idle lanes grab the next
-// unprocessed rays from a global counter (one warp-aggregated atomicAdd).  A round advances each live ray to its
-// next leaf ("while-while": TLAS steps until a BLAS is entered, interior nodes until a leaf, then the leaf's
-// triangles).  The per-ray visit order is exactly the reference's; only the lane/ray assignment is dynamic.
+// Persistent-warp traversal with dynamic ray fetch, one traversal STEP per lane per iteration.
+// Per-ray work has a heavy tail (mean ~35 node visits, some rays > 1000).  With one ray per thread for the life of a
+// warp only ~4.5 of 32 lanes were busy (ncu r01b); a while-while loop ("advance every ray to its next leaf") still ran
+// the interior-node code with 5.4 lanes (ncu r01c), because the number of interior pops before the next leaf varies
+// a lot between rays.  Here every lane keeps its own small state machine and each iteration performs exactly one step
+// of whatever its ray needs next — a TLAS pop, a BLAS pop (interior node: two child boxes; leaf: unpack) or one
+// triangle test — so no lane waits for another ray's loop to end.  At the top of each iteration (a converged point)
+// idle lanes grab the next unprocessed rays from a global counter (one warp-aggregated atomicAdd).  The per-ray
+// visit order is exactly the reference's; only the lane/ray assignment is dynamic.
 template <bool ANY>
 __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                      const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
@@ -250,13 +258,14 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
     float e2[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, inv2[3] = {0, 0, 0};
     float dist = tmax, hit = tmax;
     uint32_t tri = BVH_CUDA_NO_HIT, inst = BVH_CUDA_NO_HIT, ii = 0, tri_base = 0, bvh_index = 0;
+    uint32_t leaf_first = 0, leaf_cnt = 0;  // triangles of the current leaf still to test
     bool res_hit = false;
     bool exhausted = false;  // warp-uniform: the ray counter ran past R
 
     for (;;) {
         // ---- refill idle lanes (converged) ----
         const uint32_t idle = __ballot_sync(FULL_MASK, !active);
-        if (idle != 0 && !exhausted && (__popc(idle) >= 8 || idle == FULL_MASK)) {
+        if (idle != 0 && !exhausted && (__popc(idle) >= 6 || idle == FULL_MASK)) {
             const uint32_t n_idle = __popc(idle);
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(next_ray, (unsigned long long)n_idle);
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                 eye[0] = ro[3 * r]; eye[1] = ro[3 * r + 1]; eye[2] = ro[3 * r + 2];
                 dir[0] = rd[3 * r]; dir[1] = rd[3 * r + 1]; dir[2] = rd[3 * r + 2];
                 inv[0] = __fdiv_rn(1.0f, dir[0]); inv[1] = __fdiv_rn(1.0f, dir[1]); inv[2] = __fdiv_rn(1.0f, dir[2]);
-                th = 0; bh = 0;
+                th = 0; bh = 0; leaf_cnt = 0;
                 tstack[th++] = 0;
                 dist = tmax; hit = tmax;
                 tri = BVH_CUDA_NO_HIT; inst = BVH_CUDA_NO_HIT;
@@ -280,12 +289,41 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
             if (exhausted) break;
             continue;
         }
-        // ---- one round: advance every live ray to (and through) its next leaf ----
-        if (active) {
-            bool finished = false;
-            // TLAS steps (bvh.wgsl:89-123) until a BLAS is entered or the ray is done
-            while (bh == 0 && !finished) {
-                if (th == 0) { finished = true; break; }
+        // ---- vote which step kinds run this iteration ----
+        // The pop path always runs.  The triangle and TLAS paths are more expensive and needed less often, so lanes
+        // that need them wait until enough lanes do (or nothing else can run): "postponed leaves".  A lane's own
+        // sequence of steps is unchanged, so results are identical.
+        const bool want_pop = active && leaf_cnt == 0 && bh > 0;
+        const bool want_tlas = active && leaf_cnt == 0 && bh == 0 && th > 0;
+        const uint32_t n_pop = __popc(__ballot_sync(FULL_MASK, want_pop));
+        const uint32_t n_tlas = __popc(__ballot_sync(FULL_MASK, want_tlas));
+        bool finished = active && leaf_cnt == 0 && bh == 0 && th == 0;
+        if (want_pop) {
+            // traverse_bvh (bvh.wgsl:35-76): one pop
+            const uint32_t m = bstack[--bh];
+            if (m >> 30) {
+                leaf_cnt = m >> 30;
+                leaf_first = m & 0x3FFFFFFFu;
+            } else {
+                const uint32_t c0 = bvh_index + (m & 0x3FFFFFFFu);
+                const NodeW ca = ld_node(sc.bvh_nodes, c0), cb = ld_node(sc.bvh_nodes, c0 + 1);
+                uint32_t min_meta = pack_meta(ca), max_meta = pack_meta(cb);
+                float min_dist = aabb_w(e2, inv2, ca.a, ca.b, hit);
+                float max_dist = aabb_w(e2, inv2, cb.a, cb.b, hit);
+                if (min_dist > max_dist) {
+                    const uint32_t ti = min_meta; min_meta = max_meta; max_meta = ti;
+                    const float td = min_dist; min_dist = max_dist; max_dist = td;
+                }
+                if (!(min_dist >= hit)) {
+                    if (max_dist <= hit && bh < STACK_CAP) bstack[bh++] = max_meta;
+                    if (bh < STACK_CAP) bstack[bh++] = min_meta;
+                }
+            }
+        }
+        const uint32_t n_tri = __popc(__ballot_sync(FULL_MASK, active && leaf_cnt > 0));
+        if (n_tlas != 0 && (n_tlas >= TLAS_VOTE || (n_pop == 0 && n_tri < TRI_VOTE))) {
+            if (want_tlas) {
+                // traverse_tlas (bvh.wgsl:89-123): one pop
                 const uint32_t ni = tstack[--th];
                 const NodeW node = ld_node(sc.tlas_nodes, ni);
                 const uint32_t left_right = __float_as_uint(node.a.w);
@@ -321,53 +359,37 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                         const uint32_t ti = min_index; min_index = max_index; max_index = ti;
                         const float td = min_dist; min_dist = max_dist; max_dist = td;
                     }
-                    if (min_dist >= dist) continue;
-                    if (!twin && max_dist < dist && th < TLAS_STACK_CAP) tstack[th++] = max_index;
-                    if (th < TLAS_STACK_CAP) tstack[th++] = min_index;
-                }
-            }
-            // traverse_bvh (bvh.wgsl:35-76): interior nodes until a leaf
-            uint32_t leaf = 0;
-            while (bh > 0) {
-                const uint32_t m = bstack[--bh];
-                if (m >> 30) { leaf = m; break; }
-                const uint32_t c0 = bvh_index + (m & 0x3FFFFFFFu);
-                const NodeW ca = ld_node(sc.bvh_nodes, c0), cb = ld_node(sc.bvh_nodes, c0 + 1);
-                uint32_t min_meta = pack_meta(ca), max_meta = pack_meta(cb);
-                float min_dist = aabb_w(e2, inv2, ca.a, ca.b, hit);
-                float max_dist = aabb_w(e2, inv2, cb.a, cb.b, hit);
-                if (min_dist > max_dist) {
-                    const uint32_t ti = min_meta; min_meta = max_meta; max_meta = ti;
-                    const float td = min_dist; min_dist = max_dist; max_dist = td;
-                }
-                if (min_dist >= hit) continue;
-                if (max_dist <= hit && bh < STACK_CAP) bstack[bh++] = max_meta;
-                if (bh < STACK_CAP) bstack[bh++] = min_meta;
-            }
-            if (leaf) {
-                const uint32_t count = leaf >> 30, left_first = leaf & 0x3FFFFFFFu;
-                for (uint32_t i = 0; i < count; ++i) {
-                    const uint32_t idx = left_first + i;
-                    const float4* tp = tris + 3 * (size_t)(tri_base + idx);
-                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                    const float v0[3] = {a.x, a.y, a.z}, v1[3] = {b.x, b.y, b.z}, v2[3] = {c.x, c.y, c.z};
-                    if (trig_w(e2, d2, v0, v1, v2, &hit)) {
-                        dist = hit; tri = idx; inst = ii; res_hit = true;
-                        if (ANY) { finished = true; break; }
+                    if (!(min_dist >= dist)) {
+                        if (!twin && max_dist < dist && th < TLAS_STACK_CAP) tstack[th++] = max_index;
+                        if (th < TLAS_STACK_CAP) tstack[th++] = min_index;
                     }
                 }
             }
-            if (!finished && bh == 0 && th == 0) finished = true;
-            if (finished) {
-                if (ANY) {
-                    occ_out[r] = res_hit ? 1 : 0;
-                } else {
-                    t_out[r] = res_hit ? dist : MAXD;
-                    tri_out[r] = tri;
-                    inst_out[r] = inst;
+        }
+        if (n_tri != 0 && (n_tri >= TRI_VOTE || n_pop == 0)) {
+            if (active && leaf_cnt > 0) {
+                // one triangle of the current leaf (bvh.wgsl:43-51)
+                const uint32_t idx = leaf_first;
+                leaf_first++;
+                leaf_cnt--;
+                const float4* tp = tris + 3 * (size_t)(tri_base + idx);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                const float v0[3] = {a.x, a.y, a.z}, v1[3] = {b.x, b.y, b.z}, v2[3] = {c.x, c.y, c.z};
+                if (trig_w(e2, d2, v0, v1, v2, &hit)) {
+                    dist = hit; tri = idx; inst = ii; res_hit = true;
+                    if (ANY) finished = true;
                 }
-                active = false;
             }
+        }
+        if (finished) {
+            if (ANY) {
+                occ_out[r] = res_hit ? 1 : 0;
+            } else {
+                t_out[r] = res_hit ? dist : MAXD;
+                tri_out[r] = tri;
+                inst_out[r] = inst;
+            }
+            active = false;
         }
     }
 }
