@@ -237,7 +237,36 @@ def run_small_configs(args, local_rank):
         return torch.from_numpy(np.ascontiguousarray(a).view(dt).reshape(-1)).to(dev)
 
     out = {"n_gpus": 1, "data": "synthetic", "dtype": "f32", "steps": steps}
-    if args.workload == "bunny":
+    if args.workload == "soup":
+        # BASELINE config 4: 64 Mi-triangle random soup, one BLAS (HBM-bound top levels, grid-wide passes)
+        n = (1 << 26) if args.meshes == 1024 else args.meshes  # --meshes doubles as the triangle count here
+        g = torch.Generator(device=dev); g.manual_seed(4)
+        v0 = torch.rand((n, 1, 3), generator=g, device=dev, dtype=torch.float32)
+        e = (torch.rand((n, 2, 3), generator=g, device=dev, dtype=torch.float32) * 2 - 1) * 0.005
+        d_v = torch.cat([v0, v0 + e], dim=1).reshape(-1).contiguous()
+        del v0, e
+        d_i0 = torch.arange(3 * n, device=dev, dtype=torch.int32)
+        d_i = d_i0.clone()
+        d_nodes = torch.empty(2 * n * 8, dtype=torch.int32, device=dev)
+        ctx.set_profiling(True)
+        mm = [0]
+
+        def build():
+            d_i.copy_(d_i0)
+            mm[0] = ctx.blas_build_dev(d_v.data_ptr(), 3 * n, d_i.data_ptr(), n, d_nodes.data_ptr(), 2 * n, stream)
+
+        b_ms = timed(build, max(1, min(steps, 3)))
+        st = ctx.last_build_stats()
+        bb = build_bytes(n, 3 * n, st["sum_interior_prims"], st["n_nodes"])
+        peak, src = peaks()
+        # order must be a permutation and every leaf range covered exactly once: cheap device-side property checks
+        order = torch.sort(d_i.view(-1, 3)[:, 0] // 3)[0]
+        ok_perm = bool((order == torch.arange(n, device=dev, dtype=torch.int32)).all().item())
+        out.update({"metric": "soup_blas_build_Mtris_per_s", "value": n / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": b_ms,
+                    "config": {"workload": f"config4: {n}-triangle random soup, single BLAS"}, "stats": st, "permutation_ok": ok_perm,
+                    "roofline": {"bound": "hbm", "achieved": bb / (b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": bb / (b_ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes": bb}})
+    elif args.workload == "bunny":
         v, idx = S.bunny_class()
         n = idx.size // 3
         d_v, d_i0 = up(v, np.float32), up(idx, np.int32)
@@ -446,7 +475,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="dragon", choices=["dragon", "scene1024", "bunny", "instances"],
+    ap.add_argument("--workload", default="dragon", choices=["dragon", "scene1024", "bunny", "instances", "soup"],
                     help="dragon = BASELINE config 2 (default, the bench line the driver reads); scene1024 = config 5")
     ap.add_argument("--meshes", type=int, default=1024)
     ap.add_argument("--instances", type=int, default=32767, help="instances workload (config 3): instance count")
@@ -464,7 +493,7 @@ def main():
     if args.workload == "scene1024":
         run_scene1024(args, rank, local_rank, world)
         return
-    if args.workload in ("bunny", "instances"):
+    if args.workload in ("bunny", "instances", "soup"):
         run_small_configs(args, local_rank)
         return
 

@@ -71,3 +71,25 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_headers_compile_as_c_and_cxx(tmp_path):
+    """include/bvh_cuda.h is valid C11 and C++17; the header-only C++ mirror compiles and links against the library
+    (no device calls: without a GPU Context() must throw, with one it must construct)."""
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    c_src = tmp_path / "t.c"
+    c_src.write_text('#include "bvh_cuda.h"\nint main(void){ return sizeof(BvhNode)==32 && sizeof(TlasNode)==32 && sizeof(Instance)==144 && sizeof(MeshInfo)==48 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, str(c_src), "-o", str(tmp_path / "t_c")])
+    assert subprocess.call([str(tmp_path / "t_c")]) == 0
+    cxx_src = tmp_path / "t.cpp"
+    cxx_src.write_text(
+        '#include "bvh_cuda.hpp"\n#include <cstdio>\n'
+        "int main(){ try { bvh_cuda::Context c(0); std::puts(\"ctx\"); } catch (const bvh_cuda::Error& e) { std::puts(\"nogpu\"); }\n"
+        " return bvh_cuda_abi_version() == 1 ? 0 : 1; }\n")
+    libdir = os.path.join(ROOT, "voidin_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", inc, str(cxx_src), "-o", str(tmp_path / "t_cxx"), "-L", libdir,
+                           "-lbvh_cuda", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(tmp_path / "t_cxx")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() in ("ctx", "nogpu")

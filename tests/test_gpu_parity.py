@@ -59,6 +59,14 @@ def test_blas_context_reuse_across_sizes(ctx, oracle):
             assert bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
 
 
+def test_blas_bit_exact_tile_scan_path(ctx, oracle):
+    """> 512 tiles in one node (N > 1 048 576) switches the grid tier to the explicit per-node tile scan."""
+    v, idx = S.soup(1_300_000, 41, 0.004)
+    bvh, gi = gpu_build(ctx, v, idx)
+    rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+    assert rc == 0 and bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
+
+
 def test_blas_matches_committed_golden_hashes(ctx):
     gold = json.load(open(GOLDEN))
     for name, (v, idx) in {"uv_sphere_10": S.make_uv_sphere(1.0, 10), "soup_1000_seed7": S.soup(1000, 7, 0.05),

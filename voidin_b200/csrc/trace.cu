@@ -11,14 +11,18 @@
 // Compiled with -fmad=false: hit ids depend on exact, unfused float arithmetic in the reference's order.
 #include "common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace {
 
 constexpr int STACK_CAP = 64;        // BLAS stack (reference: 32 in blas.rs:299, 24 in stack.wgsl:1)
 // Lanes that must be waiting before the (more expensive, less frequent) triangle / TLAS paths run in an iteration.
 // Measured on the dragon-class scene: thresholds of 10 ("postponed leaves") were 14 % SLOWER than 1, because lanes
 // parked on a pending leaf thin out the pop path, which is where most instructions are.
-constexpr uint32_t TRI_VOTE = 1;
-constexpr uint32_t TLAS_VOTE = 1;
+__constant__ uint32_t c_votes[2] = {1, 1};  // {triangle path, TLAS path}; BVH_CUDA_TRACE_VOTES=tri,tlas overrides (tuning only)
+#define TRI_VOTE c_votes[0]
+#define TLAS_VOTE c_votes[1]
 constexpr int TLAS_STACK_CAP = 256;  // the reference's agglomerative TLAS can be deep (88 levels on a 32x32 lattice)
 constexpr float MAXD = 1e30f;
 
@@ -432,6 +436,16 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     if (n_rays == 0) return BVH_CUDA_OK;
     const float4* tris = reinterpret_cast<const float4*>(scene->baked);
     if (!tris) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: scene has no baked triangles");
+    static const bool votes_set = [] {
+        const char* e = getenv("BVH_CUDA_TRACE_VOTES");
+        unsigned v[2] = {1, 1};
+        if (e && sscanf(e, "%u,%u", &v[0], &v[1]) == 2) {
+            uint32_t hv[2] = {v[0] ? v[0] : 1u, v[1] ? v[1] : 1u};
+            cudaMemcpyToSymbol(c_votes, hv, sizeof(hv));
+        }
+        return true;
+    }();
+    (void)votes_set;
     // persistent warps: the ray counter lives in the scene (8 bytes), reset per launch
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(scene->counter);
     CU_CHECK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
