@@ -121,7 +121,7 @@ def test_set_bin_number_is_inert_like_the_reference(ctx):
     assert a.nodes.tobytes() == b.nodes.tobytes()
 
 
-@pytest.mark.parametrize("n_inst", [1, 2, 3, 10, 100, 1000, 3000])
+@pytest.mark.parametrize("n_inst", [1, 2, 3, 10, 100, 1000, 3000, 12288, 12289, 14001])
 def test_tlas_bit_exact(ctx, oracle, n_inst):
     def builder(v, i):
         b, gi = gpu_build(ctx, v, i)
@@ -144,6 +144,21 @@ def test_tlas_ties_on_a_regular_grid(ctx, oracle):
     verts, inds, nodes, infos = pool.pooled()
     mats = np.stack([S.mat_translation([3.0 * (k % 16), 0.0, 3.0 * (k // 16)]) for k in range(256)])
     inst = S.make_instances(mats, np.zeros(256, dtype=np.int64))
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    rc, otl, okids, _, _ = oracle.tlas_build(inst, infos)
+    assert tl.nodes.tobytes() == otl.tobytes() and (tl.children == okids).all()
+
+
+def test_tlas_ties_on_a_large_lattice_cluster_kernel(ctx, oracle):
+    """128 x 100 lattice of identical boxes: exercises the cluster (distributed shared memory) chain kernel with exact ties."""
+    v, idx = S.make_uv_sphere(1.0, 1)
+    b, gi = gpu_build(ctx, v, idx)
+    pool = S.MeshPool(lambda vv, ii: (b.nodes, gi))
+    pool.add(v, idx)
+    verts, inds, nodes, infos = pool.pooled()
+    mats = np.stack([S.mat_translation([3.0 * (k % 128), 0.0, 3.0 * (k // 128)]) for k in range(128 * 100)])
+    inst = S.make_instances(mats, np.zeros(128 * 100, dtype=np.int64))
     tl = vb.Tlas.empty(ctx)
     tl.build(inst, infos)
     rc, otl, okids, _, _ = oracle.tlas_build(inst, infos)

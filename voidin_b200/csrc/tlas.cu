@@ -10,6 +10,11 @@
 //                   left_right = a + (b << 16) in wrapping u32 (tlas.rs:71).
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
+
 namespace {
 
 constexpr int CHAIN_THREADS = 1024;
@@ -140,6 +145,195 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_tlas_chain(uint32_t n_inst, T
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Cluster version of the chain for 12 K < I <= ~117 K instances: the live slot boxes are spread over the shared
+// memory of a thread-block cluster (16 CTAs on B200, non-portable size), every find_best_match is one local scan,
+// one block reduction and ONE cluster barrier (candidates are exchanged through distributed shared memory, double
+// buffered), instead of a 1024-thread block streaming all slots from L2.  The walk state (a, b, their boxes and
+// node ids, count, nodes_used) is replicated in every thread, so no CTA ever waits to learn what to do next.
+// Same sequence of operations as tlas.rs:56-84, same tie rules.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CL_THREADS = 512;
+constexpr int CL_MAX = 16;
+
+struct Cand {
+    unsigned long long key;  // (area bits << 32) | slot, or ~0 when the CTA has no candidate
+    float box[6];
+    uint32_t ni;
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(CL_THREADS) k_tlas_chain_cluster(uint32_t n_inst, uint32_t cap, TlasNode* nodes, uint32_t* children,
+                                                                  const float* __restrict__ slot_box_init) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t C = cluster.num_blocks(), rank = cluster.block_rank();
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ float s_dyn[];
+    float* bx = s_dyn;                                              // [6][cap] boxes of my slots
+    uint32_t* ni = reinterpret_cast<uint32_t*>(s_dyn + 6 * (size_t)cap);  // [cap] node index of my slots
+    __shared__ Cand s_cl[2][CL_MAX];
+    __shared__ unsigned long long s_red[CL_THREADS / 32];
+    __shared__ unsigned long long s_blk;
+    const uint32_t base = rank * cap;
+
+    for (uint32_t j = tid; j < cap; j += CL_THREADS) {
+        const uint32_t g = base + j;
+        if (g < n_inst) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bx[(size_t)k * cap + j] = slot_box_init[(size_t)k * n_inst + g];
+            ni[j] = g + 1;
+        }
+    }
+    cluster.sync();
+
+    // read one slot (box + node id) from whichever CTA owns it
+    auto read_slot = [&](uint32_t slot, float* box, uint32_t& node_id) {
+        const uint32_t owner = slot / cap, j = slot % cap;
+        const float* rb = cluster.map_shared_rank(bx, owner);
+        const uint32_t* rn = cluster.map_shared_rank(ni, owner);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box[k] = rb[(size_t)k * cap + j];
+        node_id = rn[j];
+    };
+
+    uint32_t par = 0;
+    // find_best_match (tlas.rs:87-105) for a target whose box/node id every thread already knows
+    auto fbm = [&](uint32_t count, uint32_t target, const float* tb, uint32_t t_ni, uint32_t& best, float* bbox, uint32_t& b_ni) {
+        unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
+        for (uint32_t j = tid; j < cap; j += CL_THREADS) {
+            const uint32_t g = base + j;
+            if (g >= count) break;
+            if (g == target) continue;
+            const float lx = fminf(tb[0], bx[j]), ly = fminf(tb[1], bx[(size_t)cap + j]), lz = fminf(tb[2], bx[2 * (size_t)cap + j]);
+            const float hx = fmaxf(tb[3], bx[3 * (size_t)cap + j]), hy = fmaxf(tb[4], bx[4 * (size_t)cap + j]),
+                        hz = fmaxf(tb[5], bx[5 * (size_t)cap + j]);
+            const float sa = aabb_area(lx, ly, lz, hx, hy, hz);
+            if (sa < 1e30f) {
+                const unsigned long long k2 = ((unsigned long long)__float_as_uint(sa) << 32) | g;
+                key = k2 < key ? k2 : key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(FULL_MASK, key, o);
+            key = y < key ? y : key;
+        }
+        if (lane == 0) s_red[warp] = key;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long v = (lane < CL_THREADS / 32) ? s_red[lane] : 0xFFFFFFFFFFFFFFFFull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long y = __shfl_xor_sync(FULL_MASK, v, o);
+                v = y < v ? y : v;
+            }
+            if (lane == 0) s_blk = v;
+        }
+        __syncthreads();
+        const unsigned long long bkey = s_blk;
+        // publish my CTA's candidate into every CTA's exchange buffer (thread t writes to CTA t)
+        if (tid < C) {
+            Cand c;
+            c.key = bkey;
+            c.pad = 0;
+            if (bkey != 0xFFFFFFFFFFFFFFFFull) {
+                const uint32_t j = (uint32_t)(bkey & 0xFFFFFFFFull) - base;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) c.box[k] = bx[(size_t)k * cap + j];
+                c.ni = ni[j];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) c.box[k] = 0.0f;
+                c.ni = 0;
+            }
+            Cand* dst = cluster.map_shared_rank(&s_cl[par][rank], tid);
+            *dst = c;
+        }
+        cluster.sync();
+        unsigned long long gk = 0xFFFFFFFFFFFFFFFFull;
+        uint32_t gw = 0;
+        for (uint32_t r2 = 0; r2 < C; ++r2) {
+            const unsigned long long k2 = s_cl[par][r2].key;
+            if (k2 < gk) { gk = k2; gw = r2; }
+        }
+        if (gk == 0xFFFFFFFFFFFFFFFFull) {
+            best = target;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bbox[k] = tb[k];
+            b_ni = t_ni;
+        } else {
+            best = (uint32_t)(gk & 0xFFFFFFFFull);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bbox[k] = s_cl[par][gw].box[k];
+            b_ni = s_cl[par][gw].ni;
+        }
+        par ^= 1;
+    };
+
+    uint32_t count = n_inst, used = 1 + n_inst;
+    uint32_t a = 0, b = 0, a_ni = 0, b_ni = 0;
+    float a_box[6], b_box[6];
+    read_slot(0, a_box, a_ni);
+    fbm(count, a, a_box, a_ni, b, b_box, b_ni);
+    while (count > 0) {
+        uint32_t c = 0, c_ni = 0;
+        float c_box[6];
+        fbm(count, b, b_box, b_ni, c, c_box, c_ni);
+        if (a == c) {
+            float u[6];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { u[k] = fminf(a_box[k], b_box[k]); u[3 + k] = fmaxf(a_box[3 + k], b_box[3 + k]); }
+            const uint32_t last = count - 1;
+            if (rank == 0 && tid == 0) {
+                TlasNode nd;
+                nd.min[0] = u[0]; nd.min[1] = u[1]; nd.min[2] = u[2];
+                nd.max[0] = u[3]; nd.max[1] = u[4]; nd.max[2] = u[5];
+                nd.left_right = a_ni + (b_ni << 16);
+                nd.instance_idx = 0xFFFFFFFFu;
+                nodes[used] = nd;
+                if (children) { children[2 * (size_t)used] = a_ni; children[2 * (size_t)used + 1] = b_ni; }
+            }
+            // node_indices[a] = used; node_indices[b] = node_indices[last] (tlas.rs:74-76), in that order
+            float lb[6];
+            uint32_t l_ni = used;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) lb[k] = u[k];
+            if (last != a && tid == 0 && b / cap == rank) read_slot(last, lb, l_ni);
+            if (tid == 0 && a / cap == rank) {
+                const uint32_t j = a % cap;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bx[(size_t)k * cap + j] = u[k];
+                ni[j] = used;
+            }
+            if (tid == 0 && b / cap == rank) {
+                const uint32_t j = b % cap;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) bx[(size_t)k * cap + j] = lb[k];
+                ni[j] = l_ni;
+            }
+            cluster.sync();
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a_box[k] = u[k];
+            a_ni = used;
+            if (a == b) read_slot(a, a_box, a_ni);  // slot a was overwritten by the swap-remove
+            used += 1;
+            count -= 1;
+            fbm(count, a, a_box, a_ni, b, b_box, b_ni);
+        } else {
+            a = b; a_ni = b_ni;
+            b = c; b_ni = c_ni;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { a_box[k] = b_box[k]; b_box[k] = c_box[k]; }
+        }
+    }
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+        nodes[0] = nodes[a_ni];
+        if (children) { children[0] = children[2 * (size_t)a_ni]; children[1] = children[2 * (size_t)a_ni + 1]; }
+    }
+}
+
 }  // namespace
 
 int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
@@ -159,7 +353,35 @@ int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_i
     CU_CHECK(ctx, cudaMemsetAsync(d_nodes_out, 0, sizeof(TlasNode), stream));
     k_tlas_leaves<<<(I + 255) / 256, 256, 0, stream>>>(d_instances, I, d_meshes, (uint32_t)n_mesh, d_nodes_out, d_children_out,
                                                       slot_box, node_indices, err);
-    k_tlas_chain<<<1, CHAIN_THREADS, 0, stream>>>(I, d_nodes_out, d_children_out, slot_box, node_indices);
+    bool clustered = false;
+    static const bool no_cluster = [] { const char* e = getenv("BVH_CUDA_TLAS"); return e && e[0] == 'b'; }();  // "block": force the one-block kernel
+    if (I > 12288 && !no_cluster) {  // measured crossover: 4 096 -> block 16.7 ms vs cluster 25.1 ms; 32 767 -> 594 ms vs 234 ms
+        const uint32_t cap = (I + CL_MAX - 1) / CL_MAX;
+        const size_t smem = sizeof(float) * 6 * (size_t)cap + sizeof(uint32_t) * (size_t)cap;
+        if (smem <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_tlas_chain_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tlas_chain_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(CL_MAX);
+                cfg.blockDim = dim3(CL_THREADS);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = CL_MAX;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                uint32_t cap_arg = cap;
+                e = cudaLaunchKernelEx(&cfg, k_tlas_chain_cluster, I, cap_arg, d_nodes_out, d_children_out, (const float*)slot_box);
+            }
+            if (e == cudaSuccess) clustered = true;
+            else cudaGetLastError();  // fall through to the one-block kernel (e.g. a 16-CTA cluster cannot be placed)
+        }
+    }
+    if (!clustered) k_tlas_chain<<<1, CHAIN_THREADS, 0, stream>>>(I, d_nodes_out, d_children_out, slot_box, node_indices);
     ctx->launches += 2;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaStreamSynchronize(stream));
