@@ -29,9 +29,19 @@ def small_meshes():
         ("displaced_sphere_5k", *S.displaced_sphere(36, 72, 9)),
         ("dup_centroids_3", *dup_centroids()),
     ]
-    if os.path.exists(REF_CUBE):
-        out.append(("cube_obj", *S.load_obj_positions(REF_CUBE)))
+    out += real_meshes()
     return out
+
+
+def real_meshes():
+    """Real geometry of the reference checkout (cube.obj, DamagedHelmet.glb, AntiqueCamera.gltf), extracted once by
+    tests/golden/make_real_meshes.py into a committed .npz so it travels to the GPU box."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_meshes.npz")
+    if not os.path.exists(path):
+        return []
+    d = np.load(path)
+    names = sorted({k[:-2] for k in d.files})
+    return [("real_" + n, np.ascontiguousarray(d[n + "_v"]), np.ascontiguousarray(d[n + "_i"])) for n in names]
 
 
 def dup_centroids():

@@ -156,6 +156,21 @@ def test_recursive_traverse_matches_iterative(oracle):
     assert only_box.sum() > 0 and (t[only_box] == np.float32(1e30)).all()
 
 
+def test_real_meshes_match_the_survey_statistics(oracle):
+    """SURVEY.md Appendix F (an independent scratch restatement made during the survey): cube.obj 420 nodes / 209
+    interior / depth 11; DamagedHelmet 13 916 nodes / 6 957 interior / depth 19 / 2 474 final-pivot mismatches."""
+    from helpers import real_meshes
+
+    got = {n: oracle.blas_build(v, i) for n, v, i in real_meshes()}
+    if not got:
+        pytest.skip("tests/golden/real_meshes.npz missing")
+    rc, nodes, _, _, st = got["real_cube"]
+    assert rc == 0 and len(nodes) == 420 and st["interior_nodes"] == 209 and st["max_depth"] == 11 and st["final_pivot_differs"] == 61 and st["nan_candidates"] == 38
+    rc, nodes, _, _, st = got["real_helmet0"]
+    assert rc == 0 and len(nodes) == 13916 and st["interior_nodes"] == 6957 and st["max_depth"] == 19
+    assert st["final_pivot_differs"] == 2474 and st["nan_candidates"] == 1920 and st["candidates"] == 21 * 6957  # the survey counts 22 shuffles per node: 153 054
+
+
 def test_golden_hashes(oracle):
     """Regression pin of the oracle's own outputs (tests/golden/make_golden.py wrote them; the reference has no
     golden vectors of its own — 'parity unpinned', see oracle/bvh_oracle.cpp header)."""

@@ -421,3 +421,59 @@ def gbuffer_shadow_rays(n: int, dragon_world_tris: np.ndarray, light_corners: np
     d = np.concatenate([d1, d2])
     perm = np.random.default_rng(seed + 2000).permutation(n)  # interleave, as neighbouring pixels would be
     return np.ascontiguousarray(o[perm]), np.ascontiguousarray(d[perm])
+
+
+# ----------------------------------------------------------------------------------------------
+# minimal glTF 2.0 reader (positions + indices of every mesh primitive; no node transforms), the subset of
+# crates/app/src/models/gltf_model/mod.rs:103-155 that feeds MeshPool::add
+# ----------------------------------------------------------------------------------------------
+def load_gltf_primitives(path: str):
+    """Returns [(vertices [V,3] f32, indices [3N] u32), ...] for a .glb or a .gltf with external .bin buffers."""
+    import json
+    import os
+    import struct
+
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:4] == b"glTF":
+        length = struct.unpack_from("<I", raw, 8)[0]
+        off, doc, bins = 12, None, []
+        while off < length:
+            clen, ctype = struct.unpack_from("<II", raw, off)
+            chunk = raw[off + 8: off + 8 + clen]
+            if ctype == 0x4E4F534A:
+                doc = json.loads(chunk.decode("utf-8"))
+            elif ctype == 0x004E4942:
+                bins.append(chunk)
+            off += 8 + clen
+        buffers = bins
+    else:
+        doc = json.loads(raw.decode("utf-8"))
+        base = os.path.dirname(path)
+        buffers = [open(os.path.join(base, b["uri"]), "rb").read() for b in doc["buffers"]]
+    ctype_np = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+    ncomp = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4}
+
+    def accessor(i):
+        a = doc["accessors"][i]
+        bv = doc["bufferViews"][a["bufferView"]]
+        dt = np.dtype(ctype_np[a["componentType"]])
+        n = ncomp[a["type"]]
+        start = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+        stride = bv.get("byteStride", 0) or dt.itemsize * n
+        buf = buffers[bv["buffer"]]
+        if stride == dt.itemsize * n:
+            return np.frombuffer(buf, dtype=dt, count=a["count"] * n, offset=start).reshape(a["count"], n)
+        rows = np.lib.stride_tricks.as_strided(np.frombuffer(buf, dtype=np.uint8, offset=start),
+                                               shape=(a["count"], dt.itemsize * n), strides=(stride, 1))
+        return np.ascontiguousarray(rows).view(dt).reshape(a["count"], n)
+
+    out = []
+    for mesh in doc.get("meshes", []):
+        for prim in mesh["primitives"]:
+            if prim.get("mode", 4) != 4 or "indices" not in prim:
+                continue
+            v = np.ascontiguousarray(accessor(prim["attributes"]["POSITION"]), dtype=F32)
+            idx = np.ascontiguousarray(accessor(prim["indices"]).reshape(-1).astype(np.uint32))
+            out.append((v, idx[: idx.size // 3 * 3]))
+    return out
