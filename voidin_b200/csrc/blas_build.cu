@@ -1225,16 +1225,25 @@ __device__ __forceinline__ void p_t1_tilescan(const T1Args& g, int c) {
 }
 
 // Ballots + per-element #L-before (LF) of one tile.  Layout: j = j0 + warp*256 + i*32 + lane.
+// Issues the tile's flag loads early (before anything that waits on other loads or barriers).
 template <int EPT>
-__device__ __forceinline__ void t1_prefix(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint32_t a,
-                                          uint32_t b, uint32_t tile_lf, uint32_t* s_w, uint32_t* bal, uint32_t* LFv,
-                                          uint16_t* fw) {
+__device__ __forceinline__ void t1_load_flags(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint16_t* fw) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+        fw[i] = (j < n) ? fl[start + j] : (uint16_t)0;
+    }
+}
+
+template <int EPT>
+__device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, uint32_t b, uint32_t tile_lf, uint32_t* s_w,
+                                          uint32_t* bal, uint32_t* LFv, const uint16_t* fw) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cnt = 0;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
         const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
-        fw[i] = (j < n) ? fl[start + j] : (uint16_t)0;
         const bool L = (j < n) && ((((uint32_t)fw[i] >> (3 * a)) & 7u) < b);
         bal[i] = __ballot_sync(FULL_MASK, L);
         cnt += __popc(bal[i]);
@@ -1264,6 +1273,8 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x, start = td.y, n = td.z, lt = td.w, tile_base = tile - lt, j0 = lt * T1_TILE;
+        uint16_t fw[EPT];
+        t1_load_flags<EPT>(fl, start, n, j0, fw);
         uint32_t a, b;
         cand_of(g.sc, node, c, a, b);
         // flag of the element just before this warp's first slot (needed for the transition test)
@@ -1292,8 +1303,7 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
             if (tid == 0) g.tileLF[tile] = tile_lf;
         }
         uint32_t bal[EPT], LFv[EPT];
-        uint16_t fw[EPT];
-        t1_prefix<EPT>(fl, start, n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
+        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
         uint32_t prev_pred_bit31 = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -1347,13 +1357,21 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
         const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t n = nd.n;
+        uint16_t fwv[EPT];
+        uint32_t idv[EPT];
+        t1_load_flags<EPT>(fl, nd.start, n, j0, fwv);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            idv[i] = (j < n) ? ids_in[nd.start + j] : 0u;
+        }
         uint32_t a, b;
         cand_of(g.sc, node, c, a, b);
         const uint4 sh = g.sc[node].sh[c];
-        const uint32_t nL = sh.x, f = sh.y, pivot = sh.z, n = nd.n;
+        const uint32_t nL = sh.x, f = sh.y, pivot = sh.z;
         uint32_t bal[EPT], LFv[EPT];
-        uint16_t fwv[EPT];
-        t1_prefix<EPT>(fl, nd.start, n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv);
+        t1_prefix<EPT>(n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv);
         uint32_t own_cnt = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -1363,7 +1381,7 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
             if (j < n) {
                 const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = LFv[i], RF = j - LF;
-                const uint32_t id = ids_in[nd.start + j];
+                const uint32_t id = idv[i];
                 uint32_t fw = fwv[i];
                 uint32_t dest;
                 if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : g.table[nd.start + n - RF] - 1u);
