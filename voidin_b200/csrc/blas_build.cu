@@ -26,6 +26,9 @@ constexpr int T3_MAX = 32;
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
 constexpr int T2_CAP = 2048;    // block-per-node tier: 257..2048 (256 threads)
 constexpr int T2_THREADS = 256;
+#ifndef T2_MIN_BLOCKS
+#define T2_MIN_BLOCKS 3  // 64 registers, no spills; 0.85 -> 0.61 ms for the tier on the dragon-class mesh (4 gives no more)
+#endif
 constexpr int T2B_CAP = 16384;  // big-block tier: 2049..16384 (1024 threads, one block per SM)
 constexpr int T2B_THREADS = 1024;
 constexpr int T1_TILE = 2048;
@@ -398,7 +401,7 @@ __device__ __forceinline__ bool queue_pop(Task* q, uint32_t cap, uint32_t* head,
 }
 
 template <int CAP, int THREADS, bool BIG>
-__global__ void __launch_bounds__(THREADS) k_t2(Queues Q, uint32_t* ids, uint32_t* ids_snap,
+__global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues Q, uint32_t* ids, uint32_t* ids_snap,
                                                 const float4* __restrict__ cent, const float4* __restrict__ box,
                                                 uint4* recs, uint32_t* A, BuildState* st, uint32_t epoch) {
     constexpr int NW = THREADS / 32;
