@@ -133,6 +133,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->trace_counter) cudaFree(ctx->trace_counter);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

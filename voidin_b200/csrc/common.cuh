@@ -39,6 +39,7 @@ struct bvh_cuda_ctx {
     // host-API staging arena (grow-only, so repeated host calls do not cudaMalloc)
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    void* trace_counter = nullptr;  // persistent-warp ray counter of trace_blas
     // optional per-phase timing
     bool profiling = false;
     cudaEvent_t ev[8] = {};

@@ -86,53 +86,95 @@ __device__ __forceinline__ RDist tri_rs(const float* o, const float* d, const fl
     return r;
 }
 
+// Bvh::traverse_iter (blas.rs:247-295) with persistent warps, dynamic ray fetch and one step per lane per iteration
+// (same scheme as k_trace_scene below).  Stack entries are node indices as in the reference: the popped node is
+// re-read, because a leaf's triangles and an interior node's children both hang off its (left_first, count).
 __global__ void __launch_bounds__(128) k_trace_blas(const BvhNode* __restrict__ nodes, const float* __restrict__ V,
                                                     const uint32_t* __restrict__ I, const float* __restrict__ ro,
                                                     const float* __restrict__ rd, size_t R, float* t_out,
-                                                    uint32_t* tri_out) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const float o[3] = {ro[3 * r], ro[3 * r + 1], ro[3 * r + 2]};
-    const float d[3] = {rd[3 * r], rd[3 * r + 1], rd[3 * r + 2]};
+                                                    uint32_t* tri_out, unsigned long long* next_ray) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t stack[STACK_CAP];
     int head = 0;
-    stack[head++] = 0;
+    bool active = false, exhausted = false;
+    size_t r = 0;
+    float o[3] = {0, 0, 0}, d[3] = {0, 0, 0};
     bool hit = false;
     float t = 0.0f;
-    uint32_t tri = BVH_CUDA_NO_HIT;
-    while (head > 0) {
-        const NodeW node = ld_node(nodes, stack[--head]);
-        const uint32_t left_first = __float_as_uint(node.a.w), count = __float_as_uint(node.b.w);
-        if (count > 0) {
-            for (uint32_t i = 0; i < count; ++i) {
-                const uint32_t* idx = I + 3 * (size_t)(left_first + i);
-                const float* p0 = V + 3 * (size_t)idx[0];
-                const float* p1 = V + 3 * (size_t)idx[1];
-                const float* p2 = V + 3 * (size_t)idx[2];
-                const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
-                const RDist h = tri_rs(o, d, v0, v1, v2);
-                if (h.hit) {
-                    if (!hit) { hit = true; t = h.t; tri = left_first + i; }
-                    else if (h.t < t) { t = h.t; tri = left_first + i; }
+    uint32_t tri = BVH_CUDA_NO_HIT, leaf_first = 0, leaf_cnt = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(FULL_MASK, !active);
+        if (idle != 0 && !exhausted && (__popc(idle) >= 6 || idle == FULL_MASK)) {
+            const uint32_t n_idle = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next_ray, (unsigned long long)n_idle);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (base + n_idle >= R) exhausted = true;
+            const unsigned long long mine = base + __popc(idle & lt_mask);
+            if (!active && mine < R) {
+                r = (size_t)mine;
+                o[0] = ro[3 * r]; o[1] = ro[3 * r + 1]; o[2] = ro[3 * r + 2];
+                d[0] = rd[3 * r]; d[1] = rd[3 * r + 1]; d[2] = rd[3 * r + 2];
+                head = 0;
+                stack[head++] = 0;
+                hit = false; t = 0.0f; tri = BVH_CUDA_NO_HIT; leaf_cnt = 0;
+                active = true;
+            }
+        }
+        if (__ballot_sync(FULL_MASK, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        if (!active) continue;
+        bool finished = false;
+        if (leaf_cnt == 0) {
+            if (head > 0) {
+                const NodeW node = ld_node(nodes, stack[--head]);
+                const uint32_t left_first = __float_as_uint(node.a.w), count = __float_as_uint(node.b.w);
+                if (count > 0) {
+                    leaf_first = left_first;
+                    leaf_cnt = count;
+                } else {
+                    uint32_t min_index = left_first, max_index = left_first + 1;
+                    const NodeW ca = ld_node(nodes, min_index), cb = ld_node(nodes, max_index);
+                    const float lim = hit ? t : MAXD;
+                    RDist min_dist = aabb_rs(o, d, ca.a, ca.b, lim);
+                    RDist max_dist = aabb_rs(o, d, cb.a, cb.b, lim);
+                    if (dist_gt(min_dist, max_dist)) {
+                        const uint32_t ti = min_index; min_index = max_index; max_index = ti;
+                        const RDist td = min_dist; min_dist = max_dist; max_dist = td;
+                    }
+                    if (min_dist.hit) {
+                        if (head < STACK_CAP) stack[head++] = min_index;
+                        if (max_dist.hit && head < STACK_CAP) stack[head++] = max_index;
+                    }
                 }
+            } else {
+                finished = true;
             }
-        } else {
-            uint32_t min_index = left_first, max_index = left_first + 1;
-            const NodeW ca = ld_node(nodes, min_index), cb = ld_node(nodes, max_index);
-            const float lim = hit ? t : MAXD;
-            RDist min_dist = aabb_rs(o, d, ca.a, ca.b, lim);
-            RDist max_dist = aabb_rs(o, d, cb.a, cb.b, lim);
-            if (dist_gt(min_dist, max_dist)) {
-                const uint32_t ti = min_index; min_index = max_index; max_index = ti;
-                const RDist td = min_dist; min_dist = max_dist; max_dist = td;
+        }
+        if (leaf_cnt > 0) {
+            const uint32_t ti = leaf_first;
+            leaf_first++;
+            leaf_cnt--;
+            const uint32_t* idx = I + 3 * (size_t)ti;
+            const float* p0 = V + 3 * (size_t)idx[0];
+            const float* p1 = V + 3 * (size_t)idx[1];
+            const float* p2 = V + 3 * (size_t)idx[2];
+            const float v0[3] = {p0[0], p0[1], p0[2]}, v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+            const RDist h = tri_rs(o, d, v0, v1, v2);
+            if (h.hit) {
+                if (!hit) { hit = true; t = h.t; tri = ti; }
+                else if (h.t < t) { t = h.t; tri = ti; }
             }
-            if (!min_dist.hit) continue;
-            if (head < STACK_CAP) stack[head++] = min_index;
-            if (max_dist.hit && head < STACK_CAP) stack[head++] = max_index;
+        }
+        if (finished) {
+            t_out[r] = hit ? t : MAXD;
+            tri_out[r] = tri;
+            active = false;
         }
     }
-    t_out[r] = hit ? t : MAXD;
-    tri_out[r] = tri;
 }
 
 // Bvh::traverse (blas.rs:211-245), the recursive variant, as an explicit DFS: left before right, each node's box is
@@ -406,9 +448,12 @@ int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_
     if (!d_nodes || !d_vertices || !d_indices || !d_ray_o || !d_ray_d || !d_t || !d_tri)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: null pointer");
     if (n_rays == 0) return BVH_CUDA_OK;
-    const size_t blocks = (n_rays + 127) / 128;
-    if (blocks > 0x7FFFFFFFull) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_blas: too many rays for one call");
-    k_trace_blas<<<(unsigned)blocks, 128, 0, stream>>>(d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, d_t, d_tri);
+    if (!ctx->trace_counter) CU_CHECK(ctx, cudaMalloc(&ctx->trace_counter, 256));
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(ctx->trace_counter);
+    CU_CHECK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    const size_t want = (n_rays + 127) / 128;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    k_trace_blas<<<(unsigned)(want < cap ? want : cap), 128, 0, stream>>>(d_nodes, d_vertices, d_indices, d_ray_o, d_ray_d, n_rays, d_t, d_tri, counter);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return BVH_CUDA_OK;
