@@ -165,6 +165,28 @@ def test_tlas_ties_on_a_large_lattice_cluster_kernel(ctx, oracle):
     assert tl.nodes.tobytes() == otl.tobytes() and (tl.children == okids).all()
 
 
+def test_tlas_signed_zero_boxes_bit_exact(ctx, oracle):
+    """Instance boxes whose faces sit exactly at +-0: the folds keep the first zero they meet (tlas.rs:43,69-70)."""
+    v = np.array([[-0.0, 0.0, -0.0], [1, 0.0, 0.0], [0.0, 1, -0.0], [0.0, -0.0, 1]], dtype=np.float32)
+    idx = np.array([0, 1, 2, 0, 2, 3, 0, 3, 1, 1, 3, 2], dtype=np.uint32)
+    b, gi = gpu_build(ctx, v, idx)
+    pool = S.MeshPool(lambda vv, ii: (b.nodes, gi))
+    pool.add(v, idx)
+    verts, inds, nodes, infos = pool.pooled()
+    mats = []
+    for k in range(60):
+        m = np.eye(4)
+        m[0, 0] = -1.0 if k % 2 else 1.0  # mirrored instances turn +0 into -0
+        m[1, 1] = -1.0 if k % 3 == 0 else 1.0
+        m[:3, 3] = [0.0 if k % 4 else 2.0 * (k // 4), 0.0, 0.0 if k % 5 else 1.0 * k]
+        mats.append(m)
+    inst = S.make_instances(np.stack(mats), np.zeros(60, dtype=np.int64))
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    rc, otl, okids, _, _ = oracle.tlas_build(inst, infos)
+    assert tl.nodes.tobytes() == otl.tobytes() and (tl.children == okids).all()
+
+
 def test_trace_two_level_ids_exact(ctx, oracle):
     def builder(v, i):
         b, gi = gpu_build(ctx, v, i)
@@ -335,25 +357,16 @@ def test_ray_generation_bit_exact(ctx, oracle):
     assert np.abs(end - expect).max() < 1e-4
 
 
-def test_blas_negative_zero_inputs_known_deviation(ctx, oracle):
-    """Documented deviation: when a box face is exactly 0 and the vertices on it mix -0.0 and +0.0, the
-    reference keeps the first zero its fold meets (f32::min/max keep the accumulator); the GPU reductions order
-    -0 < +0.  Topology, primitive order and every box value are identical; only the sign bit of such a zero may differ."""
-    v, idx = S.soup(3000, 77, 0.2)
-    q = np.float32(1 / 16)
-    v = (np.round(v / q) * q).astype(np.float32)  # produces both -0.0 and +0.0
+@pytest.mark.parametrize("n,q", [(20, 1 / 4), (300, 1 / 16), (3000, 1 / 16), (40_000, 1 / 64)])
+def test_blas_negative_zero_inputs_bit_exact(ctx, oracle, n, q):
+    """Inputs that mix -0.0 and +0.0 on a box face: the reference keeps the first zero its sequential fold meets
+    (f32::min/max keep the accumulator, blas.rs:190-198).  The kernels reproduce that on a rare-path (first slot with
+    a zero on that face, in the order the node sees when it computes its box), so even the sign bits match."""
+    v, idx = S.soup(n, 77, 0.2)
+    v = (np.round(v / np.float32(q)) * np.float32(q)).astype(np.float32)  # produces both -0.0 and +0.0
     assert (np.signbit(v) & (v == 0)).any()
-    bvh, gi = gpu_build(ctx, v, idx)
     rc, onodes, oidx, oorder, _ = oracle.blas_build(v, idx)
-    assert rc == 0 and len(bvh.nodes) == len(onodes)
-    assert (bvh.nodes["left_first"] == onodes["left_first"]).all() and (bvh.nodes["count"] == onodes["count"]).all()
-    assert (gi == oidx).all() and (ctx.last_order(idx.size // 3) == oorder).all()
-    assert (bvh.nodes["min"] == onodes["min"]).all() and (bvh.nodes["max"] == onodes["max"]).all()  # float ==: -0 == +0
-    bits = lambda a: np.ascontiguousarray(a).view(np.uint32)
-    gmin, gmax, omin, omax = (np.ascontiguousarray(x) for x in (bvh.nodes["min"], bvh.nodes["max"], onodes["min"], onodes["max"]))
-    assert (gmin[bits(gmin) != bits(omin)] == 0).all() and (gmax[bits(gmax) != bits(omax)] == 0).all()
-    # canonicalised input (no -0.0) is bit-exact
-    v2 = v + np.float32(0.0)
-    bvh2, gi2 = gpu_build(ctx, v2, idx)
-    rc, onodes2, oidx2, _, _ = oracle.blas_build(v2, idx)
-    assert bvh2.nodes.tobytes() == onodes2.tobytes() and (gi2 == oidx2).all()
+    if rc != 0:
+        pytest.skip("degenerate for the reference")
+    bvh, gi = gpu_build(ctx, v, idx)
+    assert bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()

@@ -54,6 +54,7 @@ struct NodeScratch {
     uint32_t best, pad;
     uint32_t piv[21], uid[21];
     uint32_t bins[3][8][6];
+    unsigned long long zkey[6];  // rare -0.0 path: (first slot with a zero on this face << 32) | its triangle id
 };
 
 struct BuildState {
@@ -72,7 +73,7 @@ struct BuildState {
     uint32_t t2w_done;
     uint32_t levels_done;
     uint32_t t3_inline;
-    uint32_t pad[1];
+    uint32_t neg_zero;  // some referenced vertex coordinate is -0.0: box zeros need the reference's first-encounter sign
 };
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -144,13 +145,21 @@ __global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint
     const float* b = V + 3 * (size_t)(vb + i1);
     const float* c = V + 3 * (size_t)(vb + i2);
     float lo[3], hi[3], ce[3];
+    bool nz = false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float x = a[k], y = b[k], z = c[k];
         ce[k] = __fdiv_rn(__fadd_rn(__fadd_rn(x, y), z), 3.0f);
-        lo[k] = fminf(fminf(fminf(1e30f, x), y), z);
-        hi[k] = fmaxf(fmaxf(fmaxf(-1e30f, x), y), z);
+        // f32::min / f32::max keep the accumulator unless the new value is strictly smaller / larger
+        // (blas.rs:190-198): among equal zeros of different sign the first one met stays.
+        float l = 1e30f, h = -1e30f;
+        l = (x < l) ? x : l; l = (y < l) ? y : l; l = (z < l) ? z : l;
+        h = (x > h) ? x : h; h = (y > h) ? y : h; h = (z > h) ? z : h;
+        lo[k] = l;
+        hi[k] = h;
+        nz = nz || __float_as_uint(x) == 0x80000000u || __float_as_uint(y) == 0x80000000u || __float_as_uint(z) == 0x80000000u;
     }
+    if (nz) atomicOr(&st->neg_zero, 1u);
     cent[i] = make_float4(ce[0], ce[1], ce[2], 0.0f);
     box[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
     box[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
@@ -173,6 +182,7 @@ struct T3Smem {
 __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint32_t lane, uint32_t* ids,
                                            const float4* __restrict__ cent, const float4* __restrict__ box, uint4* recs,
                                            uint32_t* A, BuildState* st) {
+    const bool nz = st->neg_zero != 0;
     float (*sm_box)[32] = sm.box;
     float (*sm_cent)[32] = sm.cent;
     uint32_t* sm_gid = sm.gid;
@@ -208,6 +218,20 @@ __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint
             mx = max(__reduce_max_sync(FULL_MASK, mx), ENC_NEG_INIT);
             lo[c] = o2f(mn);
             hi[c] = o2f(mx);
+        }
+        if (nz) {
+            // rare path (-0.0 in the input): a zero face takes the sign of the first zero in slot order, as the
+            // reference's sequential fold does (lane order == slot order here)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const float cur = (c < 3) ? lo[c] : hi[c - 3];
+                if (cur == 0.0f) {
+                    const float mine = sm_box[c][e];
+                    const uint32_t p = __reduce_min_sync(FULL_MASK, (active && mine == 0.0f) ? lane : 32u);
+                    const float z = __shfl_sync(FULL_MASK, mine, p & 31u);
+                    if (c < 3) lo[c] = z; else hi[c - 3] = z;
+                }
+            }
         }
         bool descend = false;
         if (n <= 3) {  // leaf (blas.rs:106-109)
@@ -427,6 +451,7 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
     __shared__ Task s_task;
     __shared__ int s_have;
     __shared__ uint32_t s_best;
+    __shared__ uint32_t s_zpos[6];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -485,7 +510,32 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
             s_node[tid] = r;
         }
         for (uint32_t k = tid; k < 144; k += THREADS) (&s_bins[0][0][0])[k] = ((k % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
+        if (tid < 6) s_zpos[tid] = 0xFFFFFFFFu;
         __syncthreads();
+        if (st->neg_zero) {
+            // rare path (-0.0 in the input): remember, per zero-valued face, the first slot that holds a zero there
+            bool zero_face[6];
+            bool any_zero = false;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                zero_face[c] = o2f(c < 3 ? min(s_node[c], ENC_POS_INIT) : max(s_node[c], ENC_NEG_INIT)) == 0.0f;
+                any_zero = any_zero || zero_face[c];
+            }
+            if (any_zero) {
+                for (uint32_t i = 0; i < E; ++i) {
+                    const uint32_t j = warp * CHUNK + i * 32 + lane;
+                    if (j < n) {
+                        const uint32_t g = __ldcg(&ids_snap[start + j]);
+                        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+                        const float vals[6] = {b0.x, b0.y, b0.z, b1.x, b1.y, b1.z};
+#pragma unroll
+                        for (int c = 0; c < 6; ++c)
+                            if (zero_face[c] && vals[c] == 0.0f) atomicMin(&s_zpos[c], j);
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- 2. plane counts ----
         {
@@ -705,6 +755,13 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
                 lo[c] = o2f(min(s_node[c], ENC_POS_INIT));
                 hi[c] = o2f(max(s_node[3 + c], ENC_NEG_INIT));
             }
+            for (int c = 0; c < 6; ++c)
+                if (s_zpos[c] != 0xFFFFFFFFu) {  // only set on the rare -0.0 path
+                    const uint32_t g = __ldcg(&ids_snap[start + s_zpos[c]]);
+                    const float4 bb = box[2 * (size_t)g + (c < 3 ? 0 : 1)];
+                    const float z = (c % 3 == 0) ? bb.x : ((c % 3 == 1) ? bb.y : bb.z);
+                    if (c < 3) lo[c] = z; else hi[c - 3] = z;
+                }
             emit_rec(recs, 2 * (start + p) + 1, lo, hi, start, n, t.leftrun, t.pstart, t.pleftrun, t.flags);
             if (p <= 3) A[start] = t.leftrun + 1;
             push_child(Q, st, epoch, start, p, t.leftrun + 1, start, t.leftrun, t.flags & ~3u);
@@ -787,6 +844,27 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
                 nhi[k] = o2f(max(__reduce_max_sync(FULL_MASK, f2o(acc[3 + k])), ENC_NEG_INIT));
                 cmin[k] = o2f(min(__reduce_min_sync(FULL_MASK, f2o(acc[6 + k])), ENC_POS_INIT));
                 cmax[k] = o2f(max(__reduce_max_sync(FULL_MASK, f2o(acc[9 + k])), ENC_NEG_INIT));
+            }
+        }
+        if (st->neg_zero) {
+            // rare path (-0.0 in the input): sign of a zero face = first zero in slot order (see k_setup)
+            __syncwarp();
+            for (int c = 0; c < 6; ++c) {
+                const float cur = (c < 3) ? nlo[c] : nhi[c - 3];
+                if (cur != 0.0f) continue;
+                uint32_t pos = 0xFFFFFFFFu;
+                for (uint32_t i = 0; i < E; ++i) {
+                    const uint32_t j = i * 32 + lane;
+                    if (j < n) {
+                        const float4 bb = box[2 * (size_t)s_gid[w][j] + (c < 3 ? 0 : 1)];
+                        const float val = (c % 3 == 0) ? bb.x : ((c % 3 == 1) ? bb.y : bb.z);
+                        if (val == 0.0f) pos = min(pos, j);
+                    }
+                }
+                pos = __reduce_min_sync(FULL_MASK, pos);
+                const float4 bb = box[2 * (size_t)s_gid[w][pos] + (c < 3 ? 0 : 1)];
+                const float z = (c % 3 == 0) ? bb.x : ((c % 3 == 1) ? bb.y : bb.z);
+                if (c < 3) nlo[c] = z; else nhi[c - 3] = z;
             }
         }
         // ---- 2. plane counts ----
@@ -1086,6 +1164,7 @@ __device__ __forceinline__ void p_t1_init(const T1Args& g) {
         const uint32_t tid = threadIdx.x;
         if (tid < 12) s->bnd[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         if (tid == 22) s->best = 0xFFFFFFFFu;
+        if (tid >= 32 && tid < 38) s->zkey[tid - 32] = 0xFFFFFFFFFFFFFFFFull;
         if (tid < 144) (&s->bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         for (uint32_t t = tid; t < nt; t += blockDim.x) g.tile_desc[nd.tile_base + t] = make_uint4(node, nd.start, nd.n, t);
         for (uint32_t k = tid; k < 22 * nt; k += blockDim.x) g.tileL[(size_t)(k / nt) * g.tile_stride + nd.tile_base + (k % nt)] = 0;
@@ -1149,15 +1228,33 @@ __device__ __forceinline__ void p_t1_flags(const T1Args& g) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { cmin[c] = o2f(g.sc[node].bnd[6 + c]); cmax[c] = o2f(g.sc[node].bnd[9 + c]); }
         uint32_t cnt = 0;
+        bool zero_face[6];
+        bool any_zero = false;
+        if (g.st->neg_zero) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const uint32_t e = g.sc[node].bnd[c];
+                zero_face[c] = o2f(c < 3 ? min(e, ENC_POS_INIT) : max(e, ENC_NEG_INIT)) == 0.0f;
+                any_zero = any_zero || zero_face[c];
+            }
+        }
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = j0 + i * T1_THREADS + tid;
             bool L = false;
             if (j < nd.n) {
-                const float4 c = g.cent[g.ids0[nd.start + j]];
+                const uint32_t id = g.ids0[nd.start + j];
+                const float4 c = g.cent[id];
                 const uint32_t kb = plane_counts(c.x, c.y, c.z, cmin, cmax);
                 g.fl0[nd.start + j] = (uint16_t)kb;
                 L = (kb & 7u) < 1u;
+                if (any_zero) {  // rare path (-0.0 in the input): first slot with a zero on each zero-valued face
+                    const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
+                    const float vals[6] = {b0.x, b0.y, b0.z, b1.x, b1.y, b1.z};
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc)
+                        if (zero_face[cc] && vals[cc] == 0.0f) atomicMin(&g.sc[node].zkey[cc], ((unsigned long long)j << 32) | id);
+                }
             }
             cnt += __popc(__ballot_sync(FULL_MASK, L));
         }
@@ -1551,6 +1648,13 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
         float lo[3], hi[3];
         for (int c = 0; c < 3; ++c) { lo[c] = o2f(min(s->bnd[c], ENC_POS_INIT)); hi[c] = o2f(max(s->bnd[3 + c], ENC_NEG_INIT)); }
         if (p == 0 || p >= nd.n) { atomicOr(&g.st->err, DERR_DEGENERATE); continue; }
+        for (int c = 0; c < 6; ++c)
+            if (s->zkey[c] != 0xFFFFFFFFFFFFFFFFull) {  // only set on the rare -0.0 path
+                const uint32_t id = (uint32_t)(s->zkey[c] & 0xFFFFFFFFull);
+                const float4 bb = g.box[2 * (size_t)id + (c < 3 ? 0 : 1)];
+                const float z = (c % 3 == 0) ? bb.x : ((c % 3 == 1) ? bb.y : bb.z);
+                if (c < 3) lo[c] = z; else hi[c - 3] = z;
+            }
         emit_rec(recs, 2 * (nd.start + p) + 1, lo, hi, nd.start, nd.n, nd.leftrun, nd.pstart, nd.pleftrun, nd.flags);
         if (p <= 3) A[nd.start] = nd.leftrun + 1;
         for (int side = 0; side < 2; ++side) {

@@ -17,6 +17,11 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// f32::min / f32::max as the reference's folds use them: the accumulator stays unless the new value is strictly
+// smaller / larger, so among zeros of different sign the first one is kept (tlas.rs:43,69-70).
+__device__ __forceinline__ float min_rs(float acc, float v) { return (v < acc) ? v : acc; }
+__device__ __forceinline__ float max_rs(float acc, float v) { return (v > acc) ? v : acc; }
+
 constexpr int CHAIN_THREADS = 1024;
 
 __device__ __forceinline__ float3 xform_point(const float* m, float x, float y, float z) {
@@ -43,8 +48,8 @@ __global__ void __launch_bounds__(256) k_tlas_leaves(const Instance* __restrict_
     for (int c = 0; c < 8; ++c) {
         const int ix = (c & 1) == 0, iy = (c & 2) == 0, iz = (c & 4) == 0;
         const float3 q = xform_point(in->transform, bx[ix], by[iy], bz[iz]);
-        mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
-        mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+        mn[0] = min_rs(mn[0], q.x); mn[1] = min_rs(mn[1], q.y); mn[2] = min_rs(mn[2], q.z);
+        mx[0] = max_rs(mx[0], q.x); mx[1] = max_rs(mx[1], q.y); mx[2] = max_rs(mx[2], q.z);
     }
     TlasNode nd;
     nd.min[0] = mn[0]; nd.min[1] = mn[1]; nd.min[2] = mn[2];
@@ -113,8 +118,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_tlas_chain(uint32_t n_inst, T
                 const uint32_t idx_a = node_indices[a], idx_b = node_indices[b];
                 float u[6];
                 for (int k = 0; k < 3; ++k) {
-                    u[k] = fminf(slot_box[(size_t)k * n_inst + a], slot_box[(size_t)k * n_inst + b]);
-                    u[3 + k] = fmaxf(slot_box[(size_t)(3 + k) * n_inst + a], slot_box[(size_t)(3 + k) * n_inst + b]);
+                    u[k] = min_rs(slot_box[(size_t)k * n_inst + a], slot_box[(size_t)k * n_inst + b]);
+                    u[3 + k] = max_rs(slot_box[(size_t)(3 + k) * n_inst + a], slot_box[(size_t)(3 + k) * n_inst + b]);
                 }
                 TlasNode nd;
                 nd.min[0] = u[0]; nd.min[1] = u[1]; nd.min[2] = u[2];
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_tlas_chain_cluster(uint32_t n_in
         if (a == c) {
             float u[6];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { u[k] = fminf(a_box[k], b_box[k]); u[3 + k] = fmaxf(a_box[3 + k], b_box[3 + k]); }
+            for (int k = 0; k < 3; ++k) { u[k] = min_rs(a_box[k], b_box[k]); u[3 + k] = max_rs(a_box[3 + k], b_box[3 + k]); }
             const uint32_t last = count - 1;
             if (rank == 0 && tid == 0) {
                 TlasNode nd;
