@@ -55,6 +55,13 @@ def build_inputs(rank: int, n_rays: int):
     return dv, di, pv, pi, inst, ro, rd
 
 
+def measured_traffic():
+    """DRAM bytes per launch measured with ncu --set full (profiles/r01_traffic.json, written from the committed
+    summaries); None when the file is missing."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def build_bytes(n_tris, n_verts, S_sum, M):
     """12N + 12V + 36N + 44*S + 32*M + 24N."""
     return 12 * n_tris + 12 * n_verts + 36 * n_tris + 44 * S_sum + 32 * M + 24 * n_tris
@@ -667,8 +674,13 @@ def main():
         value = world * n_tris / (b_ms_step * 1e-3) / 1e6
         rvalue = world * n_rays / (r_ms_step * 1e-3) / 1e6
         lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_big_block", "ms_block", "ms_warp_node", "ms_warp", "ms_emit", "ms_total")}
+        tr = measured_traffic()
         build_roof = {"bound": "hbm", "achieved": bb / (lib_ms["ms_total"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                      "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                      "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak,
+                      "traffic": (tr["k_t1_coop"] if tr else None), "peak_source": peak_src,
+                      "dominant_kernel": {"name": "k_t1_coop (grid tier, one cooperative launch)", "ms": lib_ms["ms_grid"],
+                                          "share_of_build": lib_ms["ms_grid"] / lib_ms["ms_total"],
+                                          "traffic_note": "ncu DRAM bytes of that launch; far below the algorithmic bytes because the working set stays in L2"},
                       "kernel": "whole forest build, plane + dragon (latency-bound chain of dependent passes); per-phase device ms in phase_ms_dragon",
                       "algorithmic_bytes": bb, "S": st["sum_interior_prims"], "M": st["n_nodes"]}
         if per_ray is None:
@@ -679,7 +691,8 @@ def main():
         rb = ray_bytes(per_ray, 1)
         scene_bytes = 32 * state["M"] + 12 * n_verts + 12 * n_tris + 5 * 32 + 2 * 192
         ray_roof = {"bound": "hbm", "achieved": rb * n_rays / (r_ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": rb * n_rays / (r_ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": rb * n_rays / (r_ms_step * 1e-3) / 1e9 / peak,
+                    "traffic": (tr["k_trace_scene_any_16Mi"] if (tr and n_rays == N_RAYS) else None), "peak_source": peak_src,
                     "kernel": "k_trace_scene<ANY> (one launch per step)", "bytes_per_ray": rb, "counters_per_ray": per_ray,
                     "compulsory_GBps": ((25 * n_rays + scene_bytes) / (r_ms_step * 1e-3) / 1e9), "note": rb_note}
         line = {
