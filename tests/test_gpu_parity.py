@@ -219,6 +219,62 @@ def test_trace_two_level_ids_exact(ctx, oracle):
     assert (tri3 == otri[:20000]).all() and (ins3 == oins[:20000]).all()
 
 
+def test_any_hit_order_free_kernel_equals_reference_order(ctx, oracle):
+    """trace_any runs an order-free kernel (separate interior / leaf stacks, missed interior children skipped) and hands
+    rays with unusable reciprocals to the exact-order kernel.  Its answer must equal traverse_tlas(ray).hit of the
+    reference order bit for bit, also for grazing rays (aimed exactly at vertices and edge midpoints, where a
+    triangle test can pass although the leaf's own box test fails), finite / huge tmax and zero direction components."""
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=300)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    args = (tl.nodes, tl.children, inst, infos, nodes, verts, inds)
+    ro, rd = S.rays_toward_box(200_000, [-20, -20, -20], [20, 20, 20], seed=78)
+
+    def same(sc, a, o, d, tmax=1e30):
+        occ = sc.occluded(o, d, tmax=tmax)
+        _, _, _, oocc, _ = oracle.trace_scene(*a, o, d, tmax=tmax, any_hit=True, threads=oracle.max_threads())
+        assert (occ == oocc).all(), f"{int((occ != oocc).sum())} of {len(o)} rays differ (tmax={tmax})"
+        return int(oocc.sum())
+
+    assert same(scene, args, ro, rd) > 10_000
+    t_closest, _, _ = scene.traverse_tlas(ro, rd)
+    t_med = float(np.median(t_closest[t_closest < np.float32(1e30)]))
+    n_all = int((t_closest < np.float32(1e30)).sum())
+    n_fin = same(scene, args, ro, rd, tmax=t_med)         # finite tmax: a missed far child is not pushed
+    assert 0 < n_fin < n_all
+    same(scene, args, ro[:64], rd[:64], tmax=3e38)        # above the miss value (every node is visited): exact kernel
+    rz = rd[:60_000].copy()
+    rz[::3, 0] = 0.0
+    rz[1::3, 1] = 0.0
+    rz[2::7] = 0.0
+    same(scene, args, ro[:60_000], rz)                    # infinite / NaN reciprocals: deferred to the exact kernel
+    # grazing rays on one mesh under an identity instance
+    v, idx = S.displaced_sphere(96, 192, 4)
+    pool = S.MeshPool(builder)
+    pool.add(v, idx)
+    pv, pi, pn, pinf = pool.pooled()
+    inst1 = S.make_instances(np.eye(4)[None], [0])
+    tl1 = vb.Tlas.empty(ctx)
+    tl1.build(inst1, pinf)
+    scene1 = vb.Scene(tl1.nodes, tl1.children, inst1, pinf, pn, pv, pi, ctx)
+    args1 = (tl1.nodes, tl1.children, inst1, pinf, pn, pv, pi)
+    rng = np.random.default_rng(5)
+    tri3 = np.asarray(idx).reshape(-1, 3)
+    org = (rng.normal(size=(150_000, 3)) * 3).astype(np.float32)
+    tgt = v[rng.integers(0, len(v), len(org))]
+    same(scene1, args1, org, (tgt - org).astype(np.float32))
+    t = tri3[rng.integers(0, len(tri3), len(org))]
+    mid = ((v[t[:, 0]] + v[t[:, 1]]) * np.float32(0.5)).astype(np.float32)
+    same(scene1, args1, org, (mid - org).astype(np.float32))
+    # rays that start on a vertex (origin exactly on box planes)
+    same(scene1, args1, tgt, (org - tgt).astype(np.float32))
+
+
 def test_trace_blas_rust_mode_ids_exact(ctx, oracle):
     v, idx = S.bunny_class()
     bvh, gi = gpu_build(ctx, v, idx)

@@ -134,6 +134,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->trace_counter) cudaFree(ctx->trace_counter);
+    if (ctx->defer_list) cudaFree(ctx->defer_list);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -330,8 +331,12 @@ int bvh_cuda_scene_refresh_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, const B
 
 void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene) {
     if (!scene) return;
-    if (ctx) { DeviceGuard g(ctx->device); if (scene->owned && scene->block) cudaFree(scene->block); if (scene->baked) cudaFree(scene->baked); }
-    else { if (scene->owned && scene->block) cudaFree(scene->block); if (scene->baked) cudaFree(scene->baked); }
+    auto release = [&] {
+        if (scene->owned && scene->block) cudaFree(scene->block);
+        if (scene->baked) cudaFree(scene->baked);
+    };
+    if (ctx) { DeviceGuard g(ctx->device); release(); }
+    else release();
     delete scene;
 }
 

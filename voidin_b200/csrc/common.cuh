@@ -40,6 +40,8 @@ struct bvh_cuda_ctx {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     void* trace_counter = nullptr;  // persistent-warp ray counter of trace_blas
+    uint32_t* defer_list = nullptr;  // rays the order-free any-hit kernel hands to the exact kernel
+    size_t defer_cap = 0;
     // optional per-phase timing
     bool profiling = false;
     cudaEvent_t ev[8] = {};

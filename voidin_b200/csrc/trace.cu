@@ -6,6 +6,8 @@
 //                  WGSL tests (shaders/utils/intersections.wgsl:13-45): reciprocal slabs, back-face culling,
 //                  near child popped first; ANY = early exit at the first accepted triangle, which yields
 //                  exactly traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102).
+//   k_trace_any    the same any-hit answer without the reference's visit order (see the comment above the kernel);
+//                  this is what bvh_cuda_trace_any runs, k_trace_scene<true> takes the rays it defers.
 // One thread per ray; nodes are fetched as two 16-byte loads (32-byte aligned); per-ray stacks live in
 // local memory (64 entries; the reference's 32 / 24-entry stacks overflow silently on deeper trees).
 // Compiled with -fmad=false: hit ids depend on exact, unfused float arithmetic in the reference's order.
@@ -13,6 +15,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -293,7 +296,15 @@ template <bool ANY>
 __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                      const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                      float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out,
-                                                     uint8_t* occ_out, unsigned long long* next_ray) {
+                                                     uint8_t* occ_out, unsigned long long* next_ray,
+                                                     const uint32_t* __restrict__ list = nullptr,
+                                                     const unsigned long long* list_ctl = nullptr) {
+    // Optional indirection: trace only the rays the wide any-hit kernel deferred (list_ctl[0] = how many,
+    // list_ctl[2] != 0 = all of them, in which case the list is not used).
+    if (list_ctl) {
+        if (list_ctl[2] != 0) list = nullptr;
+        else R = (size_t)list_ctl[0];
+    }
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t tstack[TLAS_STACK_CAP], bstack[STACK_CAP];
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
             if (base + n_idle >= R) exhausted = true;
             const unsigned long long mine = base + __popc(idle & lt_mask);
             if (!active && mine < R) {
-                r = (size_t)mine;
+                r = list ? (size_t)list[mine] : (size_t)mine;
                 eye[0] = ro[3 * r]; eye[1] = ro[3 * r + 1]; eye[2] = ro[3 * r + 2];
                 dir[0] = rd[3 * r]; dir[1] = rd[3 * r + 1]; dir[2] = rd[3 * r + 2];
                 inv[0] = __fdiv_rn(1.0f, dir[0]); inv[1] = __fdiv_rn(1.0f, dir[1]); inv[2] = __fdiv_rn(1.0f, dir[2]);
@@ -440,7 +451,197 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
     }
 }
 
+
+// =====================================================================================================
+// Any-hit without the reference's visit order.
+//
+// traverse_tlas(ray).hit (raytraced_shadows.wgsl:98-102) does not depend on the order in which nodes are visited:
+// until the first triangle is accepted `hit` stays at tmax, so which leaves are reached is a pure function of box
+// tests made with t = tmax.  Written out for traverse_bvh (bvh.wgsl:35-76) with tmax = 1e30: at an interior node
+// both children are pushed as soon as ONE of their boxes is hit (the far one because `max_dist <= hit` also holds
+// for the miss value 1e30); a popped interior child whose own box was missed pushes nothing, because child boxes
+// are contained in the parent box and every operation of the slab test is monotone in the box planes (no NaN when
+// 1/dir is finite and non-zero), so its children miss as well; a popped LEAF has its triangles tested without
+// looking at its box again.  Hence
+//     leaf X is tested      <=>  box(X) is hit  or  box(sibling(X)) is hit     (tmax = 1e30)
+//     leaf X is tested      <=>  box(X) is hit                                  (tmax < 1e30: a missed far child is not pushed)
+//     interior X matters    <=>  box(X) is hit
+// With the order free, interior nodes and leaves go to two separate per-lane stacks and every iteration a lane
+// does one node step AND one triangle test, instead of one or the other; missed interior children are never
+// visited.  Rays for which the argument does not hold — a non-finite or zero reciprocal direction (world or object
+// space), a stack overflow — are handed to the exact kernel (k_trace_scene<true>) through a list; tmax > 1e30 uses
+// the exact kernel for everything.  The per-ray answer is bit-identical to the reference order's.
+constexpr int A_LSTACK = 24;
+// layout of the scene's 256-byte control block (scene->counter), in u64 words
+constexpr int CTL_RAY = 0, CTL_DEFER_N = 1, CTL_DEFER_RAY = 2;  // word 3: "defer everything" (unused, stays 0)
+
+__device__ __forceinline__ bool slab_hit_w(const float* e, const float* inv, const float4& mn, const float4& mx, float t, float& tnear) {
+    const float ax = (mn.x - e[0]) * inv[0], ay = (mn.y - e[1]) * inv[1], az = (mn.z - e[2]) * inv[2];
+    const float bx = (mx.x - e[0]) * inv[0], by = (mx.y - e[1]) * inv[1], bz = (mx.z - e[2]) * inv[2];
+    const float tmax = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+    const float tmin = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    tnear = tmin;
+    return (tmax >= tmin) && (tmin < t) && (tmax > 0.0f);
+}
+__device__ __forceinline__ bool inv_usable(const float* inv) {
+    return isfinite(inv[0]) && isfinite(inv[1]) && isfinite(inv[2]) && inv[0] != 0.0f && inv[1] != 0.0f && inv[2] != 0.0f;
+}
+
+__global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
+                                                   const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
+                                                   float tmax, uint8_t* occ_out, unsigned long long* ctl,
+                                                   uint32_t* defer_list) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool pair_rule = tmax >= MAXD;  // a missed far child is pushed iff 1e30 <= hit (bvh.wgsl:71)
+    uint32_t tstack[TLAS_STACK_CAP], nstack[STACK_CAP], lstack[A_LSTACK];
+    int th = 0, nh = 0, lh = 0;
+    bool active = false;
+    size_t r = 0;
+    float eye[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
+    float e2[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, inv2[3] = {0, 0, 0};
+    uint32_t tri_base = 0, bvh_index = 0, leaf_first = 0, leaf_cnt = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        bool defer = false;
+        const uint32_t idle = __ballot_sync(FULL_MASK, !active);
+        if (idle != 0 && !exhausted && (__popc(idle) >= 6 || idle == FULL_MASK)) {
+            const uint32_t n_idle = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctl[CTL_RAY], (unsigned long long)n_idle);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (base + n_idle >= R) exhausted = true;
+            const unsigned long long mine = base + __popc(idle & lt_mask);
+            if (!active && mine < R) {
+                r = (size_t)mine;
+                eye[0] = ro[3 * r]; eye[1] = ro[3 * r + 1]; eye[2] = ro[3 * r + 2];
+                dir[0] = rd[3 * r]; dir[1] = rd[3 * r + 1]; dir[2] = rd[3 * r + 2];
+                inv[0] = __fdiv_rn(1.0f, dir[0]); inv[1] = __fdiv_rn(1.0f, dir[1]); inv[2] = __fdiv_rn(1.0f, dir[2]);
+                th = 0; nh = 0; lh = 0; leaf_cnt = 0;
+                tstack[th++] = 0;
+                active = true;
+                if (!inv_usable(inv)) defer = true;
+            }
+        }
+        if (__ballot_sync(FULL_MASK, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        bool finished = false, occluded = false;
+        // ---- node step: one interior node, both child boxes ----
+        if (active && !defer && nh > 0 && lh <= A_LSTACK - 2) {
+            if (nh >= STACK_CAP) {
+                defer = true;
+            } else {
+                const uint32_t c0 = bvh_index + nstack[--nh];
+                const NodeW ca = ld_node(sc.bvh_nodes, c0), cb = ld_node(sc.bvh_nodes, c0 + 1);
+                uint32_t m0 = pack_meta(ca), m1 = pack_meta(cb);
+                float d0, d1;
+                bool h0 = slab_hit_w(e2, inv2, ca.a, ca.b, tmax, d0);
+                bool h1 = slab_hit_w(e2, inv2, cb.a, cb.b, tmax, d1);
+                if (h0 | h1) {
+                    // a leaf is visited when the pair is hit (tmax = 1e30), an interior node only when its own box is
+                    const bool both = pair_rule;
+                    bool v0 = h0 || (both && (m0 >> 30) != 0);
+                    bool v1 = h1 || (both && (m1 >> 30) != 0);
+                    // nearer child on top of its stack (only a heuristic here)
+                    if (h0 && h1 && d0 < d1) {
+                        const uint32_t tm = m0; m0 = m1; m1 = tm;
+                        const bool tv = v0; v0 = v1; v1 = tv;
+                    }
+                    if (v0) { if (m0 >> 30) lstack[lh++] = m0; else nstack[nh++] = m0; }
+                    if (v1) { if (m1 >> 30) lstack[lh++] = m1; else nstack[nh++] = m1; }
+                }
+            }
+        }
+        // ---- triangle step: one triangle of the current leaf (bvh.wgsl:43-51) ----
+        // A lane with pending leaves can keep doing node steps, so the triangle path waits until enough lanes have
+        // a triangle to test, or until some lane has nothing else to do (or no room for more leaves).
+        const bool has_tri = active && !defer && (leaf_cnt > 0 || lh > 0);
+        const bool must_tri = has_tri && (nh == 0 || lh > A_LSTACK - 2);
+        const uint32_t tri_lanes = __ballot_sync(FULL_MASK, has_tri);
+        const bool run_tri = (__ballot_sync(FULL_MASK, must_tri) != 0) || ((uint32_t)__popc(tri_lanes) >= TRI_VOTE);
+        if (run_tri && has_tri) {
+            if (leaf_cnt == 0) {
+                const uint32_t m = lstack[--lh];
+                leaf_cnt = m >> 30;
+                leaf_first = m & 0x3FFFFFFFu;
+            }
+            const uint32_t idx = leaf_first;
+            leaf_first++;
+            leaf_cnt--;
+            const float4* tp = tris + 3 * (size_t)(tri_base + idx);
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            const float v0[3] = {a.x, a.y, a.z}, v1[3] = {b.x, b.y, b.z}, v2[3] = {c.x, c.y, c.z};
+            float h = tmax;
+            if (trig_w(e2, d2, v0, v1, v2, &h)) { finished = true; occluded = true; }
+        }
+        // ---- TLAS step (bvh.wgsl:89-123), only when the current instance is exhausted ----
+        if (active && !defer && !finished && nh == 0 && lh == 0 && leaf_cnt == 0) {
+            if (th == 0) {
+                finished = true;
+            } else {
+                const uint32_t ni = tstack[--th];
+                const NodeW node = ld_node(sc.tlas_nodes, ni);
+                const uint32_t left_right = __float_as_uint(node.a.w);
+                if (left_right == 0) {
+                    // instance_intersect (bvh.wgsl:78-87): the BLAS root is visited without a box test
+                    const uint32_t ii = __float_as_uint(node.b.w);
+                    const Instance* in = sc.instances + ii;
+                    const MeshInfo* mesh = sc.meshes + in->mesh;
+                    tri_base = mesh->base_index / 3u;
+                    bvh_index = mesh->bvh_index;
+                    const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
+                    mat_mul(im, eye, 1.0f, e2);
+                    mat_mul(im, dir, 0.0f, d2);
+                    inv2[0] = __fdiv_rn(1.0f, d2[0]); inv2[1] = __fdiv_rn(1.0f, d2[1]); inv2[2] = __fdiv_rn(1.0f, d2[2]);
+                    if (!inv_usable(inv2)) {
+                        defer = true;
+                    } else {
+                        const uint32_t m = pack_meta(ld_node(sc.bvh_nodes, bvh_index));
+                        if (m >> 30) lstack[lh++] = m; else nstack[nh++] = m;
+                    }
+                } else {
+                    uint32_t min_index, max_index;
+                    if (sc.tlas_children) {
+                        const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        min_index = k.x; max_index = k.y;
+                    } else {
+                        min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
+                    }
+                    const bool twin = (min_index == max_index);
+                    const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
+                    const float d0 = aabb_w(eye, inv, ca.a, ca.b, tmax);
+                    const float d1 = aabb_w(eye, inv, cb.a, cb.b, tmax);
+                    // traverse_tlas pushes a child iff its distance is below `dist` (bvh.wgsl:116-119), == tmax here
+                    if (d0 < tmax && th < TLAS_STACK_CAP) tstack[th++] = min_index;
+                    if (d1 < tmax && !twin && th < TLAS_STACK_CAP) tstack[th++] = max_index;
+                }
+            }
+        }
+        if (defer) {
+            const uint32_t dm = __activemask();
+            const uint32_t dl = __ffs(dm) - 1;
+            unsigned long long slot = 0;
+            if (lane == dl) slot = atomicAdd(&ctl[CTL_DEFER_N], (unsigned long long)__popc(dm));
+            slot = __shfl_sync(dm, slot, dl);
+            defer_list[slot + __popc(dm & lt_mask)] = (uint32_t)r;
+            active = false;
+        } else if (finished) {
+            occ_out[r] = occluded ? 1 : 0;
+            active = false;
+        }
+    }
+}
+
 }  // namespace
+
+// tuning hook (not part of the ABI): lanes that must be waiting before the triangle / TLAS paths run
+extern "C" int bvh_cuda_debug_set_votes(unsigned tri, unsigned tlas) {
+    const uint32_t hv[2] = {tri ? tri : 1u, tlas ? tlas : 1u};
+    return (int)cudaMemcpyToSymbol(c_votes, hv, sizeof(hv));
+}
 
 int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices, const uint32_t* d_indices,
                       const float* d_ray_o, const float* d_ray_d, size_t n_rays, float* d_t, uint32_t* d_tri,
@@ -491,13 +692,35 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
         return true;
     }();
     (void)votes_set;
-    // persistent warps: the ray counter lives in the scene (8 bytes), reset per launch
+    // persistent warps: the ray counters live in the scene's control block, reset per launch
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(scene->counter);
-    CU_CHECK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    CU_CHECK(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), stream));
     size_t want = (n_rays + 127) / 128;
     const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
-    if (any_hit)
+    static const bool wide_off = [] { const char* e = getenv("BVH_CUDA_ANYHIT"); return e && !strcmp(e, "exact"); }();
+    if (any_hit && !wide_off && tmax <= MAXD && n_rays < 0xFFFFFFFFull) {
+        // order-free kernel first; whatever it defers (normally nothing) goes through the exact kernel
+        if (ctx->defer_cap < n_rays) {
+            if (ctx->defer_list) cudaFree(ctx->defer_list);
+            ctx->defer_list = nullptr; ctx->defer_cap = 0;
+            cudaError_t e = cudaMalloc(&ctx->defer_list, n_rays * sizeof(uint32_t));
+            if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(defer list)");
+            ctx->defer_cap = n_rays;
+        }
+        // persistent grid: exactly the resident blocks (more warps than that only start when the rays are gone)
+        static const int any_bps = [] {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_any, 128, 0) != cudaSuccess || occ < 1) occ = 8;
+            return occ;
+        }();
+        const size_t cap_any = (size_t)ctx->sm_count * any_bps;
+        k_trace_any<<<(unsigned)(want < cap_any ? want : cap_any), 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ,
+                                                                                      counter, ctx->defer_list);
+        ctx->launches++;
+        k_trace_scene<true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
+                                                         counter + CTL_DEFER_RAY, ctx->defer_list, counter + CTL_DEFER_N);
+    } else if (any_hit)
         k_trace_scene<true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
     else
         k_trace_scene<false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);

@@ -384,45 +384,6 @@ def gbuffer_shadow_rays(n: int, dragon_world_tris: np.ndarray, light_corners: np
     return np.ascontiguousarray(o), np.ascontiguousarray(d)
 
 
-def world_triangles(vertices, indices, transform=None) -> np.ndarray:
-    v = np.asarray(vertices, dtype=np.float64)
-    if transform is not None:
-        t = np.asarray(transform, dtype=np.float64)
-        v = v @ t[:3, :3].T + t[:3, 3]
-    return v[np.asarray(indices, dtype=np.int64).reshape(-1, 3)]
-
-
-def dragon_scene_instances(lift: float = 0.9):
-    """Config 2 scene: mesh 0 = ground plane scaled x200 (raytraced_shadows.rs:36-40), mesh 1 = the dragon-class
-    mesh lifted so that it rests on the ground.  Returns row-major transforms and mesh ids for make_instances."""
-    return np.stack([mat_scale(200.0), mat_translation([0.0, lift, 0.0])]), np.array([0, 1])
-
-
-def gbuffer_shadow_rays(n: int, dragon_world_tris: np.ndarray, light_corners: np.ndarray, seed: int = 12,
-                        ground_radius: float = 6.0, ground_frac: float = 0.5):
-    """Config 2 rays as a G-buffer would produce them (raytraced_shadows.wgsl:73-99 shades what the camera sees:
-    the model and the ground around it): `1-ground_frac` of the origins are uniform points on the dragon-class
-    surface, the rest uniform points of the ground plane (y = 0, normal +y) within `ground_radius` of the model.
-    Origin is pushed 1e-4 along the geometric normal; direction = (uniform point on the rect light) - origin,
-    NOT normalised, no t-max.  Area-weighted sampling over the whole x200 ground quad (40 000 area units against
-    ~12 for the model) would send 99.97 % of the rays from empty ground and make the traversal trivial."""
-    n_ground = int(n * ground_frac)
-    o1, d1 = shadow_rays(n - n_ground, dragon_world_tris, light_corners, seed=seed)
-    rng = np.random.default_rng(seed + 1000)
-    r = ground_radius * np.sqrt(rng.random(n_ground))
-    a = rng.random(n_ground) * 2 * np.pi
-    p = np.stack([r * np.cos(a), np.full(n_ground, 1e-4), r * np.sin(a)], axis=1)
-    lc = np.asarray(light_corners, dtype=np.float64)
-    u, v = rng.random(n_ground), rng.random(n_ground)
-    tgt = lc[0] + (lc[1] - lc[0]) * u[:, None] + (lc[3] - lc[0]) * v[:, None]
-    o2 = p.astype(F32)
-    d2 = (tgt - o2.astype(np.float64)).astype(F32)
-    o = np.concatenate([o1, o2])
-    d = np.concatenate([d1, d2])
-    perm = np.random.default_rng(seed + 2000).permutation(n)  # interleave, as neighbouring pixels would be
-    return np.ascontiguousarray(o[perm]), np.ascontiguousarray(d[perm])
-
-
 # ----------------------------------------------------------------------------------------------
 # minimal glTF 2.0 reader (positions + indices of every mesh primitive; no node transforms), the subset of
 # crates/app/src/models/gltf_model/mod.rs:103-155 that feeds MeshPool::add
