@@ -3,6 +3,8 @@
 // implementations; nothing here computes on the CPU.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -124,6 +126,9 @@ int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
     ctx->t2w_blocks_per_sm = blas_t2w_occupancy();
     ctx->t1_blocks_per_sm = blas_t1_coop_occupancy();
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    for (auto& row : ctx->pipe_ev) for (auto& e : row) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return BVH_CUDA_OK;
 }
@@ -136,6 +141,9 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
     if (ctx->trace_counter) cudaFree(ctx->trace_counter);
     if (ctx->defer_list) cudaFree(ctx->defer_list);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& row : ctx->pipe_ev) for (auto& e : row) if (e) cudaEventDestroy(e);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -432,32 +440,67 @@ int bvh_cuda_trace_any_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const
     return trace_scene_device(ctx, scene, d_ray_o, d_ray_d, n_rays, tmax, 1, nullptr, nullptr, nullptr, d_occluded_out, (cudaStream_t)stream);
 }
 
-int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
-                           float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out) {
-    if (!ctx) return BVH_CUDA_EINVAL;
-    if (!scene || !ray_o || !ray_d || !t_out || !tri_out || !inst_out) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_closest: null pointer");
-    if (n_rays == 0) return BVH_CUDA_OK;
+// Host-pointer traversal: the rays are cut into up to 16 chunks; chunk k+1 is uploaded (h2d stream) and chunk k-1 read
+// back (d2h stream) while chunk k is traced (own stream), so a call costs about max(PCIe in, kernels, PCIe out) instead
+// of their sum.  Needs pinned caller buffers to overlap; with pageable memory the copies simply serialise.
+static int trace_host_pipelined(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
+                                float tmax, int any_hit, float* t_out, uint32_t* tri_out, uint32_t* inst_out, uint8_t* occ_out) {
     DeviceGuard g(ctx->device);
-    cudaStream_t s = ctx->own_stream;
     Stage st(ctx);
-    const int io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays),
-              it = st.add(sizeof(float) * n_rays), itr = st.add(sizeof(uint32_t) * n_rays), iin = st.add(sizeof(uint32_t) * n_rays);
+    const int io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays);
+    const int it = st.add(any_hit ? n_rays : sizeof(float) * n_rays), itr = st.add(any_hit ? 0 : sizeof(uint32_t) * n_rays),
+              iin = st.add(any_hit ? 0 : sizeof(uint32_t) * n_rays);
     int rc = st.commit();
     if (rc) return rc;
     float* dro = st.ptr<float>(io);
     float* drd = st.ptr<float>(id);
     float* dt = st.ptr<float>(it);
+    uint8_t* docc = st.ptr<uint8_t>(it);
     uint32_t* dtri = st.ptr<uint32_t>(itr);
     uint32_t* dinst = st.ptr<uint32_t>(iin);
-    CU_CHECK(ctx, cudaMemcpyAsync(dro, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(drd, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    rc = trace_scene_device(ctx, scene, dro, drd, n_rays, tmax, 0, dt, dtri, dinst, nullptr, s);
-    if (rc) return rc;
-    CU_CHECK(ctx, cudaMemcpyAsync(t_out, dt, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(tri_out, dtri, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(inst_out, dinst, sizeof(uint32_t) * n_rays, cudaMemcpyDeviceToHost, s));
+    const bool pipe = ctx->h2d_stream && ctx->d2h_stream && ctx->pipe_ev[1][15];
+    cudaStream_t s = ctx->own_stream, sin = pipe ? ctx->h2d_stream : s, sout = pipe ? ctx->d2h_stream : s;
+    static const size_t n_chunks = [] { const char* e = getenv("BVH_CUDA_TRACE_CHUNKS"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();
+    size_t chunk = (n_rays + n_chunks - 1) / n_chunks;
+    if (chunk < ((size_t)1 << 19)) chunk = (size_t)1 << 19;
+    int k = 0;
+    for (size_t b0 = 0; b0 < n_rays; b0 += chunk, ++k) {
+        const size_t m = (n_rays - b0 < chunk) ? n_rays - b0 : chunk;
+        CU_CHECK(ctx, cudaMemcpyAsync(dro + 3 * b0, ray_o + 3 * b0, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, sin));
+        CU_CHECK(ctx, cudaMemcpyAsync(drd + 3 * b0, ray_d + 3 * b0, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, sin));
+        if (pipe) {
+            CU_CHECK(ctx, cudaEventRecord(ctx->pipe_ev[0][k], sin));
+            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->pipe_ev[0][k], 0));
+        }
+        rc = any_hit ? trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 1, nullptr, nullptr, nullptr, docc + b0, s)
+                     : trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 0, dt + b0, dtri + b0, dinst + b0, nullptr, s);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (pipe) {
+            CU_CHECK(ctx, cudaEventRecord(ctx->pipe_ev[1][k], s));
+            CU_CHECK(ctx, cudaStreamWaitEvent(sout, ctx->pipe_ev[1][k], 0));
+        }
+        if (any_hit) {
+            CU_CHECK(ctx, cudaMemcpyAsync(occ_out + b0, docc + b0, m, cudaMemcpyDeviceToHost, sout));
+        } else {
+            CU_CHECK(ctx, cudaMemcpyAsync(t_out + b0, dt + b0, sizeof(float) * m, cudaMemcpyDeviceToHost, sout));
+            CU_CHECK(ctx, cudaMemcpyAsync(tri_out + b0, dtri + b0, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, sout));
+            CU_CHECK(ctx, cudaMemcpyAsync(inst_out + b0, dinst + b0, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, sout));
+        }
+    }
+    if (pipe) {
+        CU_CHECK(ctx, cudaStreamSynchronize(sin));
+        CU_CHECK(ctx, cudaStreamSynchronize(sout));
+    }
     CU_CHECK(ctx, cudaStreamSynchronize(s));
     return BVH_CUDA_OK;
+}
+
+int bvh_cuda_trace_closest(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
+                           float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (!scene || !ray_o || !ray_d || !t_out || !tri_out || !inst_out) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_closest: null pointer");
+    if (n_rays == 0) return BVH_CUDA_OK;
+    return trace_host_pipelined(ctx, scene, ray_o, ray_d, n_rays, tmax, 0, t_out, tri_out, inst_out, nullptr);
 }
 
 int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d, size_t n_rays,
@@ -465,22 +508,7 @@ int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     if (!ctx) return BVH_CUDA_EINVAL;
     if (!scene || !ray_o || !ray_d || !occluded_out) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace_any: null pointer");
     if (n_rays == 0) return BVH_CUDA_OK;
-    DeviceGuard g(ctx->device);
-    cudaStream_t s = ctx->own_stream;
-    Stage st(ctx);
-    const int io = st.add(sizeof(float) * 3 * n_rays), id = st.add(sizeof(float) * 3 * n_rays), ic = st.add(n_rays);
-    int rc = st.commit();
-    if (rc) return rc;
-    float* dro = st.ptr<float>(io);
-    float* drd = st.ptr<float>(id);
-    uint8_t* docc = st.ptr<uint8_t>(ic);
-    CU_CHECK(ctx, cudaMemcpyAsync(dro, ray_o, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    CU_CHECK(ctx, cudaMemcpyAsync(drd, ray_d, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, s));
-    rc = trace_scene_device(ctx, scene, dro, drd, n_rays, tmax, 1, nullptr, nullptr, nullptr, docc, s);
-    if (rc) return rc;
-    CU_CHECK(ctx, cudaMemcpyAsync(occluded_out, docc, n_rays, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(ctx, cudaStreamSynchronize(s));
-    return BVH_CUDA_OK;
+    return trace_host_pipelined(ctx, scene, ray_o, ray_d, n_rays, tmax, 1, nullptr, nullptr, nullptr, occluded_out);
 }
 
 }  // extern "C"

@@ -23,6 +23,9 @@ struct bvh_cuda_ctx {
     std::string err;
     uint64_t launches = 0;
     cudaStream_t own_stream = nullptr;
+    // host-pointer trace calls: uploads and read-backs run on their own streams, pipelined against the kernels
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t pipe_ev[2][16] = {};
     // growable device workspace (one allocation, carved per call)
     void* ws = nullptr;
     size_t ws_bytes = 0;
