@@ -226,6 +226,18 @@ int bvh_cuda_gen_shadow_rays_dev(bvh_cuda_ctx* ctx, const float* d_pos, const fl
 int bvh_cuda_gen_area_shadow_rays_dev(bvh_cuda_ctx* ctx, const float* d_pos, const float* d_nor, const float* d_uv, size_t n,
                                       const float* corners, float* d_ray_o, float* d_ray_d, void* stream);
 
+/* ---- per-frame instance update: the step that makes a TLAS rebuild necessary -------------------------------- *
+ * shaders/compute_update.wgsl:12-27: for every id in d_ids (NULL = all n instances),
+ *   instance.transform = from_rotation_z(+-angle) * instance.transform        (shaders/utils/math.wgsl from_rotation_z)
+ * with + when transform[3][2] > -15.0 and - otherwise.  sin / cos are implementation-defined in WGSL, so the caller
+ * passes sin_a = sin(angle), cos_a = cos(angle) for angle = 2*sin(0.5*time)*dt; the matrix product is evaluated
+ * unfused, each component as the four-term column sum left to right.  The reference leaves inv_transform stale (it
+ * never rebuilds the TLAS: crates/app/src/app.rs:253 runs once); update_inverse != 0 also sets
+ * inv_transform = inv_transform * from_rotation_z(-+angle), so the moved instance can be traced after
+ * bvh_cuda_tlas_build_dev.  A wrapped scene (bvh_cuda_scene_wrap_dev) sees the new instances / TLAS in place. */
+int bvh_cuda_instances_rotate_z_dev(bvh_cuda_ctx* ctx, Instance* d_instances, const uint32_t* d_ids, size_t n, float sin_a,
+                                    float cos_a, int update_inverse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

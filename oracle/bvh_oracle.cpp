@@ -1085,6 +1085,31 @@ int oracle_gen_shadow_rays(const float* pos, const float* nor, size_t n, const f
     return ORACLE_OK;
 }
 
+// shaders/compute_update.wgsl:12-27 with (sin, cos) of the angle as inputs (WGSL leaves their precision open);
+// matrix product = four-term column sums left to right (math.wgsl from_rotation_z, column-major).  With
+// update_inverse the stale inv_transform is multiplied by from_rotation_z(-angle) on the right.
+static void mat_mul44(const float* A, const float* B, float* out) {
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 4; ++r)
+            out[4 * j + r] = ((A[r] * B[4 * j] + A[4 + r] * B[4 * j + 1]) + A[8 + r] * B[4 * j + 2]) + A[12 + r] * B[4 * j + 3];
+}
+int oracle_instances_rotate_z(Instance* inst, const uint32_t* ids, size_t n, float s, float c, int update_inverse) {
+    for (size_t i = 0; i < n; ++i) {
+        Instance* in = inst + (ids ? ids[i] : (uint32_t)i);
+        float R[16] = {0}, out[16];
+        const float sg = (in->transform[14] > -15.0f) ? s : -s;
+        R[0] = c; R[1] = sg; R[4] = -sg; R[5] = c; R[10] = 1.0f; R[15] = 1.0f;
+        mat_mul44(R, in->transform, out);
+        for (int k = 0; k < 16; ++k) in->transform[k] = out[k];
+        if (update_inverse) {
+            R[1] = -sg; R[4] = sg;
+            mat_mul44(in->inv_transform, R, out);
+            for (int k = 0; k < 16; ++k) in->inv_transform[k] = out[k];
+        }
+    }
+    return ORACLE_OK;
+}
+
 int oracle_max_threads(void) {
     unsigned h = std::thread::hardware_concurrency();
     return h ? (int)h : 1;

@@ -172,6 +172,19 @@ def brute_force(vertices, indices, ray_o, ray_d, mode: int):
     return t
 
 
+def instances_rotate_z(instances, ids, sin_a: float, cos_a: float, update_inverse: bool = False):
+    """compute_update.wgsl:12-27 on a copy of `instances`; ids=None rotates all of them."""
+    inst = np.array(instances, copy=True)
+    if ids is None:
+        lib().oracle_instances_rotate_z(_p(inst), None, C.c_size_t(inst.shape[0]), C.c_float(sin_a), C.c_float(cos_a),
+                                        C.c_int(1 if update_inverse else 0))
+    else:
+        i = np.ascontiguousarray(ids, dtype=np.uint32)
+        lib().oracle_instances_rotate_z(_p(inst), _p(i), C.c_size_t(i.size), C.c_float(sin_a), C.c_float(cos_a),
+                                        C.c_int(1 if update_inverse else 0))
+    return inst
+
+
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
 

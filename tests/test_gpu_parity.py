@@ -426,3 +426,59 @@ def test_blas_negative_zero_inputs_bit_exact(ctx, oracle, n, q):
         pytest.skip("degenerate for the reference")
     bvh, gi = gpu_build(ctx, v, idx)
     assert bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
+
+
+def test_animated_instances_frame_loop(ctx, oracle):
+    """the per-frame loop compute_update.wgsl implies — rotate the moving instances on the device
+    (bit-exact against the oracle twin, given sin/cos), rebuild the TLAS in place, trace through the wrapped scene."""
+    import torch
+    from voidin_b200.types import INSTANCE, TLAS_NODE
+
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    dev = torch.device("cuda", 0)
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=200)
+    inst = inst.copy()
+    inst["transform"][::5, 14] = -20.0  # some instances beyond z = -15 spin the other way (compute_update.wgsl:20-25)
+    n = inst.shape[0]
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_inst, d_info, d_nodes = to_dev(inst), to_dev(infos), to_dev(nodes)
+    d_verts, d_inds = to_dev(verts), to_dev(inds)
+    d_tlas = torch.empty((2 * n + 1) * 32, dtype=torch.uint8, device=dev)
+    d_kids = torch.empty((2 * n + 1) * 8, dtype=torch.uint8, device=dev)
+    moving = np.arange(0, n, 2, dtype=np.uint32)
+    d_ids = torch.from_numpy(moving.view(np.int32)).to(dev)
+    ctx.tlas_build_dev(d_inst.data_ptr(), n, d_info.data_ptr(), infos.shape[0], d_tlas.data_ptr(), d_kids.data_ptr())
+    scene = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_info.data_ptr(), d_nodes.data_ptr(),
+                     d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
+                     counts={"tlas_nodes": 2 * n + 1, "instances": n, "meshes": infos.shape[0], "bvh_nodes": nodes.shape[0],
+                             "vertices": verts.shape[0], "indices": inds.size})
+    ro, rd = S.rays_toward_box(50_000, [-20, -20, -20], [20, 20, 20], seed=91)
+    d_ro, d_rd = torch.from_numpy(ro.reshape(-1)).to(dev), torch.from_numpy(rd.reshape(-1)).to(dev)
+    d_t = torch.empty(len(ro), dtype=torch.float32, device=dev)
+    d_tri = torch.empty(len(ro), dtype=torch.int32, device=dev)
+    d_ins = torch.empty(len(ro), dtype=torch.int32, device=dev)
+    ref = inst
+    for frame in range(3):
+        time_s, dt = 0.7 + 0.016 * frame, 0.016
+        ang = np.float32(2.0 * np.sin(time_s * 0.5)) * np.float32(dt)
+        s_a, c_a = float(np.sin(np.float32(ang))), float(np.cos(np.float32(ang)))
+        vb.instances_rotate_z_dev(ctx, d_inst.data_ptr(), d_ids.data_ptr(), moving.size, s_a, c_a, update_inverse=True)
+        ref = oracle.instances_rotate_z(ref, moving, s_a, c_a, update_inverse=True)
+        got = d_inst.cpu().numpy().view(INSTANCE)
+        assert got.tobytes() == ref.tobytes()
+        ctx.tlas_build_dev(d_inst.data_ptr(), n, d_info.data_ptr(), infos.shape[0], d_tlas.data_ptr(), d_kids.data_ptr())
+        rc, otl, okids, _, _ = oracle.tlas_build(ref, infos)
+        assert d_tlas.cpu().numpy().view(TLAS_NODE).tobytes() == otl.tobytes()
+        scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), len(ro), d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr())
+        ot, otri, oins, _, _ = oracle.trace_scene(otl, okids, ref, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
+        assert (d_tri.cpu().numpy().view(np.uint32) == otri).all() and (d_ins.cpu().numpy().view(np.uint32) == oins).all()
+        assert np.allclose(d_t.cpu().numpy(), ot, rtol=T_RTOL, atol=0.0)
+    # the stale-inverse variant is exactly the shader: inv_transform untouched
+    before = d_inst.cpu().numpy().view(INSTANCE).copy()
+    vb.instances_rotate_z_dev(ctx, d_inst.data_ptr(), None, n, 0.01, float(np.cos(np.float32(0.01))))
+    after = d_inst.cpu().numpy().view(INSTANCE)
+    assert (after["inv_transform"] == before["inv_transform"]).all() and not (after["transform"] == before["transform"]).all()
+    assert after.tobytes() == oracle.instances_rotate_z(before, None, 0.01, float(np.cos(np.float32(0.01)))).tobytes()

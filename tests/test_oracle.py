@@ -180,3 +180,28 @@ def test_golden_hashes(oracle):
 
     now = compute()
     assert now == gold
+
+
+def test_instances_rotate_z_properties(oracle):
+    """compute_update.wgsl:12-27 twin: rotation about z, opposite sense beyond z = -15, inv_transform untouched unless
+    asked; with update_inverse the pair stays inverse to each other."""
+    inst = S.random_instances(64, 3, seed=4, extent=30.0)
+    ang = 0.05
+    s, c = float(np.sin(np.float32(ang))), float(np.cos(np.float32(ang)))
+    out = oracle.instances_rotate_z(inst, None, s, c)
+    assert (out["inv_transform"] == inst["inv_transform"]).all()
+    T0 = inst["transform"].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    T1 = out["transform"].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    for k in range(len(inst)):
+        a = ang if T0[k][2, 3] > -15.0 else -ang
+        R = np.array([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        assert np.allclose(T1[k], R @ T0[k], rtol=1e-5, atol=1e-5)
+    assert (T0[:, 2, 3] <= -15.0).any() and (T0[:, 2, 3] > -15.0).any()
+    ids = np.array([3, 9, 11], dtype=np.uint32)
+    out2 = oracle.instances_rotate_z(inst, ids, s, c, update_inverse=True)
+    untouched = np.setdiff1d(np.arange(len(inst)), ids)
+    assert out2[untouched].tobytes() == inst[untouched].tobytes()
+    for k in ids:
+        T = out2["transform"][k].reshape(4, 4).T.astype(np.float64)
+        I = out2["inv_transform"][k].reshape(4, 4).T.astype(np.float64)
+        assert np.allclose(T @ I, np.eye(4), atol=1e-4)

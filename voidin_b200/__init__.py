@@ -6,4 +6,4 @@ library has not been built or no CUDA device is present (there is no CPU fallbac
 from .types import BVH_NODE, TLAS_NODE, INSTANCE, MESH_INFO, MAX_DIST, NO_HIT  # noqa: F401
 from ._lib import BvhCudaError, LIB_PATH  # noqa: F401
 from .bvh import Bvh, BvhBuilder, Context, Ray, Scene, Tlas, Hit, MISS, default_context  # noqa: F401
-from .bvh import gen_primary_rays_dev, gen_shadow_rays_dev, gen_area_shadow_rays_dev  # noqa: F401
+from .bvh import gen_primary_rays_dev, gen_shadow_rays_dev, gen_area_shadow_rays_dev, instances_rotate_z_dev  # noqa: F401

@@ -38,6 +38,7 @@ SYMBOLS = [
     "bvh_cuda_gen_primary_rays_dev",
     "bvh_cuda_gen_shadow_rays_dev",
     "bvh_cuda_gen_area_shadow_rays_dev",
+    "bvh_cuda_instances_rotate_z_dev",
 ]
 
 
@@ -131,6 +132,7 @@ def load() -> C.CDLL:
     lib.bvh_cuda_gen_primary_rays_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
     lib.bvh_cuda_gen_shadow_rays_dev.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
     lib.bvh_cuda_gen_area_shadow_rays_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
+    lib.bvh_cuda_instances_rotate_z_dev.argtypes = [vp, vp, vp, sz, C.c_float, C.c_float, C.c_int, vp]
     for name in SYMBOLS:
         getattr(lib, name)  # AttributeError here means the header and the library disagree
     _lib = lib

@@ -112,6 +112,14 @@ def gen_area_shadow_rays_dev(ctx: Context, d_pos: int, d_nor: int, d_uv: int, n:
     ctx.check(ctx.lib.bvh_cuda_gen_area_shadow_rays_dev(ctx.h, d_pos, d_nor, d_uv, n, _vp(c), d_ro, d_rd, stream))
 
 
+def instances_rotate_z_dev(ctx: Context, d_instances: int, d_ids: int | None, n: int, sin_a: float, cos_a: float,
+                           update_inverse: bool = False, stream: int = 0):
+    """shaders/compute_update.wgsl:12-27 on device-resident instances (d_ids: device u32 ids, None/0 = all n):
+    transform = from_rotation_z(+-angle) * transform.  Rebuild the TLAS afterwards (Tlas.build / tlas_build_dev)."""
+    ctx.check(ctx.lib.bvh_cuda_instances_rotate_z_dev(ctx.h, d_instances, d_ids or None, n, float(sin_a), float(cos_a),
+                                                      1 if update_inverse else 0, stream))
+
+
 _default_ctx: Context | None = None
 
 

@@ -58,6 +58,13 @@ struct bvh_cuda_scene {
     void* counter = nullptr;  // persistent-warp ray counter (tail of `baked`)
 };
 
+// makes the context's device current for the duration of an entry point
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what);
 int ctx_cuda_fail(bvh_cuda_ctx* ctx, cudaError_t e, const char* where);
 int ctx_reserve(bvh_cuda_ctx* ctx, size_t bytes);
