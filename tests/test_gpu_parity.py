@@ -273,6 +273,19 @@ def test_any_hit_order_free_kernel_equals_reference_order(ctx, oracle):
     same(scene1, args1, org, (mid - org).astype(np.float32))
     # rays that start on a vertex (origin exactly on box planes)
     same(scene1, args1, tgt, (org - tgt).astype(np.float32))
+    # an instance rotated by 45 degrees about z: world directions (1, 1, z) have all components non-zero, but the
+    # object-space direction gets an exact zero (c*1 - s*1 with c == s in f32) -> deferred at instance entry
+    c45 = float(np.float32(np.sqrt(0.5)))
+    rot = np.array([[c45, -c45, 0, 0], [c45, c45, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)
+    inst2 = S.make_instances(np.stack([rot, np.eye(4)]), [0, 0])
+    inst2["inv_transform"][0] = np.array([[c45, c45, 0, 0], [-c45, c45, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32).T.reshape(-1)
+    tl2 = vb.Tlas.empty(ctx)
+    tl2.build(inst2, pinf)
+    scene2 = vb.Scene(tl2.nodes, tl2.children, inst2, pinf, pn, pv, pi, ctx)
+    args2 = (tl2.nodes, tl2.children, inst2, pinf, pn, pv, pi)
+    o2 = (rng.normal(size=(50_000, 3)) * 0.3 + np.array([-3.0, -3.0, 0.0])).astype(np.float32)
+    d2 = np.stack([np.ones(len(o2)), np.ones(len(o2)), rng.normal(size=len(o2)) * 0.2], axis=1).astype(np.float32)
+    assert same(scene2, args2, o2, d2) > 1000
 
 
 def test_trace_blas_rust_mode_ids_exact(ctx, oracle):
