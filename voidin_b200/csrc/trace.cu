@@ -487,7 +487,7 @@ __device__ __forceinline__ bool inv_usable(const float* inv) {
     return isfinite(inv[0]) && isfinite(inv[1]) && isfinite(inv[2]) && inv[0] != 0.0f && inv[1] != 0.0f && inv[2] != 0.0f;
 }
 
-__global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
+__global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                    const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                    float tmax, uint8_t* occ_out, unsigned long long* ctl,
                                                    uint32_t* defer_list) {
@@ -501,6 +501,8 @@ __global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const fl
     float eye[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, inv[3] = {0, 0, 0};
     float e2[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, inv2[3] = {0, 0, 0};
     uint32_t tri_base = 0, bvh_index = 0, leaf_first = 0, leaf_cnt = 0;
+    constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
+    uint32_t top = NO_NODE;  // top of the interior-node stack; nstack[0..nh) holds the rest
     bool exhausted = false;
 
     for (;;) {
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const fl
                 eye[0] = ro[3 * r]; eye[1] = ro[3 * r + 1]; eye[2] = ro[3 * r + 2];
                 dir[0] = rd[3 * r]; dir[1] = rd[3 * r + 1]; dir[2] = rd[3 * r + 2];
                 inv[0] = __fdiv_rn(1.0f, dir[0]); inv[1] = __fdiv_rn(1.0f, dir[1]); inv[2] = __fdiv_rn(1.0f, dir[2]);
-                th = 0; nh = 0; lh = 0; leaf_cnt = 0;
+                th = 0; nh = 0; lh = 0; leaf_cnt = 0; top = NO_NODE;
                 tstack[th++] = 0;
                 active = true;
                 if (!inv_usable(inv)) defer = true;
@@ -530,36 +532,41 @@ __global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const fl
         }
         bool finished = false, occluded = false;
         // ---- node step: one interior node, both child boxes ----
-        if (active && !defer && nh > 0 && lh <= A_LSTACK - 2) {
+        // The top of the interior stack lives in a register (`top`), so the common "exactly one interior child is
+        // hit" step touches no local memory and the child-pair load does not wait for a stack load.
+        if (active && !defer && top != NO_NODE && lh <= A_LSTACK - 2) {
             if (nh >= STACK_CAP) {
                 defer = true;
             } else {
-                const uint32_t c0 = bvh_index + nstack[--nh];
+                const uint32_t c0 = bvh_index + top;
                 const NodeW ca = ld_node(sc.bvh_nodes, c0), cb = ld_node(sc.bvh_nodes, c0 + 1);
                 uint32_t m0 = pack_meta(ca), m1 = pack_meta(cb);
                 float d0, d1;
                 bool h0 = slab_hit_w(e2, inv2, ca.a, ca.b, tmax, d0);
                 bool h1 = slab_hit_w(e2, inv2, cb.a, cb.b, tmax, d1);
-                if (h0 | h1) {
-                    // a leaf is visited when the pair is hit (tmax = 1e30), an interior node only when its own box is
-                    const bool both = pair_rule;
-                    bool v0 = h0 || (both && (m0 >> 30) != 0);
-                    bool v1 = h1 || (both && (m1 >> 30) != 0);
-                    // nearer child on top of its stack (only a heuristic here)
-                    if (h0 && h1 && d0 < d1) {
-                        const uint32_t tm = m0; m0 = m1; m1 = tm;
-                        const bool tv = v0; v0 = v1; v1 = tv;
-                    }
-                    if (v0) { if (m0 >> 30) lstack[lh++] = m0; else nstack[nh++] = m0; }
-                    if (v1) { if (m1 >> 30) lstack[lh++] = m1; else nstack[nh++] = m1; }
+                // a leaf is visited when the pair is hit (tmax = 1e30), an interior node only when its own box is
+                const bool any = h0 | h1;
+                bool v0 = h0 || (any && pair_rule && (m0 >> 30) != 0);
+                bool v1 = h1 || (any && pair_rule && (m1 >> 30) != 0);
+                // nearer child last, so that it ends up on top (only a heuristic here)
+                if (h0 && h1 && d0 < d1) {
+                    const uint32_t tm = m0; m0 = m1; m1 = tm;
+                    const bool tv = v0; v0 = v1; v1 = tv;
                 }
+                const bool i0 = v0 && (m0 >> 30) == 0, i1 = v1 && (m1 >> 30) == 0;
+                if (v0 && !i0) lstack[lh++] = m0;
+                if (v1 && !i1) lstack[lh++] = m1;
+                if (i0 && i1) { nstack[nh++] = m0; top = m1; }
+                else if (i0) top = m0;
+                else if (i1) top = m1;
+                else top = (nh > 0) ? nstack[--nh] : NO_NODE;
             }
         }
         // ---- triangle step: one triangle of the current leaf (bvh.wgsl:43-51) ----
         // A lane with pending leaves can keep doing node steps, so the triangle path waits until enough lanes have
         // a triangle to test, or until some lane has nothing else to do (or no room for more leaves).
         const bool has_tri = active && !defer && (leaf_cnt > 0 || lh > 0);
-        const bool must_tri = has_tri && (nh == 0 || lh > A_LSTACK - 2);
+        const bool must_tri = has_tri && (top == NO_NODE || lh > A_LSTACK - 2);
         const uint32_t tri_lanes = __ballot_sync(FULL_MASK, has_tri);
         const bool run_tri = (__ballot_sync(FULL_MASK, must_tri) != 0) || ((uint32_t)__popc(tri_lanes) >= TRI_VOTE);
         if (run_tri && has_tri) {
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const fl
             if (trig_w(e2, d2, v0, v1, v2, &h)) { finished = true; occluded = true; }
         }
         // ---- TLAS step (bvh.wgsl:89-123), only when the current instance is exhausted ----
-        if (active && !defer && !finished && nh == 0 && lh == 0 && leaf_cnt == 0) {
+        if (active && !defer && !finished && top == NO_NODE && lh == 0 && leaf_cnt == 0) {
             if (th == 0) {
                 finished = true;
             } else {
@@ -600,7 +607,7 @@ __global__ void __launch_bounds__(128) k_trace_any(BvhCudaSceneDesc sc, const fl
                         defer = true;
                     } else {
                         const uint32_t m = pack_meta(ld_node(sc.bvh_nodes, bvh_index));
-                        if (m >> 30) lstack[lh++] = m; else nstack[nh++] = m;
+                        if (m >> 30) lstack[lh++] = m; else top = m;
                     }
                 } else {
                     uint32_t min_index, max_index;
