@@ -22,3 +22,10 @@ for k in range(3):
         print(f"   {nm:12s} work {buf[2*i]/1e3:9.1f} us   barrier {buf[2*i+1]/1e3:9.1f} us")
         tw += buf[2*i]; tb += buf[2*i+1]
     print(f"   total work {tw/1e3:.1f} us, barrier {tb/1e3:.1f} us")
+    blk = (C.c_ulonglong * 2048)()
+    if ctx.lib.bvh_cuda_debug_t1_blocks(blk):
+        for kind, nm in enumerate(["table", "scatter"]):
+            a = np.array(blk[kind * 1024: kind * 1024 + 444], dtype=np.float64) / 22e3  # us per shuffle, level 0
+            order = np.argsort(a)
+            print(f"   level-0 {nm}: per-block work us/shuffle min {a.min():.2f} med {np.median(a):.2f} p90 {np.percentile(a,90):.2f} max {a.max():.2f}; slowest blocks {order[-6:].tolist()} fastest {order[:4].tolist()}")
+            print("     by tile decile:", [round(float(a[i*42:(i+1)*42].mean()),2) for i in range(10)])

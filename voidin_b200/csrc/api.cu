@@ -14,6 +14,7 @@ int blas_t2b_setup();
 int blas_t2w_occupancy();
 int blas_t1_coop_occupancy();
 int blas_t1_timing(unsigned long long* out32);
+int blas_t1_blocks(unsigned long long* out2048);
 
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what) {
     if (ctx) ctx->err = what ? what : "";
@@ -149,6 +150,7 @@ uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->laun
 
 // Debug only (library built with -DBVH_T1_TIMING): per-phase-kind work / barrier-wait ns of block 0 in the grid tier.
 int bvh_cuda_debug_t1_timing(unsigned long long* out32) { return blas_t1_timing(out32); }
+int bvh_cuda_debug_t1_blocks(unsigned long long* out2048) { return blas_t1_blocks(out2048); }
 
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable) {
     if (!ctx) return BVH_CUDA_EINVAL;

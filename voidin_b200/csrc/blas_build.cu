@@ -1111,6 +1111,7 @@ struct T1Args {
 // grows, so there is no reset race; generation g completes when it reaches g * gridDim.x.
 #ifdef BVH_T1_TIMING
 __device__ unsigned long long g_t1_time[32];  // [2*kind] work ns, [2*kind+1] barrier wait ns (block 0)
+__device__ unsigned long long g_t1_blk[2][1024];  // level 0: per-block work ns of the table / scatter phases
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -1128,6 +1129,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
             g_t1_time[2 * (kind)] += _t1 - _t0;                                          \
             g_t1_time[2 * (kind) + 1] += _t2 - _t1;                                      \
         }                                                                                \
+        if (threadIdx.x == 0 && level == 0 && ((kind) == 7 || (kind) == 8) && blockIdx.x < 1024) \
+            g_t1_blk[(kind) - 7][blockIdx.x] += _t1 - _t0;                               \
     } while (0)
 #else
 #define T1_PHASE(kind, call)          \
@@ -1968,6 +1971,18 @@ int blas_t1_timing(unsigned long long* out32) {
     return 1;
 #else
     (void)out32;
+    return 0;
+#endif
+}
+
+int blas_t1_blocks(unsigned long long* out2048) {
+#ifdef BVH_T1_TIMING
+    static unsigned long long z[2048];
+    cudaMemcpyFromSymbol(out2048, g_t1_blk, sizeof(z));
+    cudaMemcpyToSymbol(g_t1_blk, z, sizeof(z));
+    return 1;
+#else
+    (void)out2048;
     return 0;
 #endif
 }
