@@ -24,7 +24,10 @@ namespace {
 
 constexpr int T3_MAX = 32;
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
-constexpr int T2_CAP = 2048;    // block-per-node tier: 257..2048 (256 threads)
+#ifndef T2_CAP_V
+#define T2_CAP_V 2048
+#endif
+constexpr int T2_CAP = T2_CAP_V;  // block-per-node tier: 257..T2_CAP (256 threads)
 constexpr int T2_THREADS = 256;
 #ifndef T2_MIN_BLOCKS
 #define T2_MIN_BLOCKS 3  // 64 registers, no spills; 0.85 -> 0.61 ms for the tier on the dragon-class mesh (4 gives no more)
