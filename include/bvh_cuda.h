@@ -83,7 +83,7 @@ typedef struct BvhCudaBuildStats {
     uint32_t big_block_tasks;    /* nodes handled by one 1024-thread block each (2049..16384) */
     uint32_t block_tasks;        /* nodes handled one block each from the device task queue (257..2048) */
     uint32_t warp_node_tasks;    /* nodes handled one warp each from the second task queue (33..256) */
-    uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each */
+    uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each (0 when the thread tier takes them all) */
     uint32_t kernel_launches;    /* kernels launched by this build */
     /* Device time per phase in ms (CUDA events on the build's stream); all zero unless profiling is enabled. */
     float ms_setup;              /* k_setup: centroids, triangle boxes */
@@ -94,6 +94,8 @@ typedef struct BvhCudaBuildStats {
     float ms_warp;               /* k_t3: warp-per-sub-tree kernel (one launch) */
     float ms_emit;               /* numbering scan + node emit + index permutation */
     float ms_total;
+    float ms_thread;             /* k_t4: thread-per-sub-tree kernel (one launch) */
+    uint32_t thread_tasks;       /* sub-trees (<= 32 triangles) handled one thread each */
 } BvhCudaBuildStats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -103,7 +105,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx);
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
 /* Total kernels launched through this context since creation. */
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
-int bvh_cuda_abi_version(void);
+int bvh_cuda_abi_version(void); /* 2 */
 /* enable != 0: later BLAS builds record per-phase CUDA-event timings into BvhCudaBuildStats (a few extra event
  * records per build, no extra synchronisation). */
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable);

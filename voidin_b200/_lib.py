@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbvh_cuda.so")
+# BVH_CUDA_LIB selects another build of the same library (scripts/variants.py compares compile-time variants)
+LIB_PATH = os.environ.get("BVH_CUDA_LIB") or os.path.join(_HERE, "libbvh_cuda.so")
 
 # every symbol include/bvh_cuda.h declares
 SYMBOLS = [
@@ -61,6 +62,8 @@ class BuildStats(C.Structure):
         ("ms_warp", C.c_float),
         ("ms_emit", C.c_float),
         ("ms_total", C.c_float),
+        ("ms_thread", C.c_float),
+        ("thread_tasks", C.c_uint32),
     ]
 
     def as_dict(self):

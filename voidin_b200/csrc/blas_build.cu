@@ -16,6 +16,7 @@
 //   rank(X) = #interior nodes with start < X.start  +  #ancestors of X sharing X.start
 // with one prefix sum over N counters, and a final kernel emits the 32-byte BvhNodes.
 #include "common.cuh"
+#include "t4_seq.cuh"
 
 #include <cstdlib>
 #include <atomic>
@@ -23,6 +24,16 @@
 namespace {
 
 constexpr int T3_MAX = 32;
+// Thread-per-sub-tree tier (k_t4, t4_seq.cuh): sub-trees of <= T4_MAX primitives are built by ONE thread each with the
+// plain sequential algorithm.  32: k_t4 replaces the warp-per-sub-tree kernel k_t3 altogether; 16: k_t3 keeps the
+// nodes of 17..32 primitives and hands every child of <= 16 to k_t4; 0: tier off.
+#ifndef T4_MAX_V
+#define T4_MAX_V 32
+#endif
+constexpr int T4_MAX = T4_MAX_V;
+static_assert(T4_MAX == 0 || T4_MAX == 16 || T4_MAX == 32, "T4_MAX_V must be 0, 16 or 32");
+constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
+constexpr int T4_THREADS = (T4_CAP == 32) ? 224 : 448;  // 8 words per slot per thread: 229 376 B of shared memory per block
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
 #ifndef T2_CAP_V
 #define T2_CAP_V 2048
@@ -77,6 +88,7 @@ struct BuildState {
     uint32_t levels_done;
     uint32_t t3_inline;
     uint32_t neg_zero;  // some referenced vertex coordinate is -0.0: box zeros need the reference's first-encounter sign
+    uint32_t t4_count;
 };
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
@@ -169,6 +181,25 @@ __global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint
     ids[i] = i;
 }
 
+// Device task lists, by node size (see the tier table in DESIGN.md).
+struct Queues {
+    Task* qb;   // big-block tasks (T2_CAP < n <= T2B_CAP)
+    Task* q;    // block-per-node tasks (T2W_CAP < n <= T2_CAP)
+    Task* qw;   // warp-per-node tasks  (T3_MAX < n <= T2W_CAP)
+    Task* t3;   // warp-per-sub-tree tasks (T4_MAX < n <= T3_MAX)
+    Task* t4;   // thread-per-sub-tree tasks (n <= T4_MAX)
+    uint32_t qb_cap, q_cap, qw_cap, t3_cap, t4_cap;
+};
+
+__device__ __forceinline__ void push_t4(const Queues& Q, BuildState* st, uint32_t start, uint32_t n, uint32_t leftrun,
+                                        uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
+    const uint32_t idx = atomicAdd(&st->t4_count, 1u);
+    if (idx >= Q.t4_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
+    Task* d = Q.t4 + idx;
+    d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
+    d->flags = flags; d->ready = 0; d->pad = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // T3: one warp builds a whole sub-tree of <= 32 primitives.  Lane j owns slot j of the range.
 // ------------------------------------------------------------------------------------------------
@@ -184,7 +215,7 @@ struct T3Smem {
 // One warp builds the whole sub-tree of task `t` (<= 32 primitives).  Lane j owns slot j of the range.
 __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint32_t lane, uint32_t* ids,
                                            const float4* __restrict__ cent, const float4* __restrict__ box, uint4* recs,
-                                           uint32_t* A, BuildState* st) {
+                                           uint32_t* A, BuildState* st, const Queues& Q) {
     const bool nz = st->neg_zero != 0;
     float (*sm_box)[32] = sm.box;
     float (*sm_cent)[32] = sm.cent;
@@ -211,6 +242,18 @@ __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint
         const bool active = lane >= s && lane < s + n;
         const uint32_t e = pay & 31u;
         const uint32_t abs_start = t.start + s;
+        if (T4_MAX > 0 && T4_MAX < T3_MAX && (int)n <= T4_MAX) {
+            // hand the whole child sub-tree to the thread-per-sub-tree kernel (it runs after this one and reads the
+            // range in the order this warp writes back at the end; nothing below touches these slots again)
+            if (lane == 0) push_t4(Q, st, abs_start, n, leftrun, pstart, pleftrun, fl);
+            if (sp == 0) break;
+            sp--;
+            const uint32_t a2 = __shfl_sync(FULL_MASK, stk_a, sp);
+            pstart = __shfl_sync(FULL_MASK, stk_b, sp);
+            pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
+            s = a2 & 0xFFu; n = a2 >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
+            continue;
+        }
         // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
         float lo[3], hi[3];
 #pragma unroll
@@ -345,9 +388,10 @@ __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint
     if (lane < t.n) ids[t.start + lane] = sm_gid[pay & 31u];
 }
 
-__global__ void __launch_bounds__(256, 4) k_t3(const Task* __restrict__ tasks, uint32_t* ids,
+__global__ void __launch_bounds__(256, 4) k_t3(Queues Q, uint32_t* ids,
                                                const float4* __restrict__ cent, const float4* __restrict__ box,
                                                uint4* recs, uint32_t* A, BuildState* st) {
+    const Task* __restrict__ tasks = Q.t3;
     __shared__ float s_box[8][6][32];
     __shared__ float s_cent[8][3][32];
     __shared__ uint32_t s_gid[8][32];
@@ -358,7 +402,31 @@ __global__ void __launch_bounds__(256, 4) k_t3(const Task* __restrict__ tasks, u
     const T3Smem sm{s_box[w], s_cent[w], s_gid[w], s_tab[w], s_pay[w]};
     for (uint32_t ti = blockIdx.x * 8 + w; ti < n_tasks; ti += gridDim.x * 8) {
         const Task t = tasks[ti];
-        t3_subtree(t, sm, lane, ids, cent, box, recs, A, st);
+        t3_subtree(t, sm, lane, ids, cent, box, recs, A, st, Q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T4: one THREAD per sub-tree of <= CAP primitives (t4_seq.cuh).  Working set in shared memory as [word][thread].
+// ------------------------------------------------------------------------------------------------
+template <int CAP, int BD>
+__global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
+                                             const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st) {
+    extern __shared__ uint32_t s_t4[];
+    const T4Mem<CAP> m{reinterpret_cast<float*>(s_t4) + threadIdx.x, s_t4 + 6 * CAP * BD + threadIdx.x, (uint32_t)BD};
+    const uint32_t n_tasks = min(st->t4_count, Q.t4_cap);
+    for (uint32_t ti = blockIdx.x * BD + threadIdx.x; ti < n_tasks; ti += gridDim.x * BD) {
+        const Task tk = Q.t4[ti];
+        const T4Task t{tk.start, tk.n, tk.leftrun, tk.pstart, tk.pleftrun, tk.flags};
+        for (uint32_t j = 0; j < t.n; ++j) {
+            const uint32_t g = __ldcg(&ids[t.start + j]);
+            const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
+            m.gid(j) = g;
+            m.box(0, j) = b0.x; m.box(1, j) = b0.y; m.box(2, j) = b0.z;
+            m.box(3, j) = b1.x; m.box(4, j) = b1.y; m.box(5, j) = b1.z;
+        }
+        const uint32_t err = t4_core<CAP>(t, m, reinterpret_cast<const T4Cent*>(cent), ids, reinterpret_cast<T4Rec*>(recs), A);
+        if (err) atomicOr(&st->err, DERR_DEGENERATE);
     }
 }
 
@@ -366,14 +434,6 @@ __global__ void __launch_bounds__(256, 4) k_t3(const Task* __restrict__ tasks, u
 // T2: one block per node (33..CAP primitives), tasks from a device queue; children go back to the
 // queue (> 32) or to the T3 list.
 // ------------------------------------------------------------------------------------------------
-struct Queues {
-    Task* qb;   // big-block tasks (T2_CAP < n <= T2B_CAP)
-    Task* q;    // block-per-node tasks (T2W_CAP < n <= T2_CAP)
-    Task* qw;   // warp-per-node tasks  (T3_MAX < n <= T2W_CAP)
-    Task* t3;   // warp-per-sub-tree tasks (n <= T3_MAX)
-    uint32_t qb_cap, q_cap, qw_cap, t3_cap;
-};
-
 __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint32_t epoch, uint32_t start, uint32_t n,
                                            uint32_t leftrun, uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
     if (n > T3_MAX) {
@@ -393,6 +453,8 @@ __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint
         d->flags = flags; d->pad = 0;
         __threadfence();
         *(volatile uint32_t*)&d->ready = epoch;
+    } else if ((int)n <= T4_MAX) {
+        push_t4(Q, st, start, n, leftrun, pstart, pleftrun, flags);
     } else {
         const uint32_t idx = atomicAdd(&st->t3_count, 1u);
         if (idx >= Q.t3_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
@@ -1076,13 +1138,13 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
             Task c;
             c.start = start; c.n = p; c.leftrun = leftrun + 1; c.pstart = start; c.pleftrun = leftrun; c.flags = tflags & ~3u;
             c.ready = 0; c.pad = 0;
-            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st);
+            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st, Q);
         }
         if (small_r) {
             Task c;
             c.start = start + p; c.n = n - p; c.leftrun = 0; c.pstart = start; c.pleftrun = leftrun; c.flags = TF_RIGHT | (tflags & ~3u);
             c.ready = 0; c.pad = 0;
-            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st);
+            t3_subtree(c, sm3, lane, ids, cent, box, recs, A, st, Q);
         }
         __syncwarp();
     }
@@ -1949,6 +2011,7 @@ __global__ void __launch_bounds__(256) k_roots(const uint32_t* __restrict__ tbas
 
 constexpr size_t T2_SMEM = (size_t)T2_CAP * 10;    // 2 x u32 payload + u16 table per slot
 constexpr size_t T2B_SMEM = (size_t)T2B_CAP * 10;
+constexpr size_t T4_SMEM = (size_t)8 * T4_CAP * T4_THREADS * 4;  // 6 float + 2 u32 words per slot per thread
 
 int blas_t2_occupancy() {
     int occ = 0;
@@ -2034,7 +2097,10 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
     const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
     const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
-    const uint32_t t3_cap = N + NM + 16;
+    // sub-trees of <= 32 primitives: thread tasks (<= T4_MAX) and warp tasks (the rest).  Sibling ranges are disjoint,
+    // but with 0 < T4_MAX < 32 the warp kernel re-posts children of its own tasks, hence two full-size lists.
+    const uint32_t t3_cap = (T4_MAX >= T3_MAX) ? 16u : (T4_MAX > 0 ? N / (uint32_t)(T4_MAX + 1) + NM + 16 : N + NM + 16);
+    const uint32_t t4_cap = (T4_MAX > 0) ? N + NM + 16 : 16u;
     const uint32_t scan_n = N + 1;
     const uint32_t scan_blocks = (scan_n + SCAN_TILE - 1) / SCAN_TILE;
     const uint32_t mscan_n = NM + 1;
@@ -2047,7 +2113,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
              *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr;
+    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -2067,6 +2133,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         q = c.take<Task>(q_cap);
         qw = c.take<Task>(qw_cap);
         t3 = c.take<Task>(t3_cap);
+        t4 = c.take<Task>(t4_cap);
         lv[0] = c.take<LevelNode>(max_large);
         lv[1] = c.take<LevelNode>(max_large);
         sc = c.take<NodeScratch>(max_large);
@@ -2100,7 +2167,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
     const bool prof = ctx->profiling;
     if (prof) cudaEventRecord(ctx->ev[0], stream);
-    Queues Q{qb, q, qw, t3, qb_cap, q_cap, qw_cap, t3_cap};
+    Queues Q{qb, q, qw, t3, t4, qb_cap, q_cap, qw_cap, t3_cap, t4_cap};
     k_init_state<<<1, 32, 0, stream>>>(st);
     if (d_mesh_info) k_mesh_table<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(d_mesh_info, NM, 3 * N, tbase, voff, st);
     else k_single_mesh_table<<<1, 32, 0, stream>>>(N, tbase, voff);
@@ -2153,9 +2220,19 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     }
     if (prof) cudaEventRecord(ctx->ev[3], stream);
     // ---- T3: one warp per small sub-tree ----
-    {
+    if (T4_MAX < T3_MAX) {
         const int blocks = ctx->sm_count * 8;
-        k_t3<<<blocks, 256, 0, stream>>>(t3, ids0, cent, box, recs, A, st);
+        k_t3<<<blocks, 256, 0, stream>>>(Q, ids0, cent, box, recs, A, st);
+        launches++;
+    }
+    if (prof) cudaEventRecord(ctx->ev[8], stream);
+    // ---- T4: one thread per small sub-tree ----
+    if (T4_MAX > 0) {
+        if (!ctx->t4_ready) {
+            CU_CHECK(ctx, cudaFuncSetAttribute(k_t4<T4_CAP, T4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
+            ctx->t4_ready = true;
+        }
+        k_t4<T4_CAP, T4_THREADS><<<ctx->sm_count, T4_THREADS, T4_SMEM, stream>>>(Q, ids0, cent, box, recs, A, st);
         launches++;
     }
     if (prof) cudaEventRecord(ctx->ev[4], stream);
@@ -2198,6 +2275,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.block_tasks = hs->t2_done;
     stats.warp_node_tasks = hs->t2w_done;
     stats.warp_tasks = hs->t3_count + hs->t3_inline;
+    stats.thread_tasks = hs->t4_count;
     stats.kernel_launches = launches;
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
@@ -2205,7 +2283,8 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         cudaEventElapsedTime(&stats.ms_big_block, ctx->ev[2], ctx->ev[7]);
         cudaEventElapsedTime(&stats.ms_block, ctx->ev[7], ctx->ev[6]);
         cudaEventElapsedTime(&stats.ms_warp_node, ctx->ev[6], ctx->ev[3]);
-        cudaEventElapsedTime(&stats.ms_warp, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&stats.ms_warp, ctx->ev[3], ctx->ev[8]);
+        cudaEventElapsedTime(&stats.ms_thread, ctx->ev[8], ctx->ev[4]);
         cudaEventElapsedTime(&stats.ms_emit, ctx->ev[4], ctx->ev[5]);
         cudaEventElapsedTime(&stats.ms_total, ctx->ev[0], ctx->ev[5]);
     }

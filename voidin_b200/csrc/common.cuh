@@ -47,7 +47,8 @@ struct bvh_cuda_ctx {
     size_t defer_cap = 0;
     // optional per-phase timing
     bool profiling = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[9] = {};
+    bool t4_ready = false;  // k_t4's dynamic shared-memory limit has been raised on this context's device
 };
 
 struct bvh_cuda_scene {
