@@ -28,7 +28,7 @@ constexpr int T3_MAX = 32;
 // plain sequential algorithm.  32: k_t4 replaces the warp-per-sub-tree kernel k_t3 altogether; 16: k_t3 keeps the
 // nodes of 17..32 primitives and hands every child of <= 16 to k_t4; 0: tier off.
 #ifndef T4_MAX_V
-#define T4_MAX_V 32
+#define T4_MAX_V 16  // measured on the dragon-class build: 16 -> 7.53 ms, 0 (tier off) -> 7.76 ms, 32 -> 8.83 ms
 #endif
 constexpr int T4_MAX = T4_MAX_V;
 static_assert(T4_MAX == 0 || T4_MAX == 16 || T4_MAX == 32, "T4_MAX_V must be 0, 16 or 32");
