@@ -70,7 +70,11 @@ if __name__ == "__main__":
         np.savez(CACHE, nodes=onodes.view(np.uint8).reshape(-1), idx=oidx)
         print(f"oracle: dragon-class build {time.time() - t0:.1f} s on the host", flush=True)
     names = sys.argv[1:] or sorted(os.path.basename(p)[len("libbvh_cuda_"):-3] for p in glob.glob(os.path.join(ROOT, "voidin_b200", "variants", "libbvh_cuda_*.so")))
-    for name in names:
+    for spec in names:  # "<name>" or "<name>:KEY=VAL[,KEY=VAL]" (extra environment for that run)
+        name, _, extra = spec.partition(":")
         env = dict(os.environ, BVH_CUDA_LIB=os.path.join(ROOT, "voidin_b200", "variants", f"libbvh_cuda_{name}.so"))
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name], env=env, timeout=600)
+        for kv in filter(None, extra.split(",")):
+            k, _, v = kv.partition("=")
+            env[k] = v
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", spec], env=env, timeout=600)
         if r.returncode: print(f"[{name}] child exited with {r.returncode}", flush=True)
