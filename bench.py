@@ -686,7 +686,7 @@ def main():
         r_ms_step = r_tot / args.steps
         value = world * n_tris / (b_ms_step * 1e-3) / 1e6
         rvalue = world * n_rays / (r_ms_step * 1e-3) / 1e6
-        lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_big_block", "ms_block", "ms_warp_node", "ms_warp", "ms_emit", "ms_total")}
+        lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_big_block", "ms_block", "ms_warp_node", "ms_warp", "ms_thread", "ms_emit", "ms_total")}
         tr = measured_traffic()
         build_roof = {"bound": "hbm", "achieved": bb / (lib_ms["ms_total"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                       "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak,

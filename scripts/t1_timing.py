@@ -29,3 +29,7 @@ for k in range(3):
             order = np.argsort(a)
             print(f"   level-0 {nm}: per-block work us/shuffle min {a.min():.2f} med {np.median(a):.2f} p90 {np.percentile(a,90):.2f} max {a.max():.2f}; slowest blocks {order[-6:].tolist()} fastest {order[:4].tolist()}")
             print("     by tile decile:", [round(float(a[i*42:(i+1)*42].mean()),2) for i in range(10)])
+        ts = np.array(blk[900:1024], dtype=np.float64)
+        meta = np.array(blk[1024 + 900:2048], dtype=np.uint64)
+        print("   per level (us, tiles, nodes):", [(round(float(ts[i + 1] - ts[i]) / 1e3, 1), int(meta[i] & 0xFFFFFFFF), int(meta[i] >> 32))
+                                                   for i in range(len(ts) - 1) if ts[i] > 0 and ts[i + 1] > 0])

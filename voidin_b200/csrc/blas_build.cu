@@ -24,31 +24,18 @@
 namespace {
 
 constexpr int T3_MAX = 32;
-// 1: k_t3 walks a sub-tree level by level with every node of a depth as a segment of lanes (t3_subtree_seg);
-// 0: one node at a time with an explicit DFS stack (t3_subtree).
-#ifndef T3_SEG
-#define T3_SEG 0  // measured on B200 (dragon-class): 1.42 ms vs 1.34 ms for the DFS form -- SAH sub-trees are deep, not bushy
-#endif
-// 1: sub-trees of <= 32 primitives go through the same ticket queue as the warp-per-node tasks and k_t2w's warps
-// build them (t3_subtree_seg) between node tasks: no separate k_t3 launch, no ramp/tail between the two tiers.
-#ifndef T23_FUSED
-#define T23_FUSED 0
-#endif
-// 1: levels of the grid tier with at most one tile per block run PA + barrier + PB as one function (p_t1_shuffle_one)
-#ifndef T1_ONE_TILE
-#define T1_ONE_TILE 1
-#endif
-#if T23_FUSED && !T3_SEG
-#error "T23_FUSED needs T3_SEG"
-#endif
 // Thread-per-sub-tree tier (k_t4, t4_seq.cuh): sub-trees of <= T4_MAX primitives are built by ONE thread each with the
-// plain sequential algorithm.  16: k_t3 keeps the nodes of 17..32 primitives and hands every child of <= 16 to k_t4
-// while the thread tier has room (see push_t4); 0: tier off.
+// plain sequential algorithm.  32: k_t4 replaces the warp-per-sub-tree kernel k_t3 altogether; 16: k_t3 keeps the
+// nodes of 17..32 primitives and hands every child of <= 16 to k_t4; 0: tier off.
 #ifndef T4_MAX_V
 #define T4_MAX_V 16  // measured on the dragon-class build: 16 -> 7.53 ms, 0 (tier off) -> 7.76 ms, 32 -> 8.83 ms
 #endif
 constexpr int T4_MAX = T4_MAX_V;
-static_assert(T4_MAX == 0 || T4_MAX == 16, "T4_MAX_V must be 0 or 16 (32 = no warp tier at all was measured slower: 8.83 ms)");
+static_assert(T4_MAX == 0 || T4_MAX == 16 || T4_MAX == 32, "T4_MAX_V must be 0, 16 or 32");
+// Other forms of the small-sub-tree tiers that were built, verified bit-exact and measured slower on B200 (dragon-class,
+// commit 3f0c5bd and its parent): all nodes of one depth as lane segments of one warp (1.42 ms vs 1.34 ms: SAH sub-trees are
+// deep, not bushy, and a pass costs as much as a node visit); sub-trees through k_t2w's queue (2.94 ms vs 2.46 ms for the
+// two tiers); thread tier limited to whole waves of sm_count x T4_THREADS tasks (1.22 ms vs 1.24 ms).
 constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
 constexpr int T4_THREADS = (T4_CAP == 32) ? 224 : 448;  // 8 words per slot per thread: 229 376 B of shared memory per block
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
@@ -206,21 +193,15 @@ struct Queues {
     Task* t3;   // warp-per-sub-tree tasks (T4_MAX < n <= T3_MAX)
     Task* t4;   // thread-per-sub-tree tasks (n <= T4_MAX)
     uint32_t qb_cap, q_cap, qw_cap, t3_cap, t4_cap;
-    uint32_t t4_soft;  // <= t4_cap: tasks the thread tier accepts (whole waves)
 };
 
-// Returns false when the thread tier is full: k_t4 runs whole waves of sm_count x T4_THREADS tasks (a task is one
-// thread for ~0.5 ms, so a last wave that is nearly empty costs as much as a full one); the caller then keeps the
-// sub-tree on the warp tier.
-__device__ __forceinline__ bool push_t4(const Queues& Q, BuildState* st, uint32_t start, uint32_t n, uint32_t leftrun,
+__device__ __forceinline__ void push_t4(const Queues& Q, BuildState* st, uint32_t start, uint32_t n, uint32_t leftrun,
                                         uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
-    if (ld_vol(&st->t4_count) >= Q.t4_soft) return false;
     const uint32_t idx = atomicAdd(&st->t4_count, 1u);
-    if (idx >= Q.t4_soft) return false;
+    if (idx >= Q.t4_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
     Task* d = Q.t4 + idx;
     d->start = start; d->n = n; d->leftrun = leftrun; d->pstart = pstart; d->pleftrun = pleftrun;
     d->flags = flags; d->ready = 0; d->pad = 0;
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -265,20 +246,17 @@ __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint
         const bool active = lane >= s && lane < s + n;
         const uint32_t e = pay & 31u;
         const uint32_t abs_start = t.start + s;
-        if (!T3_SEG && T4_MAX > 0 && T4_MAX < T3_MAX && (int)n <= T4_MAX) {
+        if (T4_MAX > 0 && T4_MAX < T3_MAX && (int)n <= T4_MAX) {
             // hand the whole child sub-tree to the thread-per-sub-tree kernel (it runs after this one and reads the
             // range in the order this warp writes back at the end; nothing below touches these slots again)
-            uint32_t taken = 0;
-            if (lane == 0) taken = push_t4(Q, st, abs_start, n, leftrun, pstart, pleftrun, fl) ? 1u : 0u;
-            if (__shfl_sync(FULL_MASK, taken, 0)) {
-                if (sp == 0) break;
-                sp--;
-                const uint32_t a2 = __shfl_sync(FULL_MASK, stk_a, sp);
-                pstart = __shfl_sync(FULL_MASK, stk_b, sp);
-                pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
-                s = a2 & 0xFFu; n = a2 >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
-                continue;
-            }
+            if (lane == 0) push_t4(Q, st, abs_start, n, leftrun, pstart, pleftrun, fl);
+            if (sp == 0) break;
+            sp--;
+            const uint32_t a2 = __shfl_sync(FULL_MASK, stk_a, sp);
+            pstart = __shfl_sync(FULL_MASK, stk_b, sp);
+            pleftrun = __shfl_sync(FULL_MASK, stk_c, sp);
+            s = a2 & 0xFFu; n = a2 >> 8; leftrun = 0; fl = TF_RIGHT | (t.flags & ~3u);
+            continue;
         }
         // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
         float lo[3], hi[3];
@@ -414,187 +392,6 @@ __device__ __forceinline__ void t3_subtree(const Task& t, const T3Smem& sm, uint
     if (lane < t.n) ids[t.start + lane] = sm_gid[pay & 31u];
 }
 
-// Level-synchronous form of t3_subtree: all nodes of one depth of the sub-tree are processed at once, each as a
-// SEGMENT of lanes [s, s+n) (sibling ranges are disjoint and a node's result depends only on the order of its own
-// range, so the order in which nodes are visited is free).  Ballots are shifted and masked per segment, reductions
-// use the segment's lane mask, and the 21 candidates of a segment are costed by its own lanes (lane j takes
-// candidates j, j+n, ...).  A sub-tree of 32 primitives takes ~5 passes instead of ~15 node visits.
-struct T3SegSmem {
-    uint8_t* cu;  // [21][32] unexamined primitive of candidate c for the segment starting at lane s
-    uint8_t* cp;  // [21][32] recorded pivot
-};
-
-__device__ __forceinline__ void t3_subtree_seg(const Task& t, const T3Smem& sm, const T3SegSmem& sg, uint32_t lane,
-                                               uint32_t* ids, const float4* __restrict__ cent,
-                                               const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st) {
-    const bool nz = st->neg_zero != 0;
-    float (*sm_box)[32] = sm.box;
-    float (*sm_cent)[32] = sm.cent;
-    uint32_t* sm_gid = sm.gid;
-    uint8_t* sm_tab = sm.tab;
-    uint16_t* sm_pay = sm.pay;
-    __syncwarp();
-    if (lane < t.n) {
-        const uint32_t g = __ldcg(&ids[t.start + lane]);
-        const float4 c = cent[g];
-        const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-        sm_box[0][lane] = b0.x; sm_box[1][lane] = b0.y; sm_box[2][lane] = b0.z;
-        sm_box[3][lane] = b1.x; sm_box[4][lane] = b1.y; sm_box[5][lane] = b1.z;
-        sm_cent[0][lane] = c.x; sm_cent[1][lane] = c.y; sm_cent[2][lane] = c.z;
-        sm_gid[lane] = g;
-    }
-    __syncwarp();
-    const uint32_t base_fl = t.flags & ~3u;
-    uint32_t pay = lane;  // bits 0-4: local primitive, 5-13: plane counts of the current node
-    // per-lane description of the node (segment) this lane currently belongs to
-    uint32_t s = 0, n = t.n, leftrun = t.leftrun, pstart = t.pstart, pleftrun = t.pleftrun, fl = t.flags;
-    bool live = lane < t.n;
-
-    while (__any_sync(FULL_MASK, live)) {
-        const uint32_t nmask = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
-        const uint32_t segmask = live ? (nmask << s) : (1u << lane);
-        const uint32_t j = lane - s;
-        const uint32_t e = pay & 31u;
-        const uint32_t abs_start = t.start + s;
-        // own vertex box (blas.rs:87-88,117-123), folded from +-1e30
-        float lo[3], hi[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            uint32_t mn = live ? f2o(sm_box[c][e]) : ENC_POS_INIT;
-            uint32_t mx = live ? f2o(sm_box[3 + c][e]) : ENC_NEG_INIT;
-            mn = min(__reduce_min_sync(segmask, mn), ENC_POS_INIT);
-            mx = max(__reduce_max_sync(segmask, mx), ENC_NEG_INIT);
-            lo[c] = o2f(mn);
-            hi[c] = o2f(mx);
-        }
-        if (nz) {
-            // rare path (-0.0 in the input): a zero face takes the sign of the first zero in slot order, as the
-            // reference's sequential fold does (lane order == slot order inside a segment)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const float cur = (c < 3) ? lo[c] : hi[c - 3];
-                const float mine = live ? sm_box[c][e] : 1.0f;
-                const uint32_t p = __reduce_min_sync(segmask, (live && mine == 0.0f) ? lane : 32u);
-                const float z = __shfl_sync(FULL_MASK, mine, p & 31u);
-                if (live && cur == 0.0f && p < 32u) { if (c < 3) lo[c] = z; else hi[c - 3] = z; }
-            }
-        }
-        if (live && n <= 3) {  // leaf (blas.rs:106-109)
-            if (j == 0) emit_rec(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
-            live = false;
-        }
-        const bool act = live;  // lanes of interior nodes
-        if (!__any_sync(FULL_MASK, act)) break;
-        // centroid bounds (blas.rs:142) and plane counts
-        {
-            float cmin[3], cmax[3], cc[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                cc[c] = act ? sm_cent[c][e] : 0.0f;
-                uint32_t mn = act ? f2o(cc[c]) : ENC_POS_INIT;
-                uint32_t mx = act ? f2o(cc[c]) : ENC_NEG_INIT;
-                mn = min(__reduce_min_sync(segmask, mn), ENC_POS_INIT);
-                mx = max(__reduce_max_sync(segmask, mx), ENC_NEG_INIT);
-                cmin[c] = o2f(mn);
-                cmax[c] = o2f(mx);
-            }
-            pay = e | (plane_counts(cc[0], cc[1], cc[2], cmin, cmax) << 5);
-        }
-        const uint32_t below = (1u << j) - 1u;  // j < 32 always
-        // closed form of partition_shuffle (blas.rs:168-182) on the current order of every segment at once
-        auto do_shuffle = [&](uint32_t a, uint32_t b) -> uint32_t {
-            const bool L = act && (((pay >> (5 + 3 * a)) & 7u) < b);
-            const uint32_t Lm = (__ballot_sync(FULL_MASK, L) >> s) & nmask;
-            const uint32_t Rm = ~Lm & nmask;
-            const uint32_t RF = __popc(Rm & below), LF = j - RF;
-            const uint32_t nL = __popc(Lm);
-            const uint32_t LBB = (j + 2 < 32) ? __popc(Lm >> (j + 2)) : 0u;
-            const bool pred = act && (j + 2 <= n) && (LBB >= RF);
-            const uint32_t f = __popc((__ballot_sync(FULL_MASK, pred) >> s) & nmask);
-            const uint32_t pivot = nL - ((Lm >> f) & 1u);
-            const uint32_t LB = nL - LF - (L ? 1u : 0u);
-            if (act) {
-                if (L) sm_tab[s + n - 1 - LB] = (uint8_t)j;
-                else sm_tab[s + RF] = (uint8_t)j;
-            }
-            __syncwarp();
-            if (act) {
-                uint32_t dest;
-                if (j < f) dest = L ? j : (RF == 0 ? n - 1 : (uint32_t)sm_tab[s + n - RF] - 1u);
-                else if (j == f) dest = pivot;
-                else dest = L ? (uint32_t)sm_tab[s + LB] : j - 1;
-                sm_pay[s + dest] = (uint16_t)pay;
-            }
-            __syncwarp();
-            if (act) pay = sm_pay[lane];
-            return pivot;
-        };
-        for (uint32_t c = 0; c < 21; ++c) {
-            const uint32_t pivot = do_shuffle(c / 7, c % 7 + 1);
-            const uint32_t up = __shfl_sync(FULL_MASK, pay, act ? ((s + pivot) & 31u) : lane);
-            if (act && j == 0) { sg.cu[c * 32 + s] = (uint8_t)(up & 31u); sg.cp[c * 32 + s] = (uint8_t)pivot; }
-        }
-        __syncwarp();
-        // candidate costs: lane j of a segment takes candidates j, j+n, ... (blas.rs:149-155): exact boxes of
-        // {L}\{u} and {R}+{u}; sm_pay holds the order after shuffle 20, which is all a box needs (a set)
-        uint32_t best_key = 0xFFFFFFFFu, best_c = 0xFFu;
-        const uint32_t nmax = __reduce_max_sync(FULL_MASK, act ? n : 0u);
-        for (uint32_t c = j;; c += n) {
-            const bool valid = act && c < 21;
-            if (!__any_sync(FULL_MASK, valid)) break;
-            const uint32_t cs = valid ? c : 0u;
-            const uint32_t ca = cs / 7, cb = cs % 7 + 1;
-            const uint32_t my_u = valid ? (uint32_t)sg.cu[cs * 32 + s] : 0xFFu;
-            const uint32_t my_piv = valid ? (uint32_t)sg.cp[cs * 32 + s] : 0u;
-            float Lb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-            float Rb[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
-            for (uint32_t tt = 0; tt < nmax; ++tt) {
-                if (valid && tt < n) {
-                    const uint32_t p = sm_pay[s + tt];
-                    const uint32_t et = p & 31u;
-                    const bool left = (((p >> (5 + 3 * ca)) & 7u) < cb) && (et != my_u);
-                    const float x0 = sm_box[0][et], x1 = sm_box[1][et], x2 = sm_box[2][et];
-                    const float x3 = sm_box[3][et], x4 = sm_box[4][et], x5 = sm_box[5][et];
-                    if (left) {
-                        Lb[0] = fminf(Lb[0], x0); Lb[1] = fminf(Lb[1], x1); Lb[2] = fminf(Lb[2], x2);
-                        Lb[3] = fmaxf(Lb[3], x3); Lb[4] = fmaxf(Lb[4], x4); Lb[5] = fmaxf(Lb[5], x5);
-                    } else {
-                        Rb[0] = fminf(Rb[0], x0); Rb[1] = fminf(Rb[1], x1); Rb[2] = fminf(Rb[2], x2);
-                        Rb[3] = fmaxf(Rb[3], x3); Rb[4] = fmaxf(Rb[4], x4); Rb[5] = fmaxf(Rb[5], x5);
-                    }
-                }
-            }
-            const float cost = sah_cost(Lb, Rb, my_piv, n - my_piv);
-            // strict <, first candidate wins, NaN/inf never win (blas.rs:140,156); c ascends per lane
-            const uint32_t key = (valid && cost < 3.402823466e+38f) ? __float_as_uint(cost) : 0xFFFFFFFFu;
-            if (key < best_key) { best_key = key; best_c = c; }
-        }
-        const uint32_t mk = __reduce_min_sync(segmask, best_key);
-        const uint32_t win = __reduce_min_sync(segmask, (best_key == mk) ? best_c : 0xFFu);
-        const bool degen = act && (mk == 0xFFFFFFFFu);
-        if (degen) {
-            if (j == 0) atomicOr(&st->err, DERR_DEGENERATE);
-            live = false;
-        }
-        const bool go = act && !degen;
-        const uint32_t wc = go ? win : 0u;
-        const uint32_t p = go ? (uint32_t)sg.cp[wc * 32 + s] : 0u;  // recorded pivot (blas.rs:159,165)
-        do_shuffle(wc / 7, go ? wc % 7 + 1 : 0u);                   // blas.rs:164 (b = 0: no lane is L, order kept)
-        if (go) {
-            if (j == 0) {
-                emit_rec(recs, 2 * (abs_start + p) + 1, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
-                if (p <= 3) A[abs_start] = leftrun + 1;
-            }
-            pstart = abs_start;
-            pleftrun = leftrun;
-            if (j < p) { n = p; leftrun = leftrun + 1; fl = base_fl; }
-            else { s = s + p; n = n - p; leftrun = 0; fl = TF_RIGHT | base_fl; }
-        }
-        __syncwarp();
-    }
-    if (lane < t.n) ids[t.start + lane] = sm_gid[pay & 31u];
-}
-
 __global__ void __launch_bounds__(256, 4) k_t3(Queues Q, uint32_t* ids,
                                                const float4* __restrict__ cent, const float4* __restrict__ box,
                                                uint4* recs, uint32_t* A, BuildState* st) {
@@ -607,18 +404,9 @@ __global__ void __launch_bounds__(256, 4) k_t3(Queues Q, uint32_t* ids,
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t n_tasks = st->t3_count;
     const T3Smem sm{s_box[w], s_cent[w], s_gid[w], s_tab[w], s_pay[w]};
-#if T3_SEG
-    __shared__ uint8_t s_cu[8][21 * 32];
-    __shared__ uint8_t s_cp[8][21 * 32];
-    const T3SegSmem sg{s_cu[w], s_cp[w]};
-#endif
     for (uint32_t ti = blockIdx.x * 8 + w; ti < n_tasks; ti += gridDim.x * 8) {
         const Task t = tasks[ti];
-#if T3_SEG
-        t3_subtree_seg(t, sm, sg, lane, ids, cent, box, recs, A, st);
-#else
         t3_subtree(t, sm, lane, ids, cent, box, recs, A, st, Q);
-#endif
     }
 }
 
@@ -630,7 +418,7 @@ __global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, uint32_t* ids, const flo
                                              const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st) {
     extern __shared__ uint32_t s_t4[];
     const T4Mem<CAP> m{reinterpret_cast<float*>(s_t4) + threadIdx.x, s_t4 + 6 * CAP * BD + threadIdx.x, (uint32_t)BD};
-    const uint32_t n_tasks = min(st->t4_count, Q.t4_soft);
+    const uint32_t n_tasks = min(st->t4_count, Q.t4_cap);
     for (uint32_t ti = blockIdx.x * BD + threadIdx.x; ti < n_tasks; ti += gridDim.x * BD) {
         const Task tk = Q.t4[ti];
         const T4Task t{tk.start, tk.n, tk.leftrun, tk.pstart, tk.pleftrun, tk.flags};
@@ -652,8 +440,7 @@ __global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, uint32_t* ids, const flo
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint32_t epoch, uint32_t start, uint32_t n,
                                            uint32_t leftrun, uint32_t pstart, uint32_t pleftrun, uint32_t flags) {
-    if ((int)n <= T4_MAX && push_t4(Q, st, start, n, leftrun, pstart, pleftrun, flags)) return;
-    if (n > T3_MAX || T23_FUSED) {
+    if (n > T3_MAX) {
         const int tier = n > T2_CAP ? 2 : (n > T2W_CAP ? 1 : 0);
         uint32_t* pending = tier == 2 ? &st->b_pending : (tier == 1 ? &st->q_pending : &st->w_pending);
         uint32_t* tail = tier == 2 ? &st->b_tail : (tier == 1 ? &st->q_tail : &st->w_tail);
@@ -670,6 +457,8 @@ __device__ __forceinline__ void push_child(const Queues& Q, BuildState* st, uint
         d->flags = flags; d->pad = 0;
         __threadfence();
         *(volatile uint32_t*)&d->ready = epoch;
+    } else if ((int)n <= T4_MAX) {
+        push_t4(Q, st, start, n, leftrun, pstart, pleftrun, flags);
     } else {
         const uint32_t idx = atomicAdd(&st->t3_count, 1u);
         if (idx >= Q.t3_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
@@ -1070,16 +859,6 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
     __shared__ uint16_t s_tab[NWB][WCAP];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-#if T23_FUSED
-    // scratch for sub-trees of <= 32 primitives, aliased onto this warp's node scratch (a warp does one or the other):
-    // s_pay[w] (2048 B) = box 768 | cent 384 | gid 128 | pay 64 | tab 32 | cu 672;  s_gid[w] (1024 B) = cp 672
-    static_assert(WCAP == 256, "scratch aliasing below assumes 2048 B of payload and 1024 B of ids per warp");
-    char* const a0 = reinterpret_cast<char*>(&s_pay[w][0][0]);
-    const T3Smem sm3{reinterpret_cast<float (*)[32]>(a0), reinterpret_cast<float (*)[32]>(a0 + 768),
-                     reinterpret_cast<uint32_t*>(a0 + 1152), reinterpret_cast<uint8_t*>(a0 + 1344),
-                     reinterpret_cast<uint16_t*>(a0 + 1280)};
-    const T3SegSmem sg3{reinterpret_cast<uint8_t*>(a0 + 1376), reinterpret_cast<uint8_t*>(&s_gid[w][0])};
-#endif
 
     for (;;) {
         // ---- pop (lane 0) ----
@@ -1098,21 +877,6 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
         const uint32_t start = __shfl_sync(FULL_MASK, t_start, 0), n = __shfl_sync(FULL_MASK, t_n, 0);
         const uint32_t leftrun = __shfl_sync(FULL_MASK, t_leftrun, 0), pstart = __shfl_sync(FULL_MASK, t_pstart, 0);
         const uint32_t pleftrun = __shfl_sync(FULL_MASK, t_pleftrun, 0), tflags = __shfl_sync(FULL_MASK, t_flags, 0);
-#if T23_FUSED
-        if (n <= (uint32_t)T3_MAX) {  // a whole sub-tree of <= 32 primitives
-            Task c;
-            c.start = start; c.n = n; c.leftrun = leftrun; c.pstart = pstart; c.pleftrun = pleftrun; c.flags = tflags;
-            c.ready = 0; c.pad = 0;
-            t3_subtree_seg(c, sm3, sg3, lane, ids, cent, box, recs, A, st);
-            __syncwarp();
-            if (lane == 0) {
-                atomicAdd(&st->t3_inline, 1u);
-                __threadfence();
-                atomicSub(&st->w_pending, 1u);
-            }
-            continue;
-        }
-#endif
         const uint32_t E = (n + 31) >> 5;  // chunks in use, <= EPL
 
         // ---- 1. load, own vertex box, centroid bounds ----
@@ -1801,130 +1565,6 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
     }
 }
 
-// One-tile mode (a level with at most one tile per block, i.e. every mesh up to ~900 K triangles): PA(c), the grid
-// barrier and PB(c) as one function.  The block keeps its tile's flags, ballots and prefix counts in registers across
-// the barrier and prefetches its ids before it, so PB starts with the table gather instead of re-loading and
-// re-scanning the tile, and the tile descriptor is read once per level (`td`), not once per phase: two dependent L2
-// round trips and two block barriers less per shuffle on a path that is a chain of such round trips.
-__device__ __forceinline__ void p_t1_shuffle_one(const T1Args& g, int c, const uint4 td, const bool has_tile,
-                                                 const uint32_t tile, const uint32_t* ids_in, const uint16_t* fl,
-                                                 uint32_t* ids_out, uint16_t* fl_out, uint32_t& gen) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
-    __shared__ uint32_t s_w[T1_THREADS / 32];
-    __shared__ uint32_t s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t node = td.x, start = td.y, n = td.z, lt = td.w, tile_base = tile - lt, j0 = lt * T1_TILE;
-    const uint32_t jw = j0 + warp * (32 * EPT);
-    uint16_t fw[EPT];
-    uint32_t idv[EPT], bal[EPT], LFv[EPT];
-    uint32_t a = 0, b = 0, nL = 0;
-    if (has_tile) {
-        t1_load_flags<EPT>(fl, start, n, j0, fw);
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = jw + i * 32 + lane;
-            idv[i] = (j < n) ? ids_in[start + j] : 0u;
-        }
-        cand_of(g.sc, node, c, a, b);
-        uint32_t Lprev = 0;
-        if (lane == 0 && jw > 0 && jw <= n) Lprev = ((((uint32_t)fl[start + jw - 1] >> (3 * a)) & 7u) < b) ? 1u : 0u;
-        const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
-        const uint32_t nt = (n + T1_TILE - 1) / T1_TILE;
-        uint32_t pre = 0, tot = 0;
-        for (uint32_t t = tid; t < nt; t += T1_THREADS) {
-            const uint32_t v = tl[tile_base + t];
-            tot += v;
-            if (t < lt) pre += v;
-        }
-        pre = __reduce_add_sync(FULL_MASK, pre);
-        tot = __reduce_add_sync(FULL_MASK, tot);
-        if (lane == 0) { s_pre[warp] = pre; s_tot[warp] = tot; }
-        __syncthreads();
-        uint32_t tile_lf = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) { tile_lf += s_pre[w2]; nL += s_tot[w2]; }
-        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
-        uint32_t prev_pred_bit31 = 0;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = jw + i * 32 + lane;
-            bool pred = false;
-            uint32_t Lbit = 0;
-            if (j < n) {
-                Lbit = (bal[i] >> lane) & 1u;
-                const uint32_t LF = LFv[i], RF = j - LF;
-                uint32_t Lnext;
-                if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
-                else Lnext = (j + 1 < n) ? (((((uint32_t)fl[start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
-                const uint32_t LBB = nL - LF - Lbit - Lnext;
-                pred = (j + 2 <= n) && (LBB >= RF);
-                if (Lbit) g.table[start + n - 1 - (nL - LF - 1)] = j;
-                else g.table[start + RF] = j;
-            }
-            const uint32_t pb = __ballot_sync(FULL_MASK, pred);
-            if (j < n && !pred) {
-                bool prev;
-                if (lane > 0) prev = (pb >> (lane - 1)) & 1u;
-                else if (i > 0) prev = prev_pred_bit31 != 0;
-                else if (j == 0) prev = true;
-                else {
-                    const uint32_t LFp = LFv[i] - Lprev, RFp = (j - 1) - LFp;
-                    const uint32_t LBBp = nL - LFp - Lprev - Lbit;
-                    prev = (j + 1 <= n) && (LBBp >= RFp);
-                }
-                if (prev) g.sc[node].sh[c] = make_uint4(nL, j, nL - Lbit, 0);
-            }
-            prev_pred_bit31 = (pb >> 31) & 1u;
-        }
-    }
-    grid_barrier(g.barrier, gen);
-    if (has_tile) {
-        const bool count_next = c < 20;
-        const uint32_t na = (uint32_t)(c + 1) / 7, nb = (uint32_t)(c + 1) % 7 + 1;
-        uint32_t* tl_next = g.tileL + (size_t)(c + 1) * g.tile_stride;
-        const uint4 sh = g.sc[node].sh[c];
-        const uint32_t f = sh.y, pivot = sh.z;
-        uint32_t own_cnt = 0;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = jw + i * 32 + lane;
-            uint32_t dtile = 0xFFFFFFFFu;
-            bool Lnx = false;
-            if (j < n) {
-                const uint32_t Lbit = (bal[i] >> lane) & 1u;
-                const uint32_t LF = LFv[i], RF = j - LF;
-                const uint32_t id = idv[i];
-                uint32_t fwx = fw[i];
-                uint32_t dest;
-                if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : g.table[start + n - RF] - 1u);
-                else if (j == f) {
-                    dest = pivot;
-                    fwx |= 0x8000u;
-                    if (c < 21) { g.sc[node].piv[c] = pivot; g.sc[node].uid[c] = id; }
-                } else dest = Lbit ? g.table[start + (nL - LF - 1)] : j - 1;
-                ids_out[start + dest] = id;
-                fl_out[start + dest] = (uint16_t)fwx;
-                dtile = tile_base + dest / T1_TILE;
-                Lnx = ((fwx >> (3 * na)) & 7u) < nb;
-            }
-            if (count_next) {
-                const bool own = (dtile == tile);
-                own_cnt += __popc(__ballot_sync(FULL_MASK, own && Lnx));
-                uint32_t todo = __ballot_sync(FULL_MASK, dtile != 0xFFFFFFFFu && !own && Lnx);
-                while (todo) {
-                    const uint32_t leader = __ffs(todo) - 1;
-                    const uint32_t ltile = __shfl_sync(FULL_MASK, dtile, leader);
-                    const uint32_t same = __ballot_sync(FULL_MASK, dtile == ltile) & todo;
-                    if (lane == leader) atomicAdd(&tl_next[ltile], (uint32_t)__popc(same));
-                    todo &= ~same;
-                }
-            }
-        }
-        if (count_next && lane == 0 && own_cnt) atomicAdd(&tl_next[tile], own_cnt);
-    }
-}
-
 __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, const uint16_t* fl) {
     constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_bins[3][8][6];
@@ -2126,6 +1766,12 @@ __global__ void __launch_bounds__(1024) k_t1_level0(LevelNode* nodes, BuildState
 
 // The whole grid-wide tier as ONE cooperative persistent kernel: every phase boundary is a grid barrier
 // instead of a kernel launch, and the level loop never returns to the host.  ~52 barriers per level.
+// Measured on B200 (dragon-class, -DBVH_T1_TIMING): every level costs 315-440 us whether it has 426 tiles or 9
+// (390, 379, 389, 385, 440, 385, 362, 367, 355, 314 us for 426, 426, 427, 430, 435, 396, 221, 65, 17, 9 tiles): a phase is
+// ~480 dependent warp-instructions per warp (8 slots per thread) plus a barrier, ~6.5 us, not a matter of bandwidth,
+// of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (commit
+// 3f0c5bd and the two after it): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
+// descriptor read once per level (3.87 ms vs 3.70 ms); barriers restricted to the blocks that own a tile (3.67 vs 3.69).
 __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
     LevelNode* lv[2] = {lv0, lv1};
@@ -2136,17 +1782,16 @@ __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* 
         const uint32_t n_tiles = ld_vol(&g.st->lv_tiles[slot]);
         const bool scanned = ld_vol(&g.st->lv_maxtiles[slot]) > 512u;
         if (n_nodes == 0) break;
+#ifdef BVH_T1_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 0 && level < 100) {
+            g_t1_blk[0][900 + level] = gtimer();  // level start; [1][900 + level] = {nodes, tiles}
+            g_t1_blk[1][900 + level] = ((unsigned long long)n_nodes << 32) | n_tiles;
+        }
+#endif
         g.nodes = lv[slot];
         g.n_nodes = n_nodes;
         g.n_tiles = n_tiles;
         T1_PHASE(0, p_t1_init(g));
-#if T1_ONE_TILE
-        const bool one_tile = !scanned && n_tiles <= gridDim.x;
-#else
-        const bool one_tile = false;
-#endif
-        const bool has_tile = one_tile && blockIdx.x < n_tiles;
-        const uint4 my_td = has_tile ? g.tile_desc[blockIdx.x] : make_uint4(0, 0, 0, 0);
         T1_PHASE(1, p_t1_bounds(g));
         T1_PHASE(2, p_t1_flags(g));
         for (int c = 0; c < 22; ++c) {
@@ -2159,11 +1804,6 @@ __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* 
                 T1_PHASE(4, p_t1_select(g));
                 T1_PHASE(5, p_t1_count_final(g, fl_in));
             }
-            if (one_tile) {
-                p_t1_shuffle_one(g, c, my_td, has_tile, blockIdx.x, ids_in, fl_in, ids_out, fl_out, gen);
-                grid_barrier(g.barrier, gen);
-                continue;
-            }
             if (scanned) T1_PHASE(6, p_t1_tilescan(g, c));
             T1_PHASE(7, p_t1_table(g, c, fl_in, scanned));
             T1_PHASE(8, p_t1_scatter(g, c, ids_in, fl_in, ids_out, fl_out));
@@ -2172,6 +1812,9 @@ __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* 
         T1_PHASE(9, p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch));
         T1_PHASE(10, if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot));
         slot = next;
+#ifdef BVH_T1_TIMING
+        if (blockIdx.x == 0 && threadIdx.x == 0 && level < 100) g_t1_blk[0][900 + level + 1] = gtimer();
+#endif
     }
 }
 
@@ -2449,20 +2092,11 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t max_tiles = N / T1_TILE + max_large + 2;
     const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
     const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
-    // nodes with 33..256 primitives (typically ~N/28); when fused, also the sub-trees of <= 32 (disjoint ranges: <= N)
-    const uint32_t qw_cap = T23_FUSED ? N / 4 + N + 2 * NM + 4096 : N / 4 + NM + 4096;
+    const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
     // sub-trees of <= 32 primitives: thread tasks (<= T4_MAX) and warp tasks (the rest).  Sibling ranges are disjoint,
     // but with 0 < T4_MAX < 32 the warp kernel re-posts children of its own tasks, hence two full-size lists.
-    // (sibling ranges are disjoint; the thread tier may refuse tasks, so the warp list is sized for all of them)
-    const uint32_t t3_cap = T23_FUSED ? 16u : N + NM + 16;
+    const uint32_t t3_cap = (T4_MAX >= T3_MAX) ? 16u : (T4_MAX > 0 ? N / (uint32_t)(T4_MAX + 1) + NM + 16 : N + NM + 16);
     const uint32_t t4_cap = (T4_MAX > 0) ? N + NM + 16 : 16u;
-    // thread tier: whole waves only.  ~N/11 sub-trees of <= 16 primitives are expected; a fractional last wave below
-    // 3/4 goes back to the warp tier (dragon-class: 77 900 tasks = 1.17 waves of 66 304).
-    const uint32_t t4_wave = (uint32_t)ctx->sm_count * (uint32_t)T4_THREADS;
-    uint32_t t4_soft = t4_wave * (uint32_t)((N / 11 + t4_wave / 4) / t4_wave);
-    if (t4_soft < t4_wave) t4_soft = t4_wave;
-    if (t4_soft > t4_cap) t4_soft = t4_cap;
-    if (const char* e = getenv("BVH_CUDA_T4_SOFT")) t4_soft = (uint32_t)strtoul(e, nullptr, 10) < t4_cap ? (uint32_t)strtoul(e, nullptr, 10) : t4_cap;
     const uint32_t scan_n = N + 1;
     const uint32_t scan_blocks = (scan_n + SCAN_TILE - 1) / SCAN_TILE;
     const uint32_t mscan_n = NM + 1;
@@ -2529,7 +2163,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
     const bool prof = ctx->profiling;
     if (prof) cudaEventRecord(ctx->ev[0], stream);
-    Queues Q{qb, q, qw, t3, t4, qb_cap, q_cap, qw_cap, t3_cap, t4_cap, t4_soft};
+    Queues Q{qb, q, qw, t3, t4, qb_cap, q_cap, qw_cap, t3_cap, t4_cap};
     k_init_state<<<1, 32, 0, stream>>>(st);
     if (d_mesh_info) k_mesh_table<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(d_mesh_info, NM, 3 * N, tbase, voff, st);
     else k_single_mesh_table<<<1, 32, 0, stream>>>(N, tbase, voff);
@@ -2582,7 +2216,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     }
     if (prof) cudaEventRecord(ctx->ev[3], stream);
     // ---- T3: one warp per small sub-tree ----
-    if (!T23_FUSED && T4_MAX < T3_MAX) {
+    if (T4_MAX < T3_MAX) {
         const int blocks = ctx->sm_count * 8;
         k_t3<<<blocks, 256, 0, stream>>>(Q, ids0, cent, box, recs, A, st);
         launches++;
@@ -2636,8 +2270,8 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.big_block_tasks = hs->t2b_done;
     stats.block_tasks = hs->t2_done;
     stats.warp_node_tasks = hs->t2w_done;
-    stats.warp_tasks = hs->t3_count + hs->t3_inline;
-    stats.thread_tasks = hs->t4_count < t4_soft ? hs->t4_count : t4_soft;
+    stats.warp_tasks = hs->t3_count;
+    stats.thread_tasks = hs->t4_count;
     stats.kernel_launches = launches;
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
