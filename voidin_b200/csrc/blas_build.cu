@@ -33,12 +33,21 @@ constexpr int T3_MAX = 32;
 constexpr int T4_MAX = T4_MAX_V;
 static_assert(T4_MAX == 0 || T4_MAX == 16 || T4_MAX == 32, "T4_MAX_V must be 0, 16 or 32");
 // Other forms of the small-sub-tree tiers that were built, verified bit-exact and measured slower on B200 (dragon-class,
-// commit 3f0c5bd and its parent): all nodes of one depth as lane segments of one warp (1.42 ms vs 1.34 ms: SAH sub-trees are
+// commit ac13e1f): all nodes of one depth as lane segments of one warp (1.42 ms vs 1.34 ms: SAH sub-trees are
 // deep, not bushy, and a pass costs as much as a node visit); sub-trees through k_t2w's queue (2.94 ms vs 2.46 ms for the
 // two tiers); thread tier limited to whole waves of sm_count x T4_THREADS tasks (1.22 ms vs 1.24 ms).
 constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
 constexpr int T4_THREADS = (T4_CAP == 32) ? 224 : 448;  // 8 words per slot per thread: 229 376 B of shared memory per block
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
+// 1: grid tier PA publishes the boundary element from nL and three flags (one thread per node) and writes only the
+// table entries that can be looked up; 0: every thread evaluates the front-examined predicate
+#ifndef T1_CLOSED_F
+#define T1_CLOSED_F 1
+#endif
+// 1: the grid tier picks the tile size per level (p_t1_nextlevel); 0: always T1_TILE
+#ifndef T1_VAR_TILE
+#define T1_VAR_TILE 1
+#endif
 #ifndef T2_CAP_V
 #define T2_CAP_V 2048
 #endif
@@ -49,7 +58,7 @@ constexpr int T2_THREADS = 256;
 #endif
 constexpr int T2B_CAP = 16384;  // big-block tier: 2049..16384 (1024 threads, one block per SM)
 constexpr int T2B_THREADS = 1024;
-constexpr int T1_TILE = 2048;
+constexpr int T1_TILE = 2048;  // largest tile (8 slots per thread); levels that fit the grid with smaller tiles use them
 constexpr int T1_THREADS = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
@@ -82,6 +91,7 @@ struct BuildState {
     uint32_t lv_count[2];
     uint32_t lv_tiles[2];
     uint32_t lv_maxtiles[2];
+    uint32_t lv_ept[2];  // slots per thread of the level's tiles (tile = T1_THREADS * ept slots)
     uint32_t interior_total;
     unsigned long long sum_interior;
     uint32_t t2_done;
@@ -1138,6 +1148,7 @@ struct T1Args {
     const LevelNode* nodes;
     NodeScratch* sc;
     uint32_t n_nodes, n_tiles;
+    uint32_t ept, tile_sz;  // this level: slots per thread (1, 2, 4 or 8) and slots per tile (T1_THREADS * ept)
     uint32_t* ids0;
     uint32_t* ids1;
     uint16_t* fl0;
@@ -1209,7 +1220,7 @@ __device__ __forceinline__ void p_t1_init(const T1Args& g) {
     for (uint32_t node = blockIdx.x; node < g.n_nodes; node += gridDim.x) {
         NodeScratch* s = g.sc + node;
         const LevelNode nd = g.nodes[node];
-        const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
+        const uint32_t nt = (nd.n + g.tile_sz - 1) / g.tile_sz;
         const uint32_t tid = threadIdx.x;
         if (tid < 12) s->bnd[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         if (tid == 22) s->best = 0xFFFFFFFFu;
@@ -1221,18 +1232,19 @@ __device__ __forceinline__ void p_t1_init(const T1Args& g) {
 }
 
 // L1: per tile — vertex box and centroid bounds of the node (blas.rs:87-88,117-123,142).
+template <int EPT>
 __device__ __forceinline__ void p_t1_bounds(const T1Args& g) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_red[T1_THREADS / 32][12];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
-        const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t j0 = td.w * g.tile_sz;
         float acc[12] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f, 1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
+            if (i >= EPT) break;
             const uint32_t j = j0 + i * T1_THREADS + tid;
             if (j < nd.n) {
                 const uint32_t id = g.ids0[nd.start + j];
@@ -1264,15 +1276,15 @@ __device__ __forceinline__ void p_t1_bounds(const T1Args& g) {
 }
 
 // L2: per tile — plane counts of every primitive, and the tile's L count for candidate 0 (x axis, b = 1).
+template <int EPT>
 __device__ __forceinline__ void p_t1_flags(const T1Args& g) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
-        const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t j0 = td.w * g.tile_sz;
         float cmin[3], cmax[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { cmin[c] = o2f(g.sc[node].bnd[6 + c]); cmax[c] = o2f(g.sc[node].bnd[9 + c]); }
@@ -1289,6 +1301,7 @@ __device__ __forceinline__ void p_t1_flags(const T1Args& g) {
         }
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
+            if (i >= EPT) break;
             const uint32_t j = j0 + i * T1_THREADS + tid;
             bool L = false;
             if (j < nd.n) {
@@ -1319,20 +1332,21 @@ __device__ __forceinline__ void p_t1_flags(const T1Args& g) {
 }
 
 // Per-tile L count for the final (winning) candidate, whose identity is only known after select.
+template <int EPT>
 __device__ __forceinline__ void p_t1_count_final(const T1Args& g, const uint16_t* fl) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
-        const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t j0 = td.w * g.tile_sz;
         uint32_t a, b;
         cand_of(g.sc, node, 21, a, b);
         uint32_t cnt = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
+            if (i >= EPT) break;
             const uint32_t j = j0 + i * T1_THREADS + tid;
             const bool L = (j < nd.n) && ((((uint32_t)fl[nd.start + j] >> (3 * a)) & 7u) < b);
             cnt += __popc(__ballot_sync(FULL_MASK, L));
@@ -1355,7 +1369,7 @@ __device__ __forceinline__ void p_t1_tilescan(const T1Args& g, int c) {
     const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t node = gw; node < g.n_nodes; node += nw) {
         const LevelNode nd = g.nodes[node];
-        const uint32_t nt = (nd.n + T1_TILE - 1) / T1_TILE;
+        const uint32_t nt = (nd.n + g.tile_sz - 1) / g.tile_sz;
         uint32_t carry = 0;
         for (uint32_t base = 0; base < nt; base += 32) {
             const uint32_t i = base + lane;
@@ -1376,23 +1390,26 @@ __device__ __forceinline__ void p_t1_tilescan(const T1Args& g, int c) {
 // Ballots + per-element #L-before (LF) of one tile.  Layout: j = j0 + warp*256 + i*32 + lane.
 // Issues the tile's flag loads early (before anything that waits on other loads or barriers).
 template <int EPT>
-__device__ __forceinline__ void t1_load_flags(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint16_t* fw) {
+__device__ __forceinline__ void t1_load_flags(const uint16_t* fl, uint32_t start, uint32_t n, uint32_t j0, uint16_t* fw,
+                                              const uint32_t ept) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-        const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+        if (i >= (int)ept) break;
+        const uint32_t j = j0 + warp * (32 * ept) + i * 32 + lane;
         fw[i] = (j < n) ? fl[start + j] : (uint16_t)0;
     }
 }
 
 template <int EPT>
 __device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, uint32_t b, uint32_t tile_lf, uint32_t* s_w,
-                                          uint32_t* bal, uint32_t* LFv, const uint16_t* fw) {
+                                          uint32_t* bal, uint32_t* LFv, const uint16_t* fw, const uint32_t ept) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t cnt = 0;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-        const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+        if (i >= (int)ept) break;
+        const uint32_t j = j0 + warp * (32 * ept) + i * 32 + lane;
         const bool L = (j < n) && ((((uint32_t)fw[i] >> (3 * a)) & 7u) < b);
         bal[i] = __ballot_sync(FULL_MASK, L);
         cnt += __popc(bal[i]);
@@ -1404,6 +1421,7 @@ __device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, u
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
+        if (i >= (int)ept) break;
         LFv[i] = running + __popc(bal[i] & lt_mask);
         running += __popc(bal[i]);
     }
@@ -1413,29 +1431,27 @@ __device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, u
 // PA(c): per tile — tile prefix, rank->position table (Appendix B), and the boundary element f: the first
 // element that the front cursor does not examine.  "front-examined" is a prefix of the node, so exactly one
 // thread of the whole grid sees the true->false transition; it publishes {nL, f, pivot} for the scatter phase.
+template <int EPT>
 __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_t* fl, bool scanned) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
     __shared__ uint32_t s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
-        const uint32_t node = td.x, start = td.y, n = td.z, lt = td.w, tile_base = tile - lt, j0 = lt * T1_TILE;
+        constexpr uint32_t ept = EPT;
+        const uint32_t node = td.x, start = td.y, n = td.z, lt = td.w, tile_base = tile - lt, j0 = lt * g.tile_sz;
         uint16_t fw[EPT];
-        t1_load_flags<EPT>(fl, start, n, j0, fw);
+        t1_load_flags<EPT>(fl, start, n, j0, fw, ept);
         uint32_t a, b;
         cand_of(g.sc, node, c, a, b);
-        // flag of the element just before this warp's first slot (needed for the transition test)
-        const uint32_t jw = j0 + warp * (32 * EPT);
-        uint32_t Lprev = 0;
-        if (lane == 0 && jw > 0 && jw <= n) Lprev = ((((uint32_t)fl[start + jw - 1] >> (3 * a)) & 7u) < b) ? 1u : 0u;
+        const uint32_t jw = j0 + warp * (32 * ept);
         uint32_t tile_lf, nL;
         if (scanned) {
             tile_lf = g.tileLF[tile];
             nL = g.sc[node].nL[c];
         } else {
-            const uint32_t nt = (n + T1_TILE - 1) / T1_TILE;
+            const uint32_t nt = (n + g.tile_sz - 1) / g.tile_sz;
             uint32_t pre = 0, tot = 0;
             for (uint32_t t = tid; t < nt; t += T1_THREADS) {
                 const uint32_t v = tl[tile_base + t];
@@ -1451,11 +1467,43 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
             for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) { tile_lf += s_pre[w2]; nL += s_tot[w2]; }
             if (tid == 0) g.tileLF[tile] = tile_lf;
         }
+#if T1_CLOSED_F
+        // The boundary element needs no search: pred(j) <=> j + 2 <= n && j + L(j) + L(j+1) <= nL (the #L-before terms
+        // cancel), true for every j <= nL - 2 and false from nL + 1 on, so f is one of nL-1, nL, nL+1 and follows from nL
+        // and three flags.  One thread per node publishes {nL, f, pivot}; nobody else evaluates pred.
+        if (lt == 0 && tid == 0) {
+            auto l_at = [&](uint32_t j) -> uint32_t {
+                return (j < n && ((((uint32_t)fl[start + j] >> (3 * a)) & 7u) < b)) ? 1u : 0u;
+            };
+            const uint32_t l0 = nL ? l_at(nL - 1) : 0u, l1 = l_at(nL), l2 = l_at(nL + 1);
+            uint32_t f, lf;
+            if (nL >= 1 && !(nL + 1 <= n && l0 + l1 <= 1)) { f = nL - 1; lf = l0; }
+            else if (!(nL + 2 <= n && l1 + l2 == 0)) { f = nL; lf = l1; }
+            else { f = nL + 1; lf = l2; }
+            g.sc[node].sh[c] = make_uint4(nL, f, nL - lf, 0);
+        }
         uint32_t bal[EPT], LFv[EPT];
-        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw);
+        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw, ept);
+        // Only front R's (j < f) and back L's (j > f) are ever looked up; with f in [nL-1, nL+1] that is j <= nL / j >= nL.
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const uint32_t j = jw + i * 32 + lane;
+            if (j < n) {
+                const uint32_t LF = LFv[i];
+                if ((bal[i] >> lane) & 1u) { if (j >= nL) g.table[start + n - 1 - (nL - LF - 1)] = j; }
+                else if (j <= nL) g.table[start + (j - LF)] = j;
+            }
+        }
+#else
+        // flag of the element just before this warp's first slot (needed for the transition test)
+        uint32_t Lprev = 0;
+        if (lane == 0 && jw > 0 && jw <= n) Lprev = ((((uint32_t)fl[start + jw - 1] >> (3 * a)) & 7u) < b) ? 1u : 0u;
+        uint32_t bal[EPT], LFv[EPT];
+        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw, ept);
         uint32_t prev_pred_bit31 = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
+            if (i >= (int)ept) break;
             const uint32_t j = jw + i * 32 + lane;
             bool pred = false;
             uint32_t Lbit = 0;
@@ -1464,7 +1512,7 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
                 const uint32_t LF = LFv[i], RF = j - LF;
                 uint32_t Lnext;
                 if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                else if (i + 1 < EPT) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
+                else if (i + 1 < (int)ept) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
                 else Lnext = (j + 1 < n) ? (((((uint32_t)fl[start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
                 const uint32_t LBB = nL - LF - Lbit - Lnext;
                 pred = (j + 2 <= n) && (LBB >= RF);
@@ -1487,15 +1535,16 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
             }
             prev_pred_bit31 = (pb >> 31) & 1u;
         }
+#endif
         __syncthreads();
     }
 }
 
 // PB(c): per tile — destinations and scatter into the other buffer; also accumulates, per destination tile,
 // the L count of the NEXT candidate (so shuffle c+1 needs no separate counting pass).
+template <int EPT>
 __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint32_t* ids_in, const uint16_t* fl,
                                              uint32_t* ids_out, uint16_t* fl_out) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_w[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool count_next = c < 20;  // candidates 1..20 are known in advance; the final one is not
@@ -1505,14 +1554,17 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
-        const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t j0 = td.w * g.tile_sz;
         const uint32_t n = nd.n;
+        constexpr uint32_t ept = EPT;
+        const uint32_t tshift = 31 - __clz(g.tile_sz);  // tiles are powers of two
         uint16_t fwv[EPT];
         uint32_t idv[EPT];
-        t1_load_flags<EPT>(fl, nd.start, n, j0, fwv);
+        t1_load_flags<EPT>(fl, nd.start, n, j0, fwv, ept);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            if (i >= (int)ept) break;
+            const uint32_t j = j0 + warp * (32 * ept) + i * 32 + lane;
             idv[i] = (j < n) ? ids_in[nd.start + j] : 0u;
         }
         uint32_t a, b;
@@ -1520,11 +1572,12 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
         const uint4 sh = g.sc[node].sh[c];
         const uint32_t nL = sh.x, f = sh.y, pivot = sh.z;
         uint32_t bal[EPT], LFv[EPT];
-        t1_prefix<EPT>(n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv);
+        t1_prefix<EPT>(n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv, ept);
         uint32_t own_cnt = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
-            const uint32_t j = j0 + warp * (32 * EPT) + i * 32 + lane;
+            if (i >= (int)ept) break;
+            const uint32_t j = j0 + warp * (32 * ept) + i * 32 + lane;
             uint32_t dtile = 0xFFFFFFFFu;
             bool Lnx = false;
             if (j < n) {
@@ -1541,7 +1594,7 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
                 } else dest = Lbit ? g.table[nd.start + (nL - LF - 1)] : j - 1;
                 ids_out[nd.start + dest] = id;
                 fl_out[nd.start + dest] = (uint16_t)fw;
-                dtile = nd.tile_base + dest / T1_TILE;
+                dtile = nd.tile_base + (dest >> tshift);
                 Lnx = ((fw >> (3 * na)) & 7u) < nb;
             }
             if (count_next) {
@@ -1565,15 +1618,15 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
     }
 }
 
+template <int EPT>
 __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, const uint16_t* fl) {
-    constexpr int EPT = T1_TILE / T1_THREADS;
     __shared__ uint32_t s_bins[3][8][6];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         const uint4 td = g.tile_desc[tile];
         const uint32_t node = td.x;
         struct { uint32_t start, n, tile_base; } nd = {td.y, td.z, tile - td.w};
-        const uint32_t j0 = td.w * T1_TILE;
+        const uint32_t j0 = td.w * g.tile_sz;
         if (tid < 144) (&s_bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         __syncthreads();
         float lo[EPT][3], hi[EPT][3];
@@ -1601,6 +1654,7 @@ __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, 
                 bool any = false;
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
+                    if (i >= EPT) break;
                     const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
                     if (in) {
                         any = true;
@@ -1725,19 +1779,42 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
     }
 }
 
-// One block: tile_base prefix of the next level's node list; decides whether the level needs the tile scan.
-__device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other, bool count_level = true) {
+// One block: picks the level's tile size, then the tile_base prefix of its node list; decides whether the level needs
+// the tile scan.  Tile size: a phase is a fixed chain of ~60 dependent instructions per slot a thread owns, so a level
+// whose nodes fit the grid with fewer slots per thread (256-, 512- or 1024-slot tiles) takes them.
+__device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st, int slot, int other, uint32_t grid_blocks,
+                                               bool count_level = true) {
     __shared__ uint32_t s_part[1024];
     __shared__ uint32_t s_max;
+    __shared__ uint32_t s_tot[4];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t n = ld_vol(&st->lv_count[slot]);
     const uint32_t per = (n + nt - 1) / nt;
     const uint32_t b = min(n, tid * per), e = min(n, b + per);
     if (tid == 0) s_max = 0;
+    if (tid < 4) s_tot[tid] = 0;
     __syncthreads();
+    {
+        uint32_t t[4] = {0, 0, 0, 0};
+        for (uint32_t i = b; i < e; ++i) {
+            const uint32_t nn = nodes[i].n;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] += (nn + (T1_THREADS << k) - 1) / (T1_THREADS << k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k]) atomicAdd(&s_tot[k], t[k]);
+    }
+    __syncthreads();
+    uint32_t lg = 3;
+#if T1_VAR_TILE
+    for (int k = 2; k >= 0; --k)
+        if (s_tot[k] <= grid_blocks) lg = (uint32_t)k;
+#endif
+    const uint32_t ts = (uint32_t)T1_THREADS << lg;
     uint32_t sum = 0, mx = 0;
     for (uint32_t i = b; i < e; ++i) {
-        const uint32_t t = (nodes[i].n + T1_TILE - 1) / T1_TILE;
+        const uint32_t t = (nodes[i].n + ts - 1) / ts;
         sum += t;
         mx = max(mx, t);
     }
@@ -1749,6 +1826,7 @@ __device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st,
         for (uint32_t i = 0; i < nt; ++i) { const uint32_t v = s_part[i]; s_part[i] = acc; acc += v; }
         st->lv_tiles[slot] = acc;
         st->lv_maxtiles[slot] = s_max;
+        st->lv_ept[slot] = 1u << lg;
         st->lv_count[other] = 0;
         if (count_level) st->levels_done += 1;
     }
@@ -1756,21 +1834,46 @@ __device__ __forceinline__ void p_t1_nextlevel(LevelNode* nodes, BuildState* st,
     uint32_t acc = s_part[tid];
     for (uint32_t i = b; i < e; ++i) {
         nodes[i].tile_base = acc;
-        acc += (nodes[i].n + T1_TILE - 1) / T1_TILE;
+        acc += (nodes[i].n + ts - 1) / ts;
     }
     __syncthreads();
 }
 
 // Tile prefix of the root level (one block).
-__global__ void __launch_bounds__(1024) k_t1_level0(LevelNode* nodes, BuildState* st) { p_t1_nextlevel(nodes, st, 0, 1, false); }
+__global__ void __launch_bounds__(1024) k_t1_level0(LevelNode* nodes, BuildState* st, uint32_t grid_blocks) {
+    p_t1_nextlevel(nodes, st, 0, 1, grid_blocks, false);
+}
+
+// All shuffles of one level with EPT slots per thread (tile = T1_THREADS * EPT slots).
+template <int EPT>
+__device__ __forceinline__ void t1_level(const T1Args& g, const bool scanned, uint32_t& gen, const uint32_t level) {
+    (void)level;
+    T1_PHASE(0, p_t1_init(g));
+    T1_PHASE(1, p_t1_bounds<EPT>(g));
+    T1_PHASE(2, p_t1_flags<EPT>(g));
+    for (int c = 0; c < 22; ++c) {
+        const uint32_t* ids_in = (c & 1) ? g.ids1 : g.ids0;
+        uint32_t* ids_out = (c & 1) ? g.ids0 : g.ids1;
+        const uint16_t* fl_in = (c & 1) ? g.fl1 : g.fl0;
+        uint16_t* fl_out = (c & 1) ? g.fl0 : g.fl1;
+        if (c == 21) {
+            T1_PHASE(3, p_t1_bins<EPT>(g, ids_in, fl_in));
+            T1_PHASE(4, p_t1_select(g));
+            T1_PHASE(5, p_t1_count_final<EPT>(g, fl_in));
+        }
+        if (scanned) T1_PHASE(6, p_t1_tilescan(g, c));
+        T1_PHASE(7, p_t1_table<EPT>(g, c, fl_in, scanned));
+        T1_PHASE(8, p_t1_scatter<EPT>(g, c, ids_in, fl_in, ids_out, fl_out));
+    }
+}
 
 // The whole grid-wide tier as ONE cooperative persistent kernel: every phase boundary is a grid barrier
 // instead of a kernel launch, and the level loop never returns to the host.  ~52 barriers per level.
 // Measured on B200 (dragon-class, -DBVH_T1_TIMING): every level costs 315-440 us whether it has 426 tiles or 9
 // (390, 379, 389, 385, 440, 385, 362, 367, 355, 314 us for 426, 426, 427, 430, 435, 396, 221, 65, 17, 9 tiles): a phase is
 // ~480 dependent warp-instructions per warp (8 slots per thread) plus a barrier, ~6.5 us, not a matter of bandwidth,
-// of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (commit
-// 3f0c5bd and the two after it): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
+// of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (first form in
+// commit ac13e1f): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
 // descriptor read once per level (3.87 ms vs 3.70 ms); barriers restricted to the blocks that own a tile (3.67 vs 3.69).
 __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
@@ -1782,6 +1885,8 @@ __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* 
         const uint32_t n_tiles = ld_vol(&g.st->lv_tiles[slot]);
         const bool scanned = ld_vol(&g.st->lv_maxtiles[slot]) > 512u;
         if (n_nodes == 0) break;
+        g.ept = ld_vol(&g.st->lv_ept[slot]);
+        g.tile_sz = (uint32_t)T1_THREADS * g.ept;
 #ifdef BVH_T1_TIMING
         if (blockIdx.x == 0 && threadIdx.x == 0 && level < 100) {
             g_t1_blk[0][900 + level] = gtimer();  // level start; [1][900 + level] = {nodes, tiles}
@@ -1791,26 +1896,15 @@ __global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* 
         g.nodes = lv[slot];
         g.n_nodes = n_nodes;
         g.n_tiles = n_tiles;
-        T1_PHASE(0, p_t1_init(g));
-        T1_PHASE(1, p_t1_bounds(g));
-        T1_PHASE(2, p_t1_flags(g));
-        for (int c = 0; c < 22; ++c) {
-            const uint32_t* ids_in = (c & 1) ? g.ids1 : g.ids0;
-            uint32_t* ids_out = (c & 1) ? g.ids0 : g.ids1;
-            const uint16_t* fl_in = (c & 1) ? g.fl1 : g.fl0;
-            uint16_t* fl_out = (c & 1) ? g.fl0 : g.fl1;
-            if (c == 21) {
-                T1_PHASE(3, p_t1_bins(g, ids_in, fl_in));
-                T1_PHASE(4, p_t1_select(g));
-                T1_PHASE(5, p_t1_count_final(g, fl_in));
-            }
-            if (scanned) T1_PHASE(6, p_t1_tilescan(g, c));
-            T1_PHASE(7, p_t1_table(g, c, fl_in, scanned));
-            T1_PHASE(8, p_t1_scatter(g, c, ids_in, fl_in, ids_out, fl_out));
+        switch (g.ept) {
+            case 1: t1_level<1>(g, scanned, gen, level); break;
+            case 2: t1_level<2>(g, scanned, gen, level); break;
+            case 4: t1_level<4>(g, scanned, gen, level); break;
+            default: t1_level<8>(g, scanned, gen, level); break;
         }
         const int next = slot ^ 1;
         T1_PHASE(9, p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch));
-        T1_PHASE(10, if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot));
+        T1_PHASE(10, if (blockIdx.x == 0) p_t1_nextlevel(lv[next], g.st, next, slot, gridDim.x));
         slot = next;
 #ifdef BVH_T1_TIMING
         if (blockIdx.x == 0 && threadIdx.x == 0 && level < 100) g_t1_blk[0][900 + level + 1] = gtimer();
@@ -2089,7 +2183,8 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t N = (uint32_t)n_tris;
     const uint32_t NM = (uint32_t)n_meshes;
     const uint32_t max_large = N / T2B_CAP + 2;
-    const uint32_t max_tiles = N / T1_TILE + max_large + 2;
+    // (a level uses tiles smaller than T1_TILE only when it then has no more tiles than the grid has blocks)
+    const uint32_t max_tiles = N / T1_TILE + max_large + 2 + (uint32_t)ctx->sm_count * 16;
     const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
     const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
     const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
@@ -2169,7 +2264,14 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     else k_single_mesh_table<<<1, 32, 0, stream>>>(N, tbase, voff);
     k_setup<<<(N + 255) / 256, 256, 0, stream>>>(d_vertices, (uint32_t)n_vertices, d_indices, N, tbase, voff, NM, cent, box, ids0, st);
     k_roots<<<(NM + 255) / 256, 256, 0, stream>>>(tbase, NM, Q, lv[0], max_large, st, epoch);
-    k_t1_level0<<<1, 1024, 0, stream>>>(lv[0], st);
+    // grid of the cooperative kernel: enough blocks for one 256-slot tile each, at most what is co-resident
+    uint32_t t1_grid = (uint32_t)ctx->sm_count * (uint32_t)(ctx->t1_blocks_per_sm > 0 ? ctx->t1_blocks_per_sm : 1);
+    if (t1_grid > (N + T1_THREADS - 1) / T1_THREADS + 8) t1_grid = (N + T1_THREADS - 1) / T1_THREADS + 8;
+    if (const char* e = getenv("BVH_CUDA_T1_GRID")) {  // experiments: fewer blocks than are co-resident
+        const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
+        if (v >= 1 && v < t1_grid) t1_grid = v;
+    }
+    k_t1_level0<<<1, 1024, 0, stream>>>(lv[0], st, t1_grid);
     launches += 5;
     if (prof) cudaEventRecord(ctx->ev[1], stream);
 
@@ -2187,10 +2289,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         uint4* recs_p = recs;
         uint32_t* A_p = A;
         void* args[] = {&g, &lv0, &lv1, &lv_cap, &Q, &recs_p, &A_p, &ep, &max_levels};
-        const uint32_t tiles0 = (N + T1_TILE - 1) / T1_TILE;
-        uint32_t grid = (uint32_t)ctx->sm_count * (uint32_t)(ctx->t1_blocks_per_sm > 0 ? ctx->t1_blocks_per_sm : 1);
-        const uint32_t want = tiles0 + 8;  // more blocks than tiles only lengthen the barriers
-        if (grid > want) grid = want;
+        const uint32_t grid = t1_grid;
         CU_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_t1_coop, dim3(grid), dim3(T1_THREADS), args, 0, stream));
         launches += 1;
     }
