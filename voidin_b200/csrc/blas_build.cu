@@ -524,7 +524,6 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
     __shared__ uint32_t s_red[NW][12];
     __shared__ uint32_t s_node[12];
     __shared__ uint32_t s_bins[3][8][6];
-    __shared__ uint32_t s_f;
     __shared__ uint32_t s_u[21], s_piv[21], s_uk[21];
     __shared__ float s_ubox[21][6];
     __shared__ Task s_task;
@@ -546,7 +545,6 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
                 s_task.pstart = vq->pstart; s_task.pleftrun = vq->pleftrun; s_task.flags = vq->flags;
             }
             s_have = have ? 1 : 0;
-            s_f = 0;
         }
         __syncthreads();
         if (!s_have) break;
@@ -658,33 +656,31 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
                 nL += v;
                 if (w2 < (int)warp) wpre += v;
             }
-            uint32_t running = wpre, predc = 0;
+            // boundary element in closed form (see p_t1_table): f is nL-1, nL or nL+1, decided by three flags
+            uint32_t f, Lf;
+            {
+                const uint32_t l0 = nL ? ((((pin[nL - 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
+                const uint32_t l1 = (nL < n && (((pin[nL < n ? nL : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+                const uint32_t l2 = (nL + 1 < n && (((pin[nL + 1 < n ? nL + 1 : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+                if (nL >= 1 && !(nL + 1 <= n && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
+                else if (!(nL + 2 <= n && l1 + l2 == 0)) { f = nL; Lf = l1; }
+                else { f = nL + 1; Lf = l2; }
+            }
+            const uint32_t pivot = nL - Lf;
+            uint32_t running = wpre;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 if (i >= (int)E) break;
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
-                const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
-                bool pred = false;
                 if (j < n) {
-                    const uint32_t RF = j - LF;
-                    uint32_t Lnext;
-                    if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                    else if (i + 1 < (int)E) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
-                    else Lnext = (j + 1 < n) ? ((((pin[j + 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
-                    const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
-                    pred = (j + 2 <= n) && (LBB >= RF);
-                    if (Lbit) s_tab[n - 1 - (nL - LF - 1)] = (uint16_t)j;
-                    else s_tab[RF] = (uint16_t)j;
+                    // only front R's (j < f) and back L's (j > f) are looked up
+                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[n - 1 - (nL - LF - 1)] = (uint16_t)j; }
+                    else if (j <= nL) s_tab[j - LF] = (uint16_t)j;
                 }
-                predc += __popc(__ballot_sync(FULL_MASK, pred));
                 running += __popc(bal[i]);
             }
-            if (lane == 0 && predc) atomicAdd(&s_f, predc);
             __syncthreads();  // S2
-            const uint32_t f = s_f;
-            const uint32_t Lf = (((pin[f] >> sh) & 7u) < b) ? 1u : 0u;
-            const uint32_t pivot = nL - Lf;
             running = wpre;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
@@ -707,7 +703,6 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
                 }
             }
             __syncthreads();  // S3
-            if (tid == 0) s_f = 0;
         };
 
         int cur = 0;
@@ -964,34 +959,32 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
                     nL += __popc(bal[i]);
                 }
             }
-            uint32_t running = 0, f = 0;
+            // boundary element in closed form (see p_t1_table): f is nL-1, nL or nL+1, decided by three flags
+            auto l_at = [&](uint32_t j) -> uint32_t {  // one broadcast shared-memory read
+                return (j < n && (((s_pay[w][cur][j < n ? j : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+            };
+            uint32_t f, Lf;
+            {
+                const uint32_t l0 = nL ? l_at(nL - 1) : 0u, l1 = l_at(nL), l2 = l_at(nL + 1);
+                if (nL >= 1 && !(nL + 1 <= n && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
+                else if (!(nL + 2 <= n && l1 + l2 == 0)) { f = nL; Lf = l1; }
+                else { f = nL + 1; Lf = l2; }
+            }
+            const uint32_t pivot = nL - Lf;
+            uint32_t running = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
                 if (i >= (int)E) break;
                 const uint32_t j = i * 32 + lane;
-                const uint32_t Lbit = (bal[i] >> lane) & 1u;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
                 LFv[i] = LF;
-                bool pred = false;
                 if (j < n) {
-                    const uint32_t RF = j - LF;
-                    uint32_t Lnext;
-                    if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                    else Lnext = (i + 1 < (int)E) ? (bal[(i + 1 < EPL) ? i + 1 : i] & 1u) : 0u;
-                    const uint32_t LBB = nL - LF - Lbit - Lnext;  // #L in [j+2, n)
-                    pred = (j + 2 <= n) && (LBB >= RF);
-                    if (Lbit) s_tab[w][n - 1 - (nL - LF - 1)] = (uint16_t)j;
-                    else s_tab[w][RF] = (uint16_t)j;
+                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[w][n - 1 - (nL - LF - 1)] = (uint16_t)j; }
+                    else if (j <= nL) s_tab[w][j - LF] = (uint16_t)j;
                 }
-                f += __popc(__ballot_sync(FULL_MASK, pred));
                 running += __popc(bal[i]);
             }
             __syncwarp();
-            uint32_t Lf = 0;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                if ((uint32_t)i == (f >> 5)) Lf = (bal[i] >> (f & 31u)) & 1u;
-            const uint32_t pivot = nL - Lf;
             uint32_t upay = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
