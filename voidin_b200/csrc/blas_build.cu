@@ -988,8 +988,9 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
             uint32_t upay = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
+                if (i >= (int)E) break;
                 const uint32_t j = i * 32 + lane;
-                if (i < (int)E && j < n) {
+                if (j < n) {
                     uint32_t pay = s_pay[w][cur][j];
                     const uint32_t Lbit = (bal[i] >> lane) & 1u;
                     const uint32_t LF = LFv[i], RF = j - LF;
@@ -1041,6 +1042,7 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < EPL; ++i) {
+                        if (i >= (int)E) break;  // most nodes of this tier fill two or three chunks, not eight
                         const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
                         if (in) {
                             any = true;
