@@ -25,19 +25,28 @@ namespace {
 
 constexpr int T3_MAX = 32;
 // Thread-per-sub-tree tier (k_t4, t4_seq.cuh): sub-trees of <= T4_MAX primitives are built by ONE thread each with the
-// plain sequential algorithm.  32: k_t4 replaces the warp-per-sub-tree kernel k_t3 altogether; 16: k_t3 keeps the
-// nodes of 17..32 primitives and hands every child of <= 16 to k_t4; 0: tier off.
+// plain sequential algorithm.  32: k_t4 replaces the warp-per-sub-tree kernel k_t3 altogether; 4..16: k_t3 keeps the
+// larger nodes and hands every child of <= T4_MAX to k_t4; 0: tier off.
 #ifndef T4_MAX_V
-#define T4_MAX_V 16  // measured on the dragon-class build: 16 -> 7.53 ms, 0 (tier off) -> 7.76 ms, 32 -> 8.83 ms
+// measured on the dragon-class build (k_t3 + k_t4, ms): 4: 0.94+0.12, 6: 0.67+0.22, 8: 0.49+0.38, 10: 0.39+0.54,
+// 12: 0.32+0.68, 16: 0.20+0.99, 32 (no warp tier): 2.41, 0 (no thread tier): 1.34.  k_t4 is bound by its longest task
+// (one thread, ~85 K dependent instructions for 16 primitives), so smaller tasks and more threads per SM win.
+#define T4_MAX_V 8
 #endif
 constexpr int T4_MAX = T4_MAX_V;
-static_assert(T4_MAX == 0 || T4_MAX == 16 || T4_MAX == 32, "T4_MAX_V must be 0, 16 or 32");
+// 1: the thread-tier task list is sorted by sub-tree size before k_t4 runs (k_t4_sort)
+#ifndef T4_SORT
+#define T4_SORT 0  // measured: the sort costs 0.1 ms and k_t4 takes as long as before (it is bound by its longest task)
+#endif
+static_assert(T4_MAX == 0 || (T4_MAX >= 4 && T4_MAX <= 16) || T4_MAX == 32, "T4_MAX_V must be 0, 4..16 or 32");
 // Other forms of the small-sub-tree tiers that were built, verified bit-exact and measured slower on B200 (dragon-class,
 // commit ac13e1f): all nodes of one depth as lane segments of one warp (1.42 ms vs 1.34 ms: SAH sub-trees are
 // deep, not bushy, and a pass costs as much as a node visit); sub-trees through k_t2w's queue (2.94 ms vs 2.46 ms for the
 // two tiers); thread tier limited to whole waves of sm_count x T4_THREADS tasks (1.22 ms vs 1.24 ms).
 constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
-constexpr int T4_THREADS = (T4_CAP == 32) ? 224 : 448;  // 8 words per slot per thread: 229 376 B of shared memory per block
+// 8 words per slot per thread: <= 229 376 B of shared memory per block; 768 threads is the register limit (78 regs)
+constexpr int T4_THREADS_SMEM = (229376 / (32 * T4_CAP)) / 32 * 32;
+constexpr int T4_THREADS = T4_THREADS_SMEM < 768 ? T4_THREADS_SMEM : 768;
 constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
 // 1: grid tier PA publishes the boundary element from nL and three flags (one thread per node) and writes only the
 // table entries that can be looked up; 0: every thread evaluates the front-examined predicate
@@ -424,13 +433,13 @@ __global__ void __launch_bounds__(256, 4) k_t3(Queues Q, uint32_t* ids,
 // T4: one THREAD per sub-tree of <= CAP primitives (t4_seq.cuh).  Working set in shared memory as [word][thread].
 // ------------------------------------------------------------------------------------------------
 template <int CAP, int BD>
-__global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
+__global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, const Task* __restrict__ tasks, uint32_t* ids, const float4* __restrict__ cent,
                                              const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st) {
     extern __shared__ uint32_t s_t4[];
     const T4Mem<CAP> m{reinterpret_cast<float*>(s_t4) + threadIdx.x, s_t4 + 6 * CAP * BD + threadIdx.x, (uint32_t)BD};
     const uint32_t n_tasks = min(st->t4_count, Q.t4_cap);
     for (uint32_t ti = blockIdx.x * BD + threadIdx.x; ti < n_tasks; ti += gridDim.x * BD) {
-        const Task tk = Q.t4[ti];
+        const Task tk = tasks[ti];
         const T4Task t{tk.start, tk.n, tk.leftrun, tk.pstart, tk.pleftrun, tk.flags};
         for (uint32_t j = 0; j < t.n; ++j) {
             const uint32_t g = __ldcg(&ids[t.start + j]);
@@ -441,6 +450,28 @@ __global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, uint32_t* ids, const flo
         }
         const uint32_t err = t4_core<CAP>(t, m, reinterpret_cast<const T4Cent*>(cent), ids, reinterpret_cast<T4Rec*>(recs), A);
         if (err) atomicOr(&st->err, DERR_DEGENERATE);
+    }
+}
+
+// Counting sort of the thread-tier task list by sub-tree size, largest first (one block; the list is a few MB).  A warp
+// of k_t4 then starts on 32 sub-trees of the same size, so its lanes run the same trip counts for the root visit and
+// similar ones below it, and the long tasks start first.
+__global__ void __launch_bounds__(1024) k_t4_sort(const Task* __restrict__ in, Task* __restrict__ out, uint32_t cap,
+                                                  const BuildState* st) {
+    __shared__ uint32_t s_cnt[T4_CAP + 1], s_cur[T4_CAP + 1];
+    const uint32_t n_tasks = min(st->t4_count, cap);
+    if (threadIdx.x <= T4_CAP) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tasks; i += blockDim.x) atomicAdd(&s_cnt[min(in[i].n, (uint32_t)T4_CAP)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int k = T4_CAP; k >= 0; --k) { s_cur[k] = acc; acc += s_cnt[k]; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tasks; i += blockDim.x) {
+        const Task t = in[i];
+        out[atomicAdd(&s_cur[min(t.n, (uint32_t)T4_CAP)], 1u)] = t;
     }
 }
 
@@ -2199,7 +2230,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
              *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr;
+    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr, *t4s = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -2220,6 +2251,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         qw = c.take<Task>(qw_cap);
         t3 = c.take<Task>(t3_cap);
         t4 = c.take<Task>(t4_cap);
+        t4s = c.take<Task>(T4_SORT ? t4_cap : 16u);
         lv[0] = c.take<LevelNode>(max_large);
         lv[1] = c.take<LevelNode>(max_large);
         sc = c.take<NodeScratch>(max_large);
@@ -2322,7 +2354,11 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
             CU_CHECK(ctx, cudaFuncSetAttribute(k_t4<T4_CAP, T4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
             ctx->t4_ready = true;
         }
-        k_t4<T4_CAP, T4_THREADS><<<ctx->sm_count, T4_THREADS, T4_SMEM, stream>>>(Q, ids0, cent, box, recs, A, st);
+        if (T4_SORT) {
+            k_t4_sort<<<1, 1024, 0, stream>>>(t4, t4s, t4_cap, st);
+            launches++;
+        }
+        k_t4<T4_CAP, T4_THREADS><<<ctx->sm_count, T4_THREADS, T4_SMEM, stream>>>(Q, T4_SORT ? t4s : t4, ids0, cent, box, recs, A, st);
         launches++;
     }
     if (prof) cudaEventRecord(ctx->ev[4], stream);

@@ -171,18 +171,35 @@ T4_HD uint32_t t4_core(const T4Task& t, const T4Mem<CAP>& m, const T4Cent* cent,
     for (uint32_t j = 0; j < t.n; ++j) m.ord(j) = j;
 
     for (;;) {
-        const uint32_t abs_start = t.start + s;
-        // own vertex box, folded in slot order from +-1e30 (blas.rs:87-88,117-123,185-186)
-        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-        for (uint32_t j = s; j < s + n; ++j) {
-            const uint32_t e = m.ord(j) & 31u;
-            lo[0] = t4_min(lo[0], m.box(0, e)); lo[1] = t4_min(lo[1], m.box(1, e)); lo[2] = t4_min(lo[2], m.box(2, e));
-            hi[0] = t4_max(hi[0], m.box(3, e)); hi[1] = t4_max(hi[1], m.box(4, e)); hi[2] = t4_max(hi[2], m.box(5, e));
+        // Leaves first: walk on until the current node is an interior one (or the sub-tree is finished).  About half of
+        // all node visits are leaves; taking them in this short loop keeps the lanes of a warp together in the long
+        // interior part below instead of parking a leaf lane for the whole of its neighbours' 22 shuffles
+        // (ncu, first form: 8.25 of 32 lanes active).
+        uint32_t abs_start;
+        float lo[3], hi[3];
+        bool done = false;
+        for (;;) {
+            abs_start = t.start + s;
+            // own vertex box, folded in slot order from +-1e30 (blas.rs:87-88,117-123,185-186)
+            lo[0] = lo[1] = lo[2] = 1e30f;
+            hi[0] = hi[1] = hi[2] = -1e30f;
+            for (uint32_t j = s; j < s + n; ++j) {
+                const uint32_t e = m.ord(j) & 31u;
+                lo[0] = t4_min(lo[0], m.box(0, e)); lo[1] = t4_min(lo[1], m.box(1, e)); lo[2] = t4_min(lo[2], m.box(2, e));
+                hi[0] = t4_max(hi[0], m.box(3, e)); hi[1] = t4_max(hi[1], m.box(4, e)); hi[2] = t4_max(hi[2], m.box(5, e));
+            }
+            if (n > 3) break;
+            t4_emit(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);  // leaf (blas.rs:106-109)
+            if (sp == 0) { done = true; break; }
+            const uint32_t x = stk[--sp];
+            s = x & 0xFFu; n = (x >> 8) & 0xFFu;
+            pstart = t.start + ((x >> 16) & 0xFFu);
+            pleftrun = ((x >> 31) ? t.leftrun : 0u) + ((x >> 24) & 0x7Fu);
+            leftrun = 0; k = 0; allleft = 0; fl = T4_TF_RIGHT | (t.flags & ~3u);
         }
+        if (done) break;
         bool descend = false;
-        if (n <= 3) {  // leaf (blas.rs:106-109)
-            t4_emit(recs, 2 * abs_start, lo, hi, abs_start, n, leftrun, pstart, pleftrun, fl);
-        } else {
+        {
             // centroid bounds (blas.rs:142), then the plane counts of every primitive under this node's planes
             float cmin[3] = {1e30f, 1e30f, 1e30f}, cmax[3] = {-1e30f, -1e30f, -1e30f};
             for (uint32_t j = s; j < s + n; ++j) {
