@@ -680,13 +680,11 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
             }
             if (lane == 0) s_wtot[warp] = cnt;
             __syncthreads();  // S1
-            uint32_t wpre = 0, nL = 0;
-#pragma unroll
-            for (int w2 = 0; w2 < NW; ++w2) {
-                const uint32_t v = s_wtot[w2];
-                nL += v;
-                if (w2 < (int)warp) wpre += v;
-            }
+            // lane w2 reads warp w2's count: total and the sum over the warps before this one by two warp reductions
+            // (a serial walk over 32 counts was a third of a big-block shuffle of a small node)
+            const uint32_t wv = (lane < (uint32_t)NW) ? s_wtot[lane] : 0u;
+            const uint32_t nL = __reduce_add_sync(FULL_MASK, wv);
+            const uint32_t wpre = __reduce_add_sync(FULL_MASK, lane < warp ? wv : 0u);
             // boundary element in closed form (see p_t1_table): f is nL-1, nL or nL+1, decided by three flags
             uint32_t f, Lf;
             {
@@ -740,47 +738,48 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
         for (uint32_t c = 0; c < 21; ++c) { shuffle(cur, c / 7, c % 7 + 1, (int)c); cur ^= 1; }
 
         // ---- 4. exact bins over the non-special primitives (4 slots per thread at a time) ----
+        // Boxes are mapped to ordered uints once per slot, so the 24 per-bin reductions below are integer min / max
+        // feeding redux.sync directly.
         {
             const uint32_t* pin = cur ? s_pay1 : s_pay0;
             for (uint32_t i0 = 0; i0 < E; i0 += 4) {
-                float lo[4][3], hi[4][3];
+                uint32_t lo[4][3], hi[4][3];
                 uint32_t kk[4];
 #pragma unroll
                 for (int ii = 0; ii < 4; ++ii) {
                     const uint32_t i = i0 + ii;
                     const uint32_t j = warp * CHUNK + i * 32 + lane;
                     kk[ii] = 0xFFFFFFFFu;
-                    lo[ii][0] = lo[ii][1] = lo[ii][2] = 1e30f;
-                    hi[ii][0] = hi[ii][1] = hi[ii][2] = -1e30f;
+                    lo[ii][0] = lo[ii][1] = lo[ii][2] = ENC_POS_INIT;
+                    hi[ii][0] = hi[ii][1] = hi[ii][2] = ENC_NEG_INIT;
                     if (i < E && j < n) {
                         const uint32_t pay = pin[j];
                         if (!(pay & 0x80000000u)) {
                             const uint32_t g = __ldcg(&ids_snap[start + (pay & 0xFFFFu)]);
                             const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-                            lo[ii][0] = b0.x; lo[ii][1] = b0.y; lo[ii][2] = b0.z;
-                            hi[ii][0] = b1.x; hi[ii][1] = b1.y; hi[ii][2] = b1.z;
+                            lo[ii][0] = f2o(b0.x); lo[ii][1] = f2o(b0.y); lo[ii][2] = f2o(b0.z);
+                            hi[ii][0] = f2o(b1.x); hi[ii][1] = f2o(b1.y); hi[ii][2] = f2o(b1.z);
                             kk[ii] = (pay >> 16) & 0x1FFu;
                         }
                     }
                 }
                 for (uint32_t a = 0; a < 3; ++a) {
                     for (uint32_t k = 0; k < 8; ++k) {
-                        float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                        uint32_t m[6] = {ENC_POS_INIT, ENC_POS_INIT, ENC_POS_INIT, ENC_NEG_INIT, ENC_NEG_INIT, ENC_NEG_INIT};
                         bool any = false;
 #pragma unroll
                         for (int ii = 0; ii < 4; ++ii) {
                             const bool in = (kk[ii] != 0xFFFFFFFFu) && (((kk[ii] >> (3 * a)) & 7u) == k);
                             if (in) {
                                 any = true;
-                                m[0] = fminf(m[0], lo[ii][0]); m[1] = fminf(m[1], lo[ii][1]); m[2] = fminf(m[2], lo[ii][2]);
-                                m[3] = fmaxf(m[3], hi[ii][0]); m[4] = fmaxf(m[4], hi[ii][1]); m[5] = fmaxf(m[5], hi[ii][2]);
+                                m[0] = min(m[0], lo[ii][0]); m[1] = min(m[1], lo[ii][1]); m[2] = min(m[2], lo[ii][2]);
+                                m[3] = max(m[3], hi[ii][0]); m[4] = max(m[4], hi[ii][1]); m[5] = max(m[5], hi[ii][2]);
                             }
                         }
                         if (!__any_sync(FULL_MASK, any)) continue;
 #pragma unroll
                         for (int c = 0; c < 6; ++c) {
-                            const uint32_t v = f2o(m[c]);
-                            const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                            const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, m[c]) : __reduce_max_sync(FULL_MASK, m[c]);
                             if (lane == 0) {
                                 if (c < 3) atomicMin(&s_bins[a][k][c], r);
                                 else atomicMax(&s_bins[a][k][c], r);
@@ -1442,8 +1441,8 @@ __device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, u
     }
     if (lane == 0) s_w[warp] = cnt;
     __syncthreads();
-    uint32_t running = tile_lf;
-    for (uint32_t w2 = 0; w2 < warp; ++w2) running += s_w[w2];
+    const uint32_t wv = (lane < warp) ? s_w[lane & (T1_THREADS / 32 - 1)] : 0u;
+    uint32_t running = tile_lf + __reduce_add_sync(FULL_MASK, wv);
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
@@ -1655,28 +1654,28 @@ __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, 
         const uint32_t j0 = td.w * g.tile_sz;
         if (tid < 144) (&s_bins[0][0][0])[tid] = ((tid % 6) < 3) ? ENC_POS_INIT : ENC_NEG_INIT;
         __syncthreads();
-        float lo[EPT][3], hi[EPT][3];
+        uint32_t lo[EPT][3], hi[EPT][3];  // ordered uints (f2o): the per-bin reductions below are integer min / max
         uint32_t kk[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const uint32_t j = j0 + i * T1_THREADS + tid;
             kk[i] = 0xFFFFFFFFu;
-            lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
-            hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
+            lo[i][0] = lo[i][1] = lo[i][2] = ENC_POS_INIT;
+            hi[i][0] = hi[i][1] = hi[i][2] = ENC_NEG_INIT;
             if (j < nd.n) {
                 const uint32_t fw = fl[nd.start + j];
                 if (!(fw & 0x8000u)) {
                     const uint32_t id = ids[nd.start + j];
                     const float4 b0 = g.box[2 * (size_t)id], b1 = g.box[2 * (size_t)id + 1];
-                    lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
-                    hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
+                    lo[i][0] = f2o(b0.x); lo[i][1] = f2o(b0.y); lo[i][2] = f2o(b0.z);
+                    hi[i][0] = f2o(b1.x); hi[i][1] = f2o(b1.y); hi[i][2] = f2o(b1.z);
                     kk[i] = fw & 0x1FFu;
                 }
             }
         }
         for (uint32_t a = 0; a < 3; ++a) {
             for (uint32_t k = 0; k < 8; ++k) {
-                float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                uint32_t m[6] = {ENC_POS_INIT, ENC_POS_INIT, ENC_POS_INIT, ENC_NEG_INIT, ENC_NEG_INIT, ENC_NEG_INIT};
                 bool any = false;
 #pragma unroll
                 for (int i = 0; i < EPT; ++i) {
@@ -1684,15 +1683,14 @@ __device__ __forceinline__ void p_t1_bins(const T1Args& g, const uint32_t* ids, 
                     const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
                     if (in) {
                         any = true;
-                        m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
-                        m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                        m[0] = min(m[0], lo[i][0]); m[1] = min(m[1], lo[i][1]); m[2] = min(m[2], lo[i][2]);
+                        m[3] = max(m[3], hi[i][0]); m[4] = max(m[4], hi[i][1]); m[5] = max(m[5], hi[i][2]);
                     }
                 }
                 if (!__any_sync(FULL_MASK, any)) continue;
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
-                    const uint32_t v = f2o(m[c]);
-                    const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
+                    const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, m[c]) : __reduce_max_sync(FULL_MASK, m[c]);
                     if (lane == 0) {
                         if (c < 3) atomicMin(&s_bins[a][k][c], r);
                         else atomicMax(&s_bins[a][k][c], r);
