@@ -1045,30 +1045,32 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
         }
 
         // ---- 4. exact bins over the non-special primitives; lane a*8+k keeps bin (a,k) ----
-        float mybin[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+        // (ordered uints from the load to the end of the reductions: one f2o per value, one o2f per bin)
+        float mybin[6];
         {
-            float lo[EPL][3], hi[EPL][3];
+            uint32_t mb[6] = {ENC_POS_INIT, ENC_POS_INIT, ENC_POS_INIT, ENC_NEG_INIT, ENC_NEG_INIT, ENC_NEG_INIT};
+            uint32_t lo[EPL][3], hi[EPL][3];
             uint32_t kk[EPL];
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
                 const uint32_t j = i * 32 + lane;
                 kk[i] = 0xFFFFFFFFu;
-                lo[i][0] = lo[i][1] = lo[i][2] = 1e30f;
-                hi[i][0] = hi[i][1] = hi[i][2] = -1e30f;
+                lo[i][0] = lo[i][1] = lo[i][2] = ENC_POS_INIT;
+                hi[i][0] = hi[i][1] = hi[i][2] = ENC_NEG_INIT;
                 if (i < (int)E && j < n) {
                     const uint32_t pay = s_pay[w][cur][j];
                     if (!(pay & 0x80000000u)) {
                         const uint32_t g = s_gid[w][pay & 0xFFFFu];
                         const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
-                        lo[i][0] = b0.x; lo[i][1] = b0.y; lo[i][2] = b0.z;
-                        hi[i][0] = b1.x; hi[i][1] = b1.y; hi[i][2] = b1.z;
+                        lo[i][0] = f2o(b0.x); lo[i][1] = f2o(b0.y); lo[i][2] = f2o(b0.z);
+                        hi[i][0] = f2o(b1.x); hi[i][1] = f2o(b1.y); hi[i][2] = f2o(b1.z);
                         kk[i] = (pay >> 16) & 0x1FFu;
                     }
                 }
             }
             for (uint32_t a = 0; a < 3; ++a) {
                 for (uint32_t k = 0; k < 8; ++k) {
-                    float m[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                    uint32_t m[6] = {ENC_POS_INIT, ENC_POS_INIT, ENC_POS_INIT, ENC_NEG_INIT, ENC_NEG_INIT, ENC_NEG_INIT};
                     bool any = false;
 #pragma unroll
                     for (int i = 0; i < EPL; ++i) {
@@ -1076,19 +1078,20 @@ __global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const f
                         const bool in = (kk[i] != 0xFFFFFFFFu) && (((kk[i] >> (3 * a)) & 7u) == k);
                         if (in) {
                             any = true;
-                            m[0] = fminf(m[0], lo[i][0]); m[1] = fminf(m[1], lo[i][1]); m[2] = fminf(m[2], lo[i][2]);
-                            m[3] = fmaxf(m[3], hi[i][0]); m[4] = fmaxf(m[4], hi[i][1]); m[5] = fmaxf(m[5], hi[i][2]);
+                            m[0] = min(m[0], lo[i][0]); m[1] = min(m[1], lo[i][1]); m[2] = min(m[2], lo[i][2]);
+                            m[3] = max(m[3], hi[i][0]); m[4] = max(m[4], hi[i][1]); m[5] = max(m[5], hi[i][2]);
                         }
                     }
                     if (!__any_sync(FULL_MASK, any)) continue;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) {
-                        const uint32_t v = f2o(m[c]);
-                        const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, v) : __reduce_max_sync(FULL_MASK, v);
-                        if (lane == a * 8 + k) mybin[c] = o2f(r);
+                        const uint32_t r = (c < 3) ? __reduce_min_sync(FULL_MASK, m[c]) : __reduce_max_sync(FULL_MASK, m[c]);
+                        if (lane == a * 8 + k) mb[c] = r;
                     }
                 }
             }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) mybin[c] = o2f(mb[c]);
         }
         // ---- 5. candidate costs and selection ----
         float ub[6] = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};  // box of special `lane`
