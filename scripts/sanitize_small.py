@@ -10,7 +10,8 @@ ctx = vb.Context(0)
 def builder(v, i):
     i2 = i.copy(); b = vb.BvhBuilder(v, i2, ctx).build(); return b.nodes, i2
 pool = S.MeshPool(builder)
-for n in (3, 20, 200, 3000, 40000):
+big = int(sys.argv[1]) if len(sys.argv) > 1 else 40000  # 130000: grid tier on 512-slot tiles at the root, 256 below
+for n in (3, 20, 200, 3000, big):
     pool.add(*S.soup(n, 70 + n, 0.05))
 verts, inds, nodes, infos = pool.pooled()
 inst = S.random_instances(50, len(infos), seed=4, extent=5.0)

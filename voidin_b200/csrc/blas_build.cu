@@ -1461,8 +1461,11 @@ __device__ __forceinline__ void t1_prefix(uint32_t n, uint32_t j0, uint32_t a, u
 // thread of the whole grid sees the true->false transition; it publishes {nL, f, pivot} for the scatter phase.
 template <int EPT>
 __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_t* fl, bool scanned) {
-    __shared__ uint32_t s_w[T1_THREADS / 32];
-    __shared__ uint32_t s_pre[T1_THREADS / 32], s_tot[T1_THREADS / 32];
+    // 16-byte aligned: the compiler reads s_pre / s_tot with LDS.128, and an unaligned array made the first of those
+    // loads cover the last word of its neighbour (harmless, but compute-sanitizer racecheck reports it)
+    __shared__ __align__(16) uint32_t s_w[T1_THREADS / 32];
+    __shared__ __align__(16) uint32_t s_pre[T1_THREADS / 32];
+    __shared__ __align__(16) uint32_t s_tot[T1_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* tl = g.tileL + (size_t)c * g.tile_stride;
     for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
