@@ -53,6 +53,10 @@ constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
 #ifndef T1_CLOSED_F
 #define T1_CLOSED_F 1
 #endif
+// 1: PB takes the tile's ballots and warp prefix bases from PA (288 B per tile) instead of recomputing them
+#ifndef T1_PB_REUSE
+#define T1_PB_REUSE 1
+#endif
 // 1: the grid tier picks the tile size per level (p_t1_nextlevel); 0: always T1_TILE
 #ifndef T1_VAR_TILE
 #define T1_VAR_TILE 1
@@ -1184,6 +1188,7 @@ struct T1Args {
     uint32_t* table;
     uint32_t* tileL;     // [22][tile_stride] per-candidate L count of every tile (current order at that shuffle)
     uint32_t* tileLF;    // [tile_stride] #L in the node before this tile, for the shuffle in flight
+    uint32_t* pbal;      // [tile_stride][8 warps][9] PA -> PB: #L before the warp's first slot, then its <= 8 ballot words
     uint4* tile_desc;    // [tile_stride] {node, start, n, tile index inside the node}
     uint32_t tile_stride;
     const float4* cent;
@@ -1515,6 +1520,14 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
         }
         uint32_t bal[EPT], LFv[EPT];
         t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw, ept);
+#if T1_PB_REUSE
+        if (lane == 0) {  // PB of this shuffle runs on the same tile: leave it the ballots and the warp's prefix base
+            uint32_t* pb = g.pbal + ((size_t)tile * (T1_THREADS / 32) + warp) * 9;
+            pb[0] = LFv[0];
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) pb[1 + i] = bal[i];
+        }
+#endif
         // Only front R's (j < f) and back L's (j > f) are ever looked up; with f in [nL-1, nL+1] that is j <= nL / j >= nL.
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -1603,7 +1616,22 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
         const uint4 sh = g.sc[node].sh[c];
         const uint32_t nL = sh.x, f = sh.y, pivot = sh.z;
         uint32_t bal[EPT], LFv[EPT];
+#if T1_PB_REUSE && T1_CLOSED_F
+        {
+            const uint32_t* pb = g.pbal + ((size_t)tile * (T1_THREADS / 32) + warp) * 9;
+            uint32_t running = pb[0];
+            const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                bal[i] = pb[1 + i];
+                LFv[i] = running + __popc(bal[i] & lt_mask);
+                running += __popc(bal[i]);
+            }
+            (void)a; (void)b; (void)s_w;
+        }
+#else
         t1_prefix<EPT>(n, j0, a, b, g.tileLF[tile], s_w, bal, LFv, fwv, ept);
+#endif
         uint32_t own_cnt = 0;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
@@ -2230,7 +2258,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     // carve the workspace (first pass sizes, second pass assigns)
     float4 *cent = nullptr, *box = nullptr;
     uint4* tile_desc = nullptr;
-    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr, *barrier = nullptr,
+    uint32_t *ids0 = nullptr, *ids1 = nullptr, *table = nullptr, *A = nullptr, *tileL = nullptr, *tileLF = nullptr, *pbal = nullptr, *barrier = nullptr,
              *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
@@ -2261,6 +2289,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         sc = c.take<NodeScratch>(max_large);
         tileL = c.take<uint32_t>(22 * (size_t)max_tiles);
         tileLF = c.take<uint32_t>(max_tiles);
+        pbal = c.take<uint32_t>((size_t)max_tiles * (T1_THREADS / 32) * 9);
         tile_desc = c.take<uint4>(max_tiles);
         barrier = c.take<uint32_t>(64);
         scan_sums = c.take<uint32_t>(scan_blocks + 1);
@@ -2312,7 +2341,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         T1Args g;
         g.nodes = lv[0]; g.sc = sc; g.n_nodes = 0; g.n_tiles = 0;
         g.ids0 = ids0; g.ids1 = ids1; g.fl0 = fl0; g.fl1 = fl1;
-        g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.tile_desc = tile_desc; g.tile_stride = max_tiles;
+        g.table = table; g.tileL = tileL; g.tileLF = tileLF; g.pbal = pbal; g.tile_desc = tile_desc; g.tile_stride = max_tiles;
         g.cent = cent; g.box = box; g.st = st; g.barrier = barrier;
         LevelNode* lv0 = lv[0];
         LevelNode* lv1 = lv[1];
