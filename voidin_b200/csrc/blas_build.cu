@@ -47,7 +47,10 @@ constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
 // 8 words per slot per thread: <= 229 376 B of shared memory per block; 768 threads is the register limit (78 regs)
 constexpr int T4_THREADS_SMEM = (229376 / (32 * T4_CAP)) / 32 * 32;
 constexpr int T4_THREADS = T4_THREADS_SMEM < 768 ? T4_THREADS_SMEM : 768;
-constexpr int T2W_CAP = 256;  // warp-per-node tier: 33..256
+#ifndef T2W_CAP_V
+#define T2W_CAP_V 256
+#endif
+constexpr int T2W_CAP = T2W_CAP_V;  // warp-per-node tier: 33..T2W_CAP
 // 1: grid tier PA publishes the boundary element from nL and three flags (one thread per node) and writes only the
 // table entries that can be looked up; 0: every thread evaluates the front-examined predicate
 #ifndef T1_CLOSED_F
