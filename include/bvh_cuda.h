@@ -83,7 +83,7 @@ typedef struct BvhCudaBuildStats {
     uint32_t big_block_tasks;    /* nodes handled by one 1024-thread block each (2049..16384) */
     uint32_t block_tasks;        /* nodes handled one block each from the device task queue (257..2048) */
     uint32_t warp_node_tasks;    /* nodes handled one warp each from the second task queue (33..256) */
-    uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each (0 when the thread tier takes them all) */
+    uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each; their small children go to the thread tier */
     uint32_t kernel_launches;    /* kernels launched by this build */
     /* Device time per phase in ms (CUDA events on the build's stream); all zero unless profiling is enabled. */
     float ms_setup;              /* k_setup: centroids, triangle boxes */
@@ -95,7 +95,10 @@ typedef struct BvhCudaBuildStats {
     float ms_emit;               /* numbering scan + node emit + index permutation */
     float ms_total;
     float ms_thread;             /* k_t4: thread-per-sub-tree kernel (one launch) */
-    uint32_t thread_tasks;       /* sub-trees (<= 32 triangles) handled one thread each */
+    uint32_t thread_tasks;       /* small sub-trees handled one thread each (k_t4) */
+    uint32_t grid_nodes;         /* interior nodes split by the grid-wide tier */
+    uint32_t reserved0;
+    uint64_t grid_interior_prims;/* sum of their triangle counts (the S of the grid tier's algorithmic bytes) */
 } BvhCudaBuildStats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */

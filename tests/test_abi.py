@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_reference():
     assert vb.TLAS_NODE.fields["left_right"][1] == 12 and vb.TLAS_NODE.fields["instance_idx"][1] == 28
     assert vb.INSTANCE.fields["inv_transform"][1] == 64 and vb.INSTANCE.fields["mesh"][1] == 128
     assert vb.MESH_INFO.fields["vertex_offset"][1] == 32 and vb.MESH_INFO.fields["bvh_index"][1] == 36
-    assert C.sizeof(_lib.BuildStats) == 80
+    assert C.sizeof(_lib.BuildStats) == 96
 
 
 def test_null_context_calls_are_rejected_not_crashing():

@@ -64,6 +64,9 @@ class BuildStats(C.Structure):
         ("ms_total", C.c_float),
         ("ms_thread", C.c_float),
         ("thread_tasks", C.c_uint32),
+        ("grid_nodes", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("grid_interior_prims", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -119,7 +119,11 @@ struct BuildState {
     uint32_t t3_inline;
     uint32_t neg_zero;  // some referenced vertex coordinate is -0.0: box zeros need the reference's first-encounter sign
     uint32_t t4_count;
+    uint32_t grid_nodes;            // interior nodes split by the grid tier ...
+    unsigned long long sum_grid;    // ... and the sum of their primitive counts (statistics for the roofline)
 };
+
+static_assert(sizeof(BuildState) <= 256, "BuildState is read back into the first 64 words of the pinned scratch");
 
 __device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 
@@ -1821,6 +1825,8 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
             }
         emit_rec(recs, 2 * (nd.start + p) + 1, lo, hi, nd.start, nd.n, nd.leftrun, nd.pstart, nd.pleftrun, nd.flags);
         if (p <= 3) A[nd.start] = nd.leftrun + 1;
+        atomicAdd(&g.st->grid_nodes, 1u);
+        atomicAdd(&g.st->sum_grid, (unsigned long long)nd.n);
         for (int side = 0; side < 2; ++side) {
             const uint32_t cs = side ? nd.start + p : nd.start;
             const uint32_t cn = side ? nd.n - p : p;
@@ -2439,6 +2445,8 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.warp_tasks = hs->t3_count;
     stats.thread_tasks = hs->t4_count;
     stats.kernel_launches = launches;
+    stats.grid_nodes = hs->grid_nodes;
+    stats.grid_interior_prims = hs->sum_grid;
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&stats.ms_grid, ctx->ev[1], ctx->ev[2]);
