@@ -2105,6 +2105,29 @@ __global__ void __launch_bounds__(256) k_mesh_counts(const uint32_t* __restrict_
     if (m == n_meshes) node_base[m] = 0;
 }
 
+// Same for a scene of at most 1024 meshes, together with the exclusive scan that turns the counts into node bases and
+// the total: one block instead of four launches (a single mesh is the common case).
+__global__ void __launch_bounds__(1024) k_mesh_bases_small(const uint32_t* __restrict__ P, const uint32_t* __restrict__ tbase,
+                                                          uint32_t n_meshes, uint32_t* node_base, uint32_t* total) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t m = threadIdx.x, lane = m & 31, warp = m >> 5;
+    const uint32_t v = (m < n_meshes) ? 2u + 2u * (P[tbase[m + 1]] - P[tbase[m]]) : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL_MASK, inc, o);
+        if ((int)lane >= o) inc += y;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    const uint32_t wv = s_w[lane];
+    const uint32_t before = __reduce_add_sync(FULL_MASK, lane < warp ? wv : 0u);
+    const uint32_t all = __reduce_add_sync(FULL_MASK, wv);
+    if (m < n_meshes) node_base[m] = before + inc - v;
+    if (m == n_meshes) node_base[m] = all;
+    if (m == 0) *total = all;
+}
+
 __global__ void __launch_bounds__(256) k_write_bvh_index(MeshInfo* infos, const uint32_t* __restrict__ node_base, uint32_t n_meshes) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < n_meshes) infos[m].bvh_index = node_base[m];
@@ -2409,10 +2432,15 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     k_scan_top<<<1, 1024, 0, stream>>>(scan_sums, scan_blocks, scan_total);
     k_scan_apply<<<scan_blocks, 1024, 0, stream>>>(A, scan_n, scan_sums);
     // per-mesh node bases (pooled bvh_index, mesh/mod.rs:322-325): exclusive scan of M_m over the meshes
-    k_mesh_counts<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(A, tbase, NM, node_base);
-    k_scan_reduce<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
-    k_scan_top<<<1, 1024, 0, stream>>>(mscan_sums, mscan_blocks, scan_total + 1);
-    k_scan_apply<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
+    if (NM < 1024) {
+        k_mesh_bases_small<<<1, 1024, 0, stream>>>(A, tbase, NM, node_base, scan_total + 1);
+    } else {
+        k_mesh_counts<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(A, tbase, NM, node_base);
+        k_scan_reduce<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
+        k_scan_top<<<1, 1024, 0, stream>>>(mscan_sums, mscan_blocks, scan_total + 1);
+        k_scan_apply<<<mscan_blocks, 1024, 0, stream>>>(node_base, mscan_n, mscan_sums);
+        launches += 3;
+    }
     k_emit<<<(2 * N + 255) / 256, 256, 0, stream>>>(recs, 2 * N, A, tbase, node_base, d_nodes_out,
                                                     (uint32_t)(nodes_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : nodes_cap), st);
     if (d_mesh_info) { k_write_bvh_index<<<(NM + 255) / 256, 256, 0, stream>>>(d_mesh_info, node_base, NM); launches++; }
@@ -2420,7 +2448,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     uint32_t* tmp = reinterpret_cast<uint32_t*>(box);
     k_permute_gather<<<(N + 255) / 256, 256, 0, stream>>>(d_indices, ids0, N, tmp);
     CU_CHECK(ctx, cudaMemcpyAsync(d_indices, tmp, sizeof(uint32_t) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, stream));
-    launches += 9;
+    launches += 6;
     if (prof) cudaEventRecord(ctx->ev[5], stream);
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
