@@ -70,6 +70,61 @@ def test_closed_form_shuffle_equals_sequential(oracle):
         assert (out == ids).all(), (flags, out, ids)
 
 
+def _shuffle_kernel_form(flags):
+    """The shuffle as the CUDA tiers compute it since the end of round 1 (p_t1_table / k_t2 / k_t2w in blas_build.cu):
+    the boundary element f from nL and the flags at nL-1, nL, nL+1 instead of a predicate per slot, and a rank->position
+    table that only holds the entries that can be looked up (R's at j <= nL, L's at j >= nL); every other entry is
+    poisoned here so that a look-up outside the filter fails the test."""
+    n = len(flags)
+    L = np.asarray(flags, dtype=bool)
+    nL = int(L.sum())
+    RF = np.concatenate([[0], np.cumsum(~L)[:-1]])
+    LF = np.arange(n) - RF
+    at = lambda j: int(L[j]) if 0 <= j < n else 0
+    l0, l1, l2 = (at(nL - 1) if nL else 0), at(nL), at(nL + 1)
+    if nL >= 1 and not (nL + 1 <= n and l0 + l1 <= 1):
+        f, lf = nL - 1, l0
+    elif not (nL + 2 <= n and l1 + l2 == 0):
+        f, lf = nL, l1
+    else:
+        f, lf = nL + 1, l2
+    pivot = nL - lf
+    tab = np.full(n, -10**9, dtype=np.int64)
+    for j in range(n):
+        if L[j]:
+            if j >= nL:
+                tab[n - 1 - (nL - LF[j] - 1)] = j
+        elif j <= nL:
+            tab[RF[j]] = j
+    dest = np.zeros(n, dtype=np.int64)
+    for j in range(n):
+        if j < f:
+            dest[j] = j if L[j] else (n - 1 if RF[j] == 0 else tab[n - RF[j]] - 1)
+        elif j == f:
+            dest[j] = pivot
+        else:
+            dest[j] = tab[nL - LF[j] - 1] if L[j] else j - 1
+    return dest, pivot, f
+
+
+def test_kernel_form_of_the_shuffle_equals_sequential(oracle):
+    rng = np.random.default_rng(5)
+    cases = [np.zeros(n, np.uint8) for n in (1, 2, 3, 7)] + [np.ones(n, np.uint8) for n in (1, 2, 3, 7)]
+    for trial in range(4000):
+        n = int(rng.integers(1, 70))
+        cases.append((rng.random(n) < rng.random()).astype(np.uint8))
+    for flags in cases:
+        n = len(flags)
+        piv, ids = oracle.shuffle_seq(np.arange(n, dtype=np.uint32), flags)
+        dest, pivot, f = _shuffle_kernel_form(flags)
+        ref_dest, ref_pivot = _shuffle_closed_form(flags)
+        assert pivot == piv == ref_pivot, (flags, pivot, piv)
+        assert (dest >= 0).all() and (dest == ref_dest).all(), (flags, dest, ref_dest)
+        out = np.empty(n, dtype=np.int64)
+        out[dest] = np.arange(n)
+        assert (out == ids).all(), (flags, out, ids)
+
+
 def test_empty_and_invalid_inputs(oracle):
     v, idx = S.soup(4, 1, 0.05)
     rc, *_ = oracle.blas_build(v, np.zeros(0, dtype=np.uint32))
