@@ -894,8 +894,11 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
 // but warp-synchronous: ballots and popcounts replace the block scan, bins and specials live in registers
 // (lane a*8+k owns bin (a,k); lane c owns candidate c and special c).  No block barriers.
 // ------------------------------------------------------------------------------------------------
+#ifndef T2W_MIN_BLOCKS
+#define T2W_MIN_BLOCKS 3
+#endif
 template <int WCAP>
-__global__ void __launch_bounds__(256, 3) k_t2w(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
+__global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t* ids, const float4* __restrict__ cent,
                                              const float4* __restrict__ box, uint4* recs, uint32_t* A, BuildState* st,
                                              uint32_t epoch) {
     constexpr int EPL = WCAP / 32;
