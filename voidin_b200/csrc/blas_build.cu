@@ -7,10 +7,14 @@
 // closed-form scan + scatter (see DESIGN.md "shuffle in scan form"), and evaluates the candidates from
 // 3x8 exact bins plus the <=21 "unexamined" primitives that the shuffles single out.
 //
-// Three tiers, by node size:
-//   T1  n > 2048   grid-wide, level-synchronous phases over 2048-slot tiles (global memory ping-pong)
-//   T2  33..2048   one block per node from a device task queue (everything in shared memory)
-//   T3  <= 32      one warp per whole sub-tree (registers + 2 KB shared memory), explicit DFS stack
+// Six tiers, by node size (boundaries measured):
+//   k_t1_coop   n > 16384      grid-wide, level-synchronous phases over tiles of 256..2048 slots chosen per level
+//                              (global-memory ping-pong, one cooperative launch for all levels)
+//   k_t2 (big)  2049..16384    one 1024-thread block per node from a device task queue (payload in shared memory)
+//   k_t2        257..2048      one 256-thread block per node, second queue
+//   k_t2w       33..256        one warp per node, third queue
+//   k_t3        9..32          one warp per sub-tree, explicit DFS stack spread over the lanes
+//   k_t4        <= 8           one thread per sub-tree running the reference's sequential loops (t4_seq.cuh)
 // Every node writes one 48-byte record at a collision-free slot (leaf: 2*start, interior: 2*split+1);
 // DFS pre-order pair numbering (blas.rs:110-112) is recovered afterwards from
 //   rank(X) = #interior nodes with start < X.start  +  #ancestors of X sharing X.start
