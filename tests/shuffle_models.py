@@ -1,0 +1,181 @@
+"""Numpy models of the tiled forms of partition_shuffle (crates/bvh/src/blas.rs:168-182) used or planned by the grid tier
+of the CUDA BLAS build.  Test infrastructure only (imported by tests/test_oracle.py); nothing here is on a product path.
+
+`two_phase`  the form k_t1_coop runs today: PA builds the part of the rank->position table that can be looked up, a grid
+             barrier, PB gathers from it and scatters.
+`one_phase`  groundwork for DESIGN.md section 9 item 2 (one barrier per shuffle): no global table.  The only elements that
+             change place are the front R's (before the boundary element f) and the back L's (after f):
+                 m-th front R (m >= 1)  ->  position of the (m-1)-th L from the back, minus one   (the 0-th goes to n-1)
+                 k-th L from the back   ->  position of the k-th front R
+             so every move needs one rank-select in a tile on the other side of f.  A tile can answer those for itself
+             from the per-tile L counts (known before the shuffle starts) plus the flags of the partner tile, which it
+             loads.  To keep the number of partner tiles per tile bounded whatever the plane's left fraction is, a move
+             that involves front tile A and back tile B is executed by A if A holds no more R's than B holds L's, else
+             by B: both sides evaluate the same rule from the per-tile counts alone, and a tile that drives a partner
+             spends at most its own element count of that partner's ranks, so it drives ~2 partners per direction.
+             The model executes the shuffle tile by tile under exactly that information budget and reports how many
+             partner tiles every tile had to load."""
+import numpy as np
+
+
+def boundary(L, n, nL):
+    """f and pivot from nL and the flags at nL-1, nL, nL+1 (the closed form the kernels use)."""
+    at = lambda j: int(L[j]) if 0 <= j < n else 0
+    l0, l1, l2 = (at(nL - 1) if nL else 0), at(nL), at(nL + 1)
+    if nL >= 1 and not (nL + 1 <= n and l0 + l1 <= 1):
+        f, lf = nL - 1, l0
+    elif not (nL + 2 <= n and l1 + l2 == 0):
+        f, lf = nL, l1
+    else:
+        f, lf = nL + 1, l2
+    return f, nL - lf
+
+
+def two_phase(flags, tile):
+    """dest[] and pivot as PA + PB compute them, tile by tile (the table is global, as in the kernel)."""
+    n = len(flags)
+    L = np.asarray(flags, dtype=bool)
+    nt = (n + tile - 1) // tile
+    cnt = np.array([int(L[t * tile:(t + 1) * tile].sum()) for t in range(nt)])
+    pre = np.concatenate([[0], np.cumsum(cnt)])
+    nL = int(pre[-1])
+    f, pivot = boundary(L, n, nL)
+    table = np.full(n, -10**9, dtype=np.int64)
+    for t in range(nt):  # PA
+        lf = pre[t]
+        for j in range(t * tile, min(n, (t + 1) * tile)):
+            if L[j]:
+                if j >= nL:
+                    table[n - 1 - (nL - lf - 1)] = j
+                lf += 1
+            elif j <= nL:
+                table[j - lf] = j
+    dest = np.zeros(n, dtype=np.int64)
+    for t in range(nt):  # PB
+        lf = pre[t]
+        for j in range(t * tile, min(n, (t + 1) * tile)):
+            rf = j - lf
+            if j < f:
+                dest[j] = j if L[j] else (n - 1 if rf == 0 else table[n - rf] - 1)
+            elif j == f:
+                dest[j] = pivot
+            else:
+                dest[j] = table[nL - lf - 1] if L[j] else j - 1
+            lf += int(L[j])
+    return dest, pivot
+
+
+def one_phase(flags, tile):
+    """dest[] (-1 where nobody moved the element: a bug), pivot, and the number of partner tiles each tile loaded."""
+    n = len(flags)
+    L = np.asarray(flags, dtype=bool)
+    nt = (n + tile - 1) // tile
+    size = np.array([min(n, (t + 1) * tile) - t * tile for t in range(nt)])
+    cnt = np.array([int(L[t * tile:(t + 1) * tile].sum()) for t in range(nt)])  # published before the shuffle starts
+    pre = np.concatenate([[0], np.cumsum(cnt)])                                # L's before tile t
+    nL = int(pre[-1])
+    f, pivot = boundary(L, n, nL)  # three flag reads, every tile does them for itself
+    dest = np.full(n, -1, dtype=np.int64)
+    moved = np.zeros(n, dtype=np.int64)
+    loads = np.zeros(nt, dtype=np.int64)
+
+    def put(j, d):
+        dest[j] = d
+        moved[j] += 1
+
+    # what a tile may know about another tile without loading it: its L count, hence the rank ranges it holds
+    def r_front_range(t):  # ranks (RF) of the R's of tile t, as [lo, hi): exact for tiles that end before f
+        lo = t * tile - pre[t]
+        return lo, lo + (size[t] - cnt[t])
+
+    def l_back_range(t):  # ranks from the back (LB) of the L's of tile t, as [lo, hi)
+        return nL - pre[t + 1], nL - pre[t]
+
+    def a_drives(a, b):  # the rule both sides evaluate: front tile a, back tile b
+        return (size[a] - cnt[a]) <= cnt[b]
+
+    def load_positions(t):  # "load the flags of tile t": positions of its R's by RF and of its L's by LB
+        lf = pre[t]
+        rpos, lpos = {}, {}
+        for j in range(t * tile, min(n, (t + 1) * tile)):
+            if L[j]:
+                lpos[nL - lf - 1] = j
+                lf += 1
+            else:
+                rpos[j - lf] = j
+        return rpos, lpos
+
+    for x in range(nt):
+        own_r, own_l = load_positions(x)
+        cache = {}
+
+        def partner(t):
+            if t == x:
+                return own_r, own_l
+            if t not in cache:
+                cache[t] = load_positions(t)
+                loads[x] += 1
+            return cache[t]
+
+        def tile_of_l_back(k):  # tile holding the k-th L from the back: per-tile counts only
+            for t in range(nt - 1, -1, -1):
+                lo, hi = l_back_range(t)
+                if lo <= k < hi:
+                    return t
+            raise AssertionError("rank out of range")
+
+        def tile_of_r_front(k):
+            for t in range(nt):
+                lo, hi = r_front_range(t)
+                if lo <= k < hi:
+                    return t
+            raise AssertionError("rank out of range")
+
+        lf = pre[x]
+        for j in range(x * tile, min(n, (x + 1) * tile)):
+            rf = j - lf
+            if j == f:
+                put(j, pivot)
+            elif j < f and L[j]:
+                put(j, j)                      # front L stays
+            elif j > f and not L[j]:
+                put(j, j - 1)                  # back R shifts by one
+            elif j < f:                        # front R number rf
+                if rf == 0:
+                    put(j, n - 1)
+                else:
+                    b = tile_of_l_back(rf - 1)
+                    if b == x or a_drives(x, b):
+                        put(j, partner(b)[1][rf - 1] - 1)
+            else:                              # back L number lb: goes to the rf == lb front R
+                lb = nL - lf - 1
+                a = tile_of_r_front(lb)
+                if a == x or not a_drives(a, x):
+                    put(j, partner(a)[0][lb])
+            lf += int(L[j])
+        # moves this tile executes on behalf of partners that do not drive them
+        # (a) as a front tile for back L's: L_back(k) -> position of my R with RF == k, for the partners b I drive
+        for k, q in own_r.items():
+            if q < f:
+                # my front R number k is the landing place of L_back(k), if that L exists behind f
+                if k < nL:
+                    try:
+                        b = tile_of_l_back(k)
+                    except AssertionError:
+                        b = None
+                    if b is not None and b != x and a_drives(x, b):
+                        p = partner(b)[1].get(k)
+                        if p is not None and p > f:
+                            put(p, q)
+        # (b) as a back tile for front R's: R_front(m) -> (position of my L with LB == m-1) - 1
+        for k, q in own_l.items():
+            if q > f:
+                try:
+                    a = tile_of_r_front(k + 1)
+                except AssertionError:
+                    a = None
+                if a is not None and a != x and not a_drives(a, x):
+                    p = partner(a)[0].get(k + 1)
+                    if p is not None and p < f:
+                        put(p, q - 1)
+    return dest, pivot, loads, moved

@@ -125,6 +125,42 @@ def test_kernel_form_of_the_shuffle_equals_sequential(oracle):
         assert (out == ids).all(), (flags, out, ids)
 
 
+def test_tiled_shuffle_models_equal_sequential(oracle):
+    """The tiled two-phase form the grid tier runs, and the one-phase form planned for it (no global table, every move
+    executed by the lighter of the two tiles it involves): both must reproduce partition_shuffle on any flag vector and
+    tile size; the one-phase form must also keep the number of partner tiles a tile loads small whatever the left
+    fraction of the plane is."""
+    import shuffle_models as M
+    rng = np.random.default_rng(11)
+    worst = 0
+    cases = []
+    for trial in range(600):
+        n = int(rng.integers(1, 400))
+        tile = int(rng.choice([4, 8, 16, 32]))
+        kind = trial % 3
+        if kind == 0:    # random order, any left fraction (extreme ones included)
+            flags = (rng.random(n) < rng.choice([0.01, 0.05, 0.125, 0.5, 0.875, 0.95, 0.99, rng.random()])).astype(np.uint8)
+        elif kind == 1:  # the order the previous plane of the same axis leaves behind: an all-L front, then a mix
+            cut = int(rng.integers(0, n + 1))
+            flags = np.concatenate([np.ones(cut, np.uint8), (rng.random(n - cut) < rng.random()).astype(np.uint8)])
+        else:            # all L / all R / a single odd one out
+            flags = np.full(n, trial % 2, np.uint8)
+            if n > 2 and trial % 4 < 2:
+                flags[int(rng.integers(0, n))] ^= 1
+        cases.append((flags, tile))
+    for flags, tile in cases:
+        n = len(flags)
+        piv, ids = oracle.shuffle_seq(np.arange(n, dtype=np.uint32), flags)
+        want = np.empty(n, dtype=np.int64)
+        want[ids.astype(np.int64)] = np.arange(n)  # want[j] = destination of the element that starts at j
+        d2, p2 = M.two_phase(flags, tile)
+        assert p2 == piv and (d2 == want).all(), (flags, tile)
+        d1, p1, loads, moved = M.one_phase(flags, tile)
+        assert p1 == piv and (moved == 1).all() and (d1 == want).all(), (flags, tile, d1, want, moved)
+        worst = max(worst, int(loads.max()) if len(loads) else 0)
+    assert worst <= 6, worst
+
+
 def test_empty_and_invalid_inputs(oracle):
     v, idx = S.soup(4, 1, 0.05)
     rc, *_ = oracle.blas_build(v, np.zeros(0, dtype=np.uint32))
