@@ -38,15 +38,12 @@ constexpr int T3_MAX = 32;
 #define T4_MAX_V 8
 #endif
 constexpr int T4_MAX = T4_MAX_V;
-// 1: the thread-tier task list is sorted by sub-tree size before k_t4 runs (k_t4_sort)
-#ifndef T4_SORT
-#define T4_SORT 0  // measured: the sort costs 0.1 ms and k_t4 takes as long as before (it is bound by its longest task)
-#endif
 static_assert(T4_MAX == 0 || (T4_MAX >= 4 && T4_MAX <= 16) || T4_MAX == 32, "T4_MAX_V must be 0, 4..16 or 32");
 // Other forms of the small-sub-tree tiers that were built, verified bit-exact and measured slower on B200 (dragon-class,
 // commit ac13e1f): all nodes of one depth as lane segments of one warp (1.42 ms vs 1.34 ms: SAH sub-trees are
 // deep, not bushy, and a pass costs as much as a node visit); sub-trees through k_t2w's queue (2.94 ms vs 2.46 ms for the
-// two tiers); thread tier limited to whole waves of sm_count x T4_THREADS tasks (1.22 ms vs 1.24 ms).
+// two tiers); thread tier limited to whole waves of sm_count x T4_THREADS tasks (1.22 ms vs 1.24 ms); thread-tier task
+// list counting-sorted by size first (+0.1 ms for the sort, k_t4 unchanged: it is bound by its longest task).
 constexpr int T4_CAP = T4_MAX ? T4_MAX : 16;
 // 8 words per slot per thread: <= 229 376 B of shared memory per block; 768 threads is the register limit (78 regs)
 constexpr int T4_THREADS_SMEM = (229376 / (32 * T4_CAP)) / 32 * 32;
@@ -55,11 +52,6 @@ constexpr int T4_THREADS = T4_THREADS_SMEM < 768 ? T4_THREADS_SMEM : 768;
 #define T2W_CAP_V 256
 #endif
 constexpr int T2W_CAP = T2W_CAP_V;  // warp-per-node tier: 33..T2W_CAP
-// 1: grid tier PA publishes the boundary element from nL and three flags (one thread per node) and writes only the
-// table entries that can be looked up; 0: every thread evaluates the front-examined predicate
-#ifndef T1_CLOSED_F
-#define T1_CLOSED_F 1
-#endif
 // 1: PB takes the tile's ballots and warp prefix bases from PA (288 B per tile) instead of recomputing them
 #ifndef T1_PB_REUSE
 #define T1_PB_REUSE 1
@@ -465,28 +457,6 @@ __global__ void __launch_bounds__(BD, 1) k_t4(Queues Q, const Task* __restrict__
         }
         const uint32_t err = t4_core<CAP>(t, m, reinterpret_cast<const T4Cent*>(cent), ids, reinterpret_cast<T4Rec*>(recs), A);
         if (err) atomicOr(&st->err, DERR_DEGENERATE);
-    }
-}
-
-// Counting sort of the thread-tier task list by sub-tree size, largest first (one block; the list is a few MB).  A warp
-// of k_t4 then starts on 32 sub-trees of the same size, so its lanes run the same trip counts for the root visit and
-// similar ones below it, and the long tasks start first.
-__global__ void __launch_bounds__(1024) k_t4_sort(const Task* __restrict__ in, Task* __restrict__ out, uint32_t cap,
-                                                  const BuildState* st) {
-    __shared__ uint32_t s_cnt[T4_CAP + 1], s_cur[T4_CAP + 1];
-    const uint32_t n_tasks = min(st->t4_count, cap);
-    if (threadIdx.x <= T4_CAP) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_tasks; i += blockDim.x) atomicAdd(&s_cnt[min(in[i].n, (uint32_t)T4_CAP)], 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int k = T4_CAP; k >= 0; --k) { s_cur[k] = acc; acc += s_cnt[k]; }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_tasks; i += blockDim.x) {
-        const Task t = in[i];
-        out[atomicAdd(&s_cur[min(t.n, (uint32_t)T4_CAP)], 1u)] = t;
     }
 }
 
@@ -1517,7 +1487,6 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
             for (int w2 = 0; w2 < T1_THREADS / 32; ++w2) { tile_lf += s_pre[w2]; nL += s_tot[w2]; }
             if (tid == 0) g.tileLF[tile] = tile_lf;
         }
-#if T1_CLOSED_F
         // The boundary element needs no search: pred(j) <=> j + 2 <= n && j + L(j) + L(j+1) <= nL (the #L-before terms
         // cancel), true for every j <= nL - 2 and false from nL + 1 on, so f is one of nL-1, nL, nL+1 and follows from nL
         // and three flags.  One thread per node publishes {nL, f, pivot}; nobody else evaluates pred.
@@ -1552,48 +1521,6 @@ __device__ __forceinline__ void p_t1_table(const T1Args& g, int c, const uint16_
                 else if (j <= nL) g.table[start + (j - LF)] = j;
             }
         }
-#else
-        // flag of the element just before this warp's first slot (needed for the transition test)
-        uint32_t Lprev = 0;
-        if (lane == 0 && jw > 0 && jw <= n) Lprev = ((((uint32_t)fl[start + jw - 1] >> (3 * a)) & 7u) < b) ? 1u : 0u;
-        uint32_t bal[EPT], LFv[EPT];
-        t1_prefix<EPT>(n, j0, a, b, tile_lf, s_w, bal, LFv, fw, ept);
-        uint32_t prev_pred_bit31 = 0;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            if (i >= (int)ept) break;
-            const uint32_t j = jw + i * 32 + lane;
-            bool pred = false;
-            uint32_t Lbit = 0;
-            if (j < n) {
-                Lbit = (bal[i] >> lane) & 1u;
-                const uint32_t LF = LFv[i], RF = j - LF;
-                uint32_t Lnext;
-                if (lane < 31) Lnext = (bal[i] >> (lane + 1)) & 1u;
-                else if (i + 1 < (int)ept) Lnext = bal[(i + 1 < EPT) ? i + 1 : i] & 1u;
-                else Lnext = (j + 1 < n) ? (((((uint32_t)fl[start + j + 1] >> (3 * a)) & 7u) < b) ? 1u : 0u) : 0u;
-                const uint32_t LBB = nL - LF - Lbit - Lnext;
-                pred = (j + 2 <= n) && (LBB >= RF);
-                if (Lbit) g.table[start + n - 1 - (nL - LF - 1)] = j;
-                else g.table[start + RF] = j;
-            }
-            const uint32_t pb = __ballot_sync(FULL_MASK, pred);
-            if (j < n && !pred) {
-                bool prev;
-                if (lane > 0) prev = (pb >> (lane - 1)) & 1u;
-                else if (i > 0) prev = prev_pred_bit31 != 0;
-                else if (j == 0) prev = true;
-                else {
-                    // pred(j-1) from this element's prefix counts: LF(j-1) = LF(j) - L(j-1)
-                    const uint32_t LFp = LFv[i] - Lprev, RFp = (j - 1) - LFp;
-                    const uint32_t LBBp = nL - LFp - Lprev - Lbit;
-                    prev = (j + 1 <= n) && (LBBp >= RFp);
-                }
-                if (prev) g.sc[node].sh[c] = make_uint4(nL, j, nL - Lbit, 0);
-            }
-            prev_pred_bit31 = (pb >> 31) & 1u;
-        }
-#endif
         __syncthreads();
     }
 }
@@ -1630,7 +1557,7 @@ __device__ __forceinline__ void p_t1_scatter(const T1Args& g, int c, const uint3
         const uint4 sh = g.sc[node].sh[c];
         const uint32_t nL = sh.x, f = sh.y, pivot = sh.z;
         uint32_t bal[EPT], LFv[EPT];
-#if T1_PB_REUSE && T1_CLOSED_F
+#if T1_PB_REUSE
         {
             const uint32_t* pb = g.pbal + ((size_t)tile * (T1_THREADS / 32) + warp) * 9;
             uint32_t running = pb[0];
@@ -2301,7 +2228,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
              *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr, *t4s = nullptr;
+    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -2322,7 +2249,6 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         qw = c.take<Task>(qw_cap);
         t3 = c.take<Task>(t3_cap);
         t4 = c.take<Task>(t4_cap);
-        t4s = c.take<Task>(T4_SORT ? t4_cap : 16u);
         lv[0] = c.take<LevelNode>(max_large);
         lv[1] = c.take<LevelNode>(max_large);
         sc = c.take<NodeScratch>(max_large);
@@ -2426,11 +2352,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
             CU_CHECK(ctx, cudaFuncSetAttribute(k_t4<T4_CAP, T4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
             ctx->t4_ready = true;
         }
-        if (T4_SORT) {
-            k_t4_sort<<<1, 1024, 0, stream>>>(t4, t4s, t4_cap, st);
-            launches++;
-        }
-        k_t4<T4_CAP, T4_THREADS><<<ctx->sm_count, T4_THREADS, T4_SMEM, stream>>>(Q, T4_SORT ? t4s : t4, ids0, cent, box, recs, A, st);
+        k_t4<T4_CAP, T4_THREADS><<<ctx->sm_count, T4_THREADS, T4_SMEM, stream>>>(Q, t4, ids0, cent, box, recs, A, st);
         launches++;
     }
     if (prof) cudaEventRecord(ctx->ev[4], stream);
