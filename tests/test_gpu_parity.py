@@ -356,6 +356,25 @@ def test_blas_batch_forest_build_equals_per_mesh_builds(ctx, oracle):
     assert (sc.indices.cpu().numpy().view(np.uint32) == inds).all()
 
 
+def test_blas_forest_with_more_grid_tiles_than_blocks(ctx, oracle):
+    """A forest whose grid-tier levels have more tiles than the cooperative kernel has blocks while no single node is large
+    enough for the tile-scan path: every block walks several tiles per phase (PA leaves each tile's ballots for PB)."""
+    import torch
+    from voidin_b200 import multi_gpu as MG
+
+    meshes = [S.soup(30_000 + 997 * k, 400 + k, 0.02) for k in range(36)]  # 36 x ~15 tiles of 2048 > 444 blocks
+    dev = torch.device("cuda", 0)
+    tm = [(torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(i.view(np.int32)).to(dev)) for v, i in meshes]
+    outs = MG.cuda_build_batch_fn(ctx)(tm)
+    st = ctx.last_build_stats()
+    assert st["grid_levels"] >= 1 and st["grid_nodes"] >= len(meshes)
+    for (v, idx), (nodes, perm) in zip(meshes, outs):
+        rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+        assert rc == 0
+        assert nodes.cpu().numpy().tobytes() == onodes.tobytes()
+        assert (perm.cpu().numpy().view(np.uint32) == oidx).all()
+
+
 def test_blas_batch_rejects_bad_mesh_table(ctx):
     import torch
     from voidin_b200.types import MESH_INFO
