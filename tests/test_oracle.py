@@ -71,7 +71,7 @@ def test_closed_form_shuffle_equals_sequential(oracle):
 
 
 def _shuffle_kernel_form(flags):
-    """The shuffle as the CUDA tiers compute it since the end of round 1 (p_t1_table / k_t2 / k_t2w in blas_build.cu):
+    """The shuffle as the CUDA tiers compute it since the end of round 1 (p_t1_table in blas_grid.cuh, k_t2 / k_t2w in blas_block.cuh):
     the boundary element f from nL and the flags at nL-1, nL, nL+1 instead of a predicate per slot, and a rank->position
     table that only holds the entries that can be looked up (R's at j <= nL, L's at j >= nL); every other entry is
     poisoned here so that a look-up outside the filter fails the test."""
