@@ -10,14 +10,15 @@
 #include "../../voidin_b200/csrc/t4_seq.cuh"
 
 namespace {
-constexpr int CAP = 32;
 constexpr uint32_t TF_ROOT = 2u;
 
 struct Node { uint32_t w[8]; };  // {min[3], left_first, max[3], count}
 }  // namespace
 
-extern "C" int t4_host_build(const float* V, const uint32_t* I, uint32_t n, uint32_t stride, uint32_t column,
-                             uint32_t* nodes_out /* 8 words x 2n */, uint32_t* n_nodes_out, uint32_t* order_out) {
+// CAP = capacity the builder is instantiated with: 8 is what libbvh_cuda.so ships (k_t4<8,768>), 32 covers every size.
+template <int CAP>
+static int build_with_cap(const float* V, const uint32_t* I, uint32_t n, uint32_t stride, uint32_t column,
+                          uint32_t* nodes_out /* 8 words x 2n */, uint32_t* n_nodes_out, uint32_t* order_out) {
     if (n == 0 || n > (uint32_t)CAP || stride == 0 || column >= stride) return -1;
     std::vector<float> f((size_t)6 * CAP * stride, 0.0f);
     std::vector<uint32_t> u((size_t)2 * CAP * stride, 0u);
@@ -71,4 +72,19 @@ extern "C" int t4_host_build(const float* V, const uint32_t* I, uint32_t n, uint
     *n_nodes_out = M;
     for (uint32_t i = 0; i < n; ++i) order_out[i] = ids[i];
     return 0;
+}
+
+extern "C" int t4_host_build_cap(const float* V, const uint32_t* I, uint32_t n, uint32_t stride, uint32_t column,
+                                 uint32_t* nodes_out, uint32_t* n_nodes_out, uint32_t* order_out, uint32_t cap) {
+    switch (cap) {
+        case 8: return build_with_cap<8>(V, I, n, stride, column, nodes_out, n_nodes_out, order_out);
+        case 16: return build_with_cap<16>(V, I, n, stride, column, nodes_out, n_nodes_out, order_out);
+        case 32: return build_with_cap<32>(V, I, n, stride, column, nodes_out, n_nodes_out, order_out);
+        default: return -1;
+    }
+}
+
+extern "C" int t4_host_build(const float* V, const uint32_t* I, uint32_t n, uint32_t stride, uint32_t column,
+                             uint32_t* nodes_out, uint32_t* n_nodes_out, uint32_t* order_out) {
+    return build_with_cap<32>(V, I, n, stride, column, nodes_out, n_nodes_out, order_out);
 }

@@ -25,15 +25,16 @@ def t4():
     return C.CDLL(LIB)
 
 
-def run(t4, v, idx, stride=1, column=0):
+def run(t4, v, idx, stride=1, column=0, cap=32):
     v = np.ascontiguousarray(v, dtype=np.float32)
     idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
     n = idx.size // 3
     nodes = np.zeros(2 * n, dtype=O.BVH_NODE)
     order = np.zeros(n, dtype=np.uint32)
     m = C.c_uint32(0)
-    rc = t4.t4_host_build(v.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(stride),
-                          C.c_uint32(column), nodes.ctypes.data_as(C.c_void_p), C.byref(m), order.ctypes.data_as(C.c_void_p))
+    rc = t4.t4_host_build_cap(v.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(stride),
+                              C.c_uint32(column), nodes.ctypes.data_as(C.c_void_p), C.byref(m), order.ctypes.data_as(C.c_void_p),
+                              C.c_uint32(cap))
     return rc, nodes[: m.value], order
 
 
@@ -54,6 +55,17 @@ def test_soups_all_sizes(t4):
         for seed in range(12):
             v, i = S.soup(n, 1000 * n + seed, 0.2)
             check(t4, v, i)
+
+
+def test_shipped_capacity_eight(t4):
+    """k_t4 is instantiated with a capacity of 8 primitives in libbvh_cuda.so (768 threads per block): the same
+    instantiation, with the block's [word][thread] layout, on every size it takes."""
+    rng = np.random.default_rng(8)
+    for n in range(1, 9):
+        for seed in range(40):
+            v, i = S.soup(n, 50_000 + 100 * n + seed, float(rng.choice([0.5, 0.2, 0.02])))
+            check(t4, v, i, cap=8)
+            check(t4, v, i, cap=8, stride=768, column=int(rng.integers(0, 768)))
 
 
 def test_layout_stride_and_column(t4):
