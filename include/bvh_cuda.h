@@ -108,7 +108,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx);
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
 /* Total kernels launched through this context since creation. */
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
-int bvh_cuda_abi_version(void); /* 2 */
+int bvh_cuda_abi_version(void); /* 3 */
 /* enable != 0: later BLAS builds record per-phase CUDA-event timings into BvhCudaBuildStats (a few extra event
  * records per build, no extra synchronisation). */
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable);

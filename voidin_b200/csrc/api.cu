@@ -92,7 +92,7 @@ struct DevBuf {
 
 extern "C" {
 
-int bvh_cuda_abi_version(void) { return 2; }  // 2: BvhCudaBuildStats grew (ms_thread, thread_tasks)
+int bvh_cuda_abi_version(void) { return 3; }  // 2: BvhCudaBuildStats grew (ms_thread, thread_tasks); 3: again (grid_nodes, grid_interior_prims)
 
 int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
     if (!out) return BVH_CUDA_EINVAL;
