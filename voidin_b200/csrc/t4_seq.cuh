@@ -216,9 +216,15 @@ T4_HD uint32_t t4_core(const T4Task& t, const T4Mem<CAP>& m, const T4Cent* cent,
             float best_cost = 3.402823466e+38f;  // f32::MAX (blas.rs:140)
             uint32_t best = 0xFFFFFFFFu, best_p = 0;
             uint32_t prev_set = 0;  // primitives on the left of the previous candidate (never empty when evaluated)
+            uint32_t prev_p = 0;    // pivot of the previous plane of the same axis
             for (uint32_t c = 0; c < 21; ++c) {
                 const uint32_t a = c / 7, b = c % 7 + 1;
-                const uint32_t p = t4_shuffle<CAP>(m, s, n, 5 + 3 * a, b);
+                // From the second plane of an axis on, everything before the previous pivot is on the left of this plane
+                // too (the planes grow with b and partition_shuffle leaves [0, pivot) all-left): the front cursor would
+                // walk over that prefix without a swap, so the shuffle starts behind it.
+                const uint32_t off = (b == 1) ? 0u : prev_p;
+                const uint32_t p = off + t4_shuffle<CAP>(m, s + off, n - off, 5 + 3 * a, b);
+                prev_p = p;
                 // The cost (blas.rs:149-155) depends only on WHICH primitives ended up left of the pivot.  An empty left
                 // side costs NaN (area of the inverted box is +inf, times 0) and a candidate that splits exactly like
                 // the previous one costs the same; neither can win under the strict < of blas.rs:156.
