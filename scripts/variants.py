@@ -1,7 +1,9 @@
 """A/B timing of compile-time variants of libbvh_cuda.so on the GPU box.  For every voidin_b200/variants/libbvh_cuda_<name>.so
 (built with `make -C voidin_b200/csrc variant NAME=<name> EXTRA=-D...`) a child process builds the dragon-class mesh a few
 times with per-phase timing, checks nodes and primitive order byte-for-byte against the CPU oracle (computed once), and
-runs the small-mesh parity ladder.  Usage: python scripts/variants.py [name ...]"""
+runs the small-mesh parity ladder.  Usage: python scripts/variants.py [name[:ENV=VAL[,ENV=VAL]] ...]
+(a name may carry extra environment for that run, e.g. base:BVH_CUDA_T1_GRID=296).  The round-1 results are tabulated in
+profiles/r01_build_variants_ab.txt."""
 import glob, json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
