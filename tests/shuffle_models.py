@@ -14,8 +14,34 @@ of the CUDA BLAS build.  Test infrastructure only (imported by tests/test_oracle
              by B: both sides evaluate the same rule from the per-tile counts alone, and a tile that drives a partner
              spends at most its own element count of that partner's ranks, so it drives ~2 partners per direction.
              The model executes the shuffle tile by tile under exactly that information budget and reports how many
-             partner tiles every tile had to load."""
+             partner tiles every tile had to load.
+`axis_with_frozen_prefix`  groundwork for DESIGN.md section 9 item 0: the buffer plan that lets the ping-pong tiers shuffle
+             only the suffix behind the previous pivot on the 2nd..7th plane of an axis."""
 import numpy as np
+
+
+def axis_with_frozen_prefix(ids, k_axis, shuffle):
+    """Buffer plan for DESIGN.md section 9 item 0 in the ping-pong tiers (grid, block, warp): the 7 planes of one axis with
+    only the suffix behind the previous pivot taking part in the ping-pong.  `ids`: the order before the axis' first plane;
+    `k_axis[id]`: the primitive's plane count on this axis; `shuffle(ids, flags_by_id) -> (pivot, ids)`: the sequential
+    partition_shuffle.  Shuffle b reads the suffix [pivot_{b-1}, n) from the current buffer and writes it to the other one,
+    so segment [pivot_{b-1}, pivot_b) stays frozen in the buffer shuffle b wrote; one merge pass at the end copies the
+    segments that are stale in the final buffer.  Returns (pivots, merged order, slots copied by the merge)."""
+    n = len(ids)
+    buf = [np.array(ids, dtype=np.uint32), np.full(n, 0xFFFFFFFF, dtype=np.uint32)]  # the other buffer holds garbage
+    cur, off = 0, 0
+    pivots, owner = [], np.zeros(n, dtype=np.int64)  # owner[j]: buffer that holds the valid value of slot j
+    for b in range(1, 8):
+        fl = (np.asarray(k_axis) < b).astype(np.uint8)
+        piv, out = shuffle(buf[cur][off:], fl) if n > off else (0, buf[cur][off:])
+        buf[cur ^ 1][off:] = out
+        owner[off:] = cur ^ 1
+        cur ^= 1
+        off += piv
+        pivots.append(off)
+    stale = owner != cur
+    buf[cur][stale] = buf[cur ^ 1][stale]  # the merge pass (before an axis change, the bins, or the final shuffle)
+    return pivots, buf[cur], int(stale.sum())
 
 
 def boundary(L, n, nL):

@@ -149,6 +149,27 @@ def test_same_axis_planes_only_move_the_suffix(oracle):
     assert 0.55 < active / total < 0.70
 
 
+def test_frozen_prefix_buffer_plan_equals_full_shuffles(oracle):
+    """The ping-pong plan for the suffix-only shuffles (shuffle_models.axis_with_frozen_prefix): pivots and the merged
+    order after an axis must be those of the seven full shuffles; the merge pass copies well under one array."""
+    import shuffle_models as M
+    rng = np.random.default_rng(33)
+    copied = total = 0
+    for trial in range(800):
+        n = int(rng.integers(1, 300))
+        k = rng.integers(0, 8, size=n) if trial % 4 else np.full(n, rng.integers(0, 8))
+        ids = rng.permutation(n).astype(np.uint32)
+        want, pivs = ids, []
+        for b in range(1, 8):
+            piv, want = oracle.shuffle_seq(want, (k < b).astype(np.uint8))
+            pivs.append(piv)
+        got_p, got, moved = M.axis_with_frozen_prefix(ids, k, oracle.shuffle_seq)
+        assert got_p == pivs and (got == want).all(), (n, k, got_p, pivs)
+        copied += moved
+        total += n
+    assert copied < 0.6 * total
+
+
 def test_tiled_shuffle_models_equal_sequential(oracle):
     """The tiled two-phase form the grid tier runs, and the one-phase form planned for it (no global table, every move
     executed by the lighter of the two tiles it involves): both must reproduce partition_shuffle on any flag vector and
