@@ -7,7 +7,10 @@
  * Conventions
  *   - Plain pointers and sizes only.  "host" entry points take host pointers and do their own H2D/D2H copies;
  *     the `_dev` twins take device pointers plus a `cudaStream_t` (passed as void*) and leave results on the
- *     device.  Work of one context is serialised on the stream it is given.
+ *     device.  Work of one context is serialised on the stream it is given.  A context and a scene each own
+ *     mutable device scratch (build workspace, persistent-warp ray counter, deferral list): do NOT issue calls on
+ *     the same context, or traces of the same scene, concurrently from several streams or threads — use one
+ *     context (and one scene wrap) per stream.  Different contexts are independent.
  *   - Every function returns a status: 0 ok, <0 error.  Nothing unwinds, nothing prints.  The reference has
  *     no error channel — it panics (blas.rs:84 on N=0, mesh/mod.rs:321 on len%3!=0, OOB on bad indices) or
  *     never terminates on degenerate input (blas.rs:115,139); those cases map to EINVAL / EDEGENERATE here.

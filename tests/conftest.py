@@ -24,4 +24,7 @@ def oracle():
 def ctx():
     import voidin_b200 as vb
 
-    return vb.Context(0)
+    try:
+        return vb.Context(0)
+    except (vb.BvhCudaError, OSError, ImportError) as e:  # CPU-only box: the gpu-marked tests are skipped, not errors
+        pytest.skip(f"no CUDA device / libbvh_cuda.so unavailable: {e}")

@@ -196,9 +196,13 @@ __global__ void __launch_bounds__(256) k_roots(const uint32_t* __restrict__ tbas
                                                uint32_t lv_cap, BuildState* st, uint32_t epoch) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_meshes) return;
+    // An inconsistent caller mesh table (k_mesh_table) or an out-of-range vertex index (k_setup) has already been
+    // flagged by an earlier launch: post no root at all, so that every tier exits at once and the build returns EINVAL
+    // without ever sizing tiles or queues from a bogus triangle range.
+    if (ld_vol(&st->err) & DERR_BAD_INDEX) return;
     const uint32_t start = tbase[m], n = tbase[m + 1] - tbase[m];
     const uint32_t flags = TF_ROOT | (m << TF_MESH_SHIFT);
-    if (n == 0) { atomicOr(&st->err, DERR_BAD_INDEX); return; }
+    if (n == 0 || tbase[m + 1] < start) { atomicOr(&st->err, DERR_BAD_INDEX); return; }
     if (n > T2B_CAP) {
         const uint32_t idx = atomicAdd(&st->lv_count[0], 1u);
         if (idx >= lv_cap) { atomicOr(&st->err, DERR_QUEUE); return; }

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256, 4) k_t3(Queues Q, uint32_t* ids,
     __shared__ uint8_t s_tab[8][32];
     __shared__ uint16_t s_pay[8][32];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t n_tasks = st->t3_count;
+    const uint32_t n_tasks = min(st->t3_count, Q.t3_cap);  // push_child keeps counting after an overflow (DERR_QUEUE)
     const T3Smem sm{s_box[w], s_cent[w], s_gid[w], s_tab[w], s_pay[w]};
     for (uint32_t ti = blockIdx.x * 8 + w; ti < n_tasks; ti += gridDim.x * 8) {
         const Task t = tasks[ti];

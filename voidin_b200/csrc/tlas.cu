@@ -350,6 +350,9 @@ int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_i
     const size_t need = 256 + sizeof(float) * 6 * (size_t)I + 256 + sizeof(uint32_t) * (size_t)I + 256;
     int rc = ctx_reserve(ctx, need);
     if (rc) return rc;
+    // the workspace is shared with the BLAS builder: its "last order" snapshot is overwritten from here on
+    ctx->d_last_order = nullptr;
+    ctx->last_n = 0;
     char* base = (char*)ctx->ws;
     uint32_t* err = (uint32_t*)base;
     float* slot_box = (float*)(base + 256);

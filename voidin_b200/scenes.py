@@ -438,3 +438,31 @@ def load_gltf_primitives(path: str):
             idx = np.ascontiguousarray(accessor(prim["indices"]).reshape(-1).astype(np.uint32))
             out.append((v, idx[: idx.size // 3 * 3]))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE config 3 inputs (shared by bench.py, the GPU parity tests and tests/golden/make_golden_large.py)
+# ----------------------------------------------------------------------------------------------
+def config3_meshes():
+    """bunny-class, dragon-class and a DamagedHelmet-sized stand-in for ferris3d (the real assets are absent from the
+    reference checkout, .MISSING_LARGE_BLOBS)."""
+    return [bunny_class(), dragon_class(), displaced_sphere(62, 124, 3)]
+
+
+def pooled_mesh_info(meshes) -> np.ndarray:
+    """MeshInfo of `meshes` pooled in order, as MeshPool::add lays them out (crates/pools/src/mesh/mod.rs:322-347);
+    bvh_index is left 0 (the forest build fills it in)."""
+    info = np.zeros(len(meshes), dtype=MESH_INFO)
+    info["index_count"] = [i.size for _, i in meshes]
+    info["vertex_offset"] = np.concatenate([[0], np.cumsum([v.shape[0] for v, _ in meshes])[:-1]])
+    info["base_index"] = np.concatenate([[0], np.cumsum(info["index_count"])[:-1]])
+    info["min"] = [v.min(0) for v, _ in meshes]
+    info["max"] = [v.max(0) for v, _ in meshes]
+    return info
+
+
+def config3_scene_inputs(n_inst: int, meshes=None):
+    """(instances, mesh_info) of config 3: `n_inst` instances, mesh uniform, T(uniform [-500,500]^3) R(uniform
+    quaternion) S(uniform [0.5,2]), seed 3."""
+    meshes = config3_meshes() if meshes is None else meshes
+    return random_instances(n_inst, len(meshes), seed=3, extent=500.0), pooled_mesh_info(meshes)
