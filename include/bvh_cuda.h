@@ -99,9 +99,11 @@ typedef struct BvhCudaBuildStats {
     float ms_total;
     float ms_thread;             /* k_t4: thread-per-sub-tree kernel (one launch) */
     uint32_t thread_tasks;       /* small sub-trees handled one thread each (k_t4) */
-    uint32_t grid_nodes;         /* interior nodes split by the grid-wide tier */
+    uint32_t grid_nodes;         /* interior nodes split by the grid-wide and cluster tiers (n > 16384) */
+    uint32_t cluster_tasks;      /* nodes handled one thread-block cluster each (16385..262144); also counted in grid_nodes */
+    uint64_t grid_interior_prims;/* sum of their triangle counts (the S of the large-node tiers' algorithmic bytes) */
+    float ms_cluster;            /* k_tc: cluster-per-node task-queue kernel (one launch) */
     uint32_t reserved0;
-    uint64_t grid_interior_prims;/* sum of their triangle counts (the S of the grid tier's algorithmic bytes) */
 } BvhCudaBuildStats;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -111,7 +113,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx);
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
 /* Total kernels launched through this context since creation. */
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
-int bvh_cuda_abi_version(void); /* 3 */
+int bvh_cuda_abi_version(void); /* 4 */
 /* enable != 0: later BLAS builds record per-phase CUDA-event timings into BvhCudaBuildStats (a few extra event
  * records per build, no extra synchronisation). */
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bvh_cuda.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.bvh_cuda_abi_version() == 3
+    assert lib.bvh_cuda_abi_version() == 4
 
 
 def test_struct_layouts_match_the_reference():
@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_reference():
     assert vb.TLAS_NODE.fields["left_right"][1] == 12 and vb.TLAS_NODE.fields["instance_idx"][1] == 28
     assert vb.INSTANCE.fields["inv_transform"][1] == 64 and vb.INSTANCE.fields["mesh"][1] == 128
     assert vb.MESH_INFO.fields["vertex_offset"][1] == 32 and vb.MESH_INFO.fields["bvh_index"][1] == 36
-    assert C.sizeof(_lib.BuildStats) == 96
+    assert C.sizeof(_lib.BuildStats) == 104
 
 
 def test_null_context_calls_are_rejected_not_crashing():
@@ -87,7 +87,7 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
     cxx_src.write_text(
         '#include "bvh_cuda.hpp"\n#include <cstdio>\n'
         "int main(){ try { bvh_cuda::Context c(0); std::puts(\"ctx\"); } catch (const bvh_cuda::Error& e) { std::puts(\"nogpu\"); }\n"
-        " return bvh_cuda_abi_version() == 3 ? 0 : 1; }\n")
+        " return bvh_cuda_abi_version() == 4 ? 0 : 1; }\n")
     libdir = os.path.join(ROOT, "voidin_b200")
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", inc, str(cxx_src), "-o", str(tmp_path / "t_cxx"), "-L", libdir,
                            "-lbvh_cuda", f"-Wl,-rpath,{libdir}"])

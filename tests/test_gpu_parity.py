@@ -46,8 +46,43 @@ def test_blas_bit_exact_grid_tier(ctx, oracle, n, seed, edge):
     rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
     assert rc == 0 and bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
     st = ctx.last_build_stats()
-    assert st["grid_levels"] >= (2 if n >= 100_000 else 1) and st["big_block_tasks"] > 0 and st["block_tasks"] > 0
+    # nodes above 16 384 triangles: cluster tier up to 262 144, grid tier (level-synchronous) above that
+    assert st["cluster_tasks"] >= (2 if n >= 100_000 else 1) and st["grid_levels"] >= (1 if n > 262_144 else 0)
+    assert st["big_block_tasks"] > 0 and st["block_tasks"] > 0
     assert st["warp_node_tasks"] > 0 and st["warp_tasks"] > 0 and st["thread_tasks"] > 0
+
+
+def _build_in_child(meshes, mode, env):
+    """Builds `meshes` in a child process with extra environment (tests/_child_build.py); returns ([(nodes, perm)], stats)."""
+    import subprocess
+    import sys
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        src, dst = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
+        np.savez(src, **{f"v{i}": m[0] for i, m in enumerate(meshes)}, **{f"i{i}": m[1] for i, m in enumerate(meshes)})
+        subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_child_build.py"), src, dst, mode],
+                       check=True, env=dict(os.environ, **env), timeout=600)
+        d = np.load(dst)
+        outs = [(d[f"n{i}"].copy(), d[f"g{i}"].copy()) for i in range(len(meshes))]
+        return outs, json.loads(bytes(d["stats"]).decode())
+
+
+def test_blas_grid_tier_alone_still_exact_without_the_cluster_tier(oracle):
+    """BVH_CUDA_NO_CLUSTER=1 (A/B switch, read once per process): every node above 16 384 triangles goes through the
+    level-synchronous grid tier, as in round 1 — a single mesh, and a forest whose grid-tier levels have more tiles
+    than the cooperative kernel has blocks (every block walks several tiles per phase)."""
+    v, idx = S.soup(150_000, 7, 0.01)
+    outs, st = _build_in_child([(v, idx)], "single", {"BVH_CUDA_NO_CLUSTER": "1"})
+    rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+    assert st["cluster_tasks"] == 0 and st["grid_levels"] >= 2, st
+    assert rc == 0 and outs[0][0].tobytes() == onodes.tobytes() and (outs[0][1] == oidx).all()
+    meshes = [S.soup(30_000 + 997 * k, 400 + k, 0.02) for k in range(36)]  # 36 x ~15 tiles of 2048 > 444 blocks
+    outs, st = _build_in_child(meshes, "forest", {"BVH_CUDA_NO_CLUSTER": "1"})
+    assert st["cluster_tasks"] == 0 and st["grid_levels"] >= 1 and st["grid_nodes"] >= len(meshes), st
+    for (v, idx), (nodes, perm) in zip(meshes, outs):
+        rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+        assert rc == 0 and nodes.tobytes() == onodes.tobytes() and (perm == oidx).all()
 
 
 def test_blas_context_reuse_across_sizes(ctx, oracle):
@@ -356,9 +391,9 @@ def test_blas_batch_forest_build_equals_per_mesh_builds(ctx, oracle):
     assert (sc.indices.cpu().numpy().view(np.uint32) == inds).all()
 
 
-def test_blas_forest_with_more_grid_tiles_than_blocks(ctx, oracle):
-    """A forest whose grid-tier levels have more tiles than the cooperative kernel has blocks while no single node is large
-    enough for the tile-scan path: every block walks several tiles per phase (PA leaves each tile's ballots for PB)."""
+def test_blas_forest_with_more_cluster_tasks_than_clusters(ctx, oracle):
+    """A forest of 36 roots of 30-65 K triangles: five times more cluster-tier tasks than co-resident clusters, all posted
+    at once by k_roots (the grid-tier twin of this case runs in test_blas_grid_tier_alone_still_exact_without_the_cluster_tier)."""
     import torch
     from voidin_b200 import multi_gpu as MG
 
@@ -367,7 +402,7 @@ def test_blas_forest_with_more_grid_tiles_than_blocks(ctx, oracle):
     tm = [(torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(i.view(np.int32)).to(dev)) for v, i in meshes]
     outs = MG.cuda_build_batch_fn(ctx)(tm)
     st = ctx.last_build_stats()
-    assert st["grid_levels"] >= 1 and st["grid_nodes"] >= len(meshes)
+    assert st["cluster_tasks"] >= len(meshes) and st["grid_nodes"] >= len(meshes)
     for (v, idx), (nodes, perm) in zip(meshes, outs):
         rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
         assert rc == 0

@@ -65,8 +65,10 @@ class BuildStats(C.Structure):
         ("ms_thread", C.c_float),
         ("thread_tasks", C.c_uint32),
         ("grid_nodes", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("cluster_tasks", C.c_uint32),
         ("grid_interior_prims", C.c_uint64),
+        ("ms_cluster", C.c_float),
+        ("reserved0", C.c_uint32),
     ]
 
     def as_dict(self):

@@ -13,6 +13,8 @@ int blas_t2_occupancy();
 int blas_t2b_setup();
 int blas_t2w_occupancy();
 int blas_t1_coop_occupancy();
+int blas_tc_setup(int cluster_size);
+int blas_tc_log(unsigned long long* out, unsigned int cap_rows);
 int blas_t1_timing(unsigned long long* out32);
 int blas_t1_blocks(unsigned long long* out2048);
 
@@ -92,7 +94,7 @@ struct DevBuf {
 
 extern "C" {
 
-int bvh_cuda_abi_version(void) { return 3; }  // 2: BvhCudaBuildStats grew (ms_thread, thread_tasks); 3: again (grid_nodes, grid_interior_prims)
+int bvh_cuda_abi_version(void) { return 4; }  // 2: BvhCudaBuildStats grew (ms_thread, thread_tasks); 3: again (grid_nodes, grid_interior_prims); 4: cluster tier (cluster_tasks, ms_cluster)
 
 int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
     if (!out) return BVH_CUDA_EINVAL;
@@ -120,6 +122,10 @@ int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
     if (blas_t2b_setup() < 1) { bvh_cuda_destroy(ctx); return BVH_CUDA_ECUDA; }
     ctx->t2w_blocks_per_sm = blas_t2w_occupancy();
     ctx->t1_blocks_per_sm = blas_t1_coop_occupancy();
+    for (int cs : {16, 8}) {  // cluster tier: the largest cluster the device can place (16 is a non-portable size)
+        const int nc = blas_tc_setup(cs);
+        if (nc > 0) { ctx->tc_cluster_size = cs; ctx->tc_clusters = nc; break; }
+    }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
@@ -151,6 +157,8 @@ uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->laun
 // Debug only (library built with -DBVH_T1_TIMING): per-phase-kind work / barrier-wait ns of block 0 in the grid tier.
 int bvh_cuda_debug_t1_timing(unsigned long long* out32) { return blas_t1_timing(out32); }
 int bvh_cuda_debug_t1_blocks(unsigned long long* out2048) { return blas_t1_blocks(out2048); }
+// Debug only (-DBVH_TC_TIMING): per-node time stamps of the cluster tier; returns the number of rows (8 u64 each), -1 if not built in.
+int bvh_cuda_debug_tc_log(unsigned long long* out, unsigned int cap_rows) { return blas_tc_log(out, cap_rows); }
 
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable) {
     if (!ctx) return BVH_CUDA_EINVAL;

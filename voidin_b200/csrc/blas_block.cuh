@@ -72,12 +72,11 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
     uint32_t* const q_head = BIG ? &st->b_head : &st->q_head;
     uint32_t* const q_tail = BIG ? &st->b_tail : &st->q_tail;
     uint32_t* const q_pending = BIG ? &st->b_pending : &st->q_pending;
-    // dynamic shared memory: payload ping-pong (bits 0-15 local primitive, 16-24 plane counts, 31 special) and the
-    // rank -> position table.  The local-primitive -> triangle-id map lives in global memory (ids_snap).
+    // dynamic shared memory: payload (bits 0-15 local primitive, 16-24 plane counts, 31 special), shuffled in place, and
+    // the rank -> position table.  The local-primitive -> triangle-id map lives in global memory (ids_snap).
     extern __shared__ uint32_t s_dyn[];
     uint32_t* const s_pay0 = s_dyn;
-    uint32_t* const s_pay1 = s_dyn + CAP;
-    uint16_t* const s_tab = reinterpret_cast<uint16_t*>(s_dyn + 2 * CAP);
+    uint16_t* const s_tab = reinterpret_cast<uint16_t*>(s_dyn + CAP);
     __shared__ uint32_t s_wtot[NW];
     __shared__ uint32_t s_red[NW][12];
     __shared__ uint32_t s_node[12];
@@ -188,19 +187,26 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
         }
         __syncthreads();
 
-        // ---- 3. shuffles ----
-        auto shuffle = [&](int cur, uint32_t a, uint32_t b, int cidx) {
-            const uint32_t* pin = cur ? s_pay1 : s_pay0;
-            uint32_t* pout = cur ? s_pay0 : s_pay1;
+        // ---- 3. shuffles: partition_shuffle (blas.rs:168-182) in closed form, IN PLACE on [s0, n) ----
+        // Plane b of an axis leaves [0, pivot_{b-1}) untouched (the front cursor walks over an all-left prefix without a
+        // swap), so it is the shuffle of the suffix alone; the active range is re-spread over all threads, which is what
+        // shortens the dependent chain: E = ceil(active / THREADS) slots per thread instead of ceil(n / THREADS).
+        // In place: every thread keeps its slots' payloads in registers from the counting pass to the scatter.
+        auto shuffle = [&](uint32_t a, uint32_t b, uint32_t s0, int cidx) -> uint32_t {
+            uint32_t* const p = s_pay0 + s0;
+            const uint32_t act = n - s0;
+            const uint32_t Ea = (act + THREADS - 1) / THREADS, CH = 32 * Ea;
             const uint32_t sh = 16 + 3 * a;
-            uint32_t bal[EPT];
+            uint32_t bal[EPT], pay[EPT];
             uint32_t cnt = 0;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 bal[i] = 0;
-                if (i < (int)E) {
-                    const uint32_t j = warp * CHUNK + i * 32 + lane;
-                    const bool L = (j < n) && (((pin[j] >> sh) & 7u) < b);
+                pay[i] = 0;
+                if (i < (int)Ea) {
+                    const uint32_t j = warp * CH + i * 32 + lane;
+                    if (j < act) pay[i] = p[j];
+                    const bool L = (j < act) && (((pay[i] >> sh) & 7u) < b);
                     bal[i] = __ballot_sync(FULL_MASK, L);
                     cnt += __popc(bal[i]);
                 }
@@ -208,67 +214,71 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
             if (lane == 0) s_wtot[warp] = cnt;
             __syncthreads();  // S1
             // lane w2 reads warp w2's count: total and the sum over the warps before this one by two warp reductions
-            // (a serial walk over 32 counts was a third of a big-block shuffle of a small node)
             const uint32_t wv = (lane < (uint32_t)NW) ? s_wtot[lane] : 0u;
             const uint32_t nL = __reduce_add_sync(FULL_MASK, wv);
             const uint32_t wpre = __reduce_add_sync(FULL_MASK, lane < warp ? wv : 0u);
             // boundary element in closed form (see p_t1_table): f is nL-1, nL or nL+1, decided by three flags
             uint32_t f, Lf;
             {
-                const uint32_t l0 = nL ? ((((pin[nL - 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
-                const uint32_t l1 = (nL < n && (((pin[nL < n ? nL : 0] >> sh) & 7u) < b)) ? 1u : 0u;
-                const uint32_t l2 = (nL + 1 < n && (((pin[nL + 1 < n ? nL + 1 : 0] >> sh) & 7u) < b)) ? 1u : 0u;
-                if (nL >= 1 && !(nL + 1 <= n && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
-                else if (!(nL + 2 <= n && l1 + l2 == 0)) { f = nL; Lf = l1; }
+                const uint32_t l0 = nL ? ((((p[nL - 1] >> sh) & 7u) < b) ? 1u : 0u) : 0u;
+                const uint32_t l1 = (nL < act && (((p[nL < act ? nL : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+                const uint32_t l2 = (nL + 1 < act && (((p[nL + 1 < act ? nL + 1 : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+                if (nL >= 1 && !(nL + 1 <= act && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
+                else if (!(nL + 2 <= act && l1 + l2 == 0)) { f = nL; Lf = l1; }
                 else { f = nL + 1; Lf = l2; }
             }
             const uint32_t pivot = nL - Lf;
             uint32_t running = wpre;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
-                if (i >= (int)E) break;
-                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                if (i >= (int)Ea) break;
+                const uint32_t j = warp * CH + i * 32 + lane;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
-                if (j < n) {
+                if (j < act) {
                     // only front R's (j < f) and back L's (j > f) are looked up
-                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[n - 1 - (nL - LF - 1)] = (uint16_t)j; }
+                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[act - 1 - (nL - LF - 1)] = (uint16_t)j; }
                     else if (j <= nL) s_tab[j - LF] = (uint16_t)j;
                 }
                 running += __popc(bal[i]);
             }
-            __syncthreads();  // S2
+            __syncthreads();  // S2: table complete, and every read of p (counting pass, boundary flags) is done
             running = wpre;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
-                if (i >= (int)E) break;
-                const uint32_t j = warp * CHUNK + i * 32 + lane;
+                if (i >= (int)Ea) break;
+                const uint32_t j = warp * CH + i * 32 + lane;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
                 running += __popc(bal[i]);
-                if (j < n) {
-                    uint32_t pay = pin[j];
+                if (j < act) {
                     const uint32_t Lbit = (bal[i] >> lane) & 1u;
                     const uint32_t RF = j - LF;
-                    uint32_t dest;
-                    if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[n - RF] - 1u);
-                    else if (j == f) {
-                        dest = pivot;
-                        pay |= 0x80000000u;
-                        if (cidx >= 0) { s_u[cidx] = pay & 0xFFFFu; s_uk[cidx] = (pay >> 16) & 0x1FFu; s_piv[cidx] = pivot; }
-                    } else dest = Lbit ? (uint32_t)s_tab[nL - LF - 1] : j - 1;
-                    pout[dest] = pay;
+                    if (j < f) {
+                        if (!Lbit) p[RF == 0 ? act - 1 : (uint32_t)s_tab[act - RF] - 1u] = pay[i];  // front L's stay where they are
+                    } else if (j == f) {
+                        const uint32_t up = pay[i] | 0x80000000u;
+                        p[pivot] = up;
+                        if (cidx >= 0) { s_u[cidx] = up & 0xFFFFu; s_uk[cidx] = (up >> 16) & 0x1FFu; s_piv[cidx] = s0 + pivot; }
+                    } else p[Lbit ? (uint32_t)s_tab[nL - LF - 1] : j - 1] = pay[i];
                 }
             }
             __syncthreads();  // S3
+            return pivot;
         };
 
-        int cur = 0;
-        for (uint32_t c = 0; c < 21; ++c) { shuffle(cur, c / 7, c % 7 + 1, (int)c); cur ^= 1; }
+        {
+            uint32_t s0 = 0;
+            for (uint32_t c = 0; c < 21; ++c) {
+                const uint32_t b = c % 7 + 1;
+                if (b == 1) s0 = 0;  // a new axis starts on the whole range
+                s0 += shuffle(c / 7, b, s0, (int)c);
+            }
+        }
 
         // ---- 4. exact bins over the non-special primitives (4 slots per thread at a time) ----
         // Boxes are mapped to ordered uints once per slot, so the 24 per-bin reductions below are integer min / max
         // feeding redux.sync directly.
         {
-            const uint32_t* pin = cur ? s_pay1 : s_pay0;
+            const uint32_t* pin = s_pay0;
             for (uint32_t i0 = 0; i0 < E; i0 += 4) {
                 uint32_t lo[4][3], hi[4][3];
                 uint32_t kk[4];
@@ -366,10 +376,9 @@ __global__ void __launch_bounds__(THREADS, BIG ? 1 : T2_MIN_BLOCKS) k_t2(Queues 
             continue;
         }
         // ---- 6. final shuffle (blas.rs:164), write the order back ----
-        shuffle(cur, best / 7, best % 7 + 1, -1);
-        cur ^= 1;
+        shuffle(best / 7, best % 7 + 1, 0, -1);
         {
-            const uint32_t* pin = cur ? s_pay1 : s_pay0;
+            const uint32_t* pin = s_pay0;
 #pragma unroll 4
             for (int i = 0; i < EPT; ++i) {
                 const uint32_t j = warp * CHUNK + i * 32 + lane;
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t*
                                              uint32_t epoch) {
     constexpr int EPL = WCAP / 32;
     constexpr int NWB = 8;
-    __shared__ uint32_t s_pay[NWB][2][WCAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special
+    __shared__ uint32_t s_pay[NWB][WCAP];  // bits 0-15 local primitive, 16-24 plane counts, 31 special; shuffled in place
     __shared__ uint32_t s_gid[NWB][WCAP];
     __shared__ uint16_t s_tab[NWB][WCAP];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -498,67 +507,73 @@ __global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t*
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             const uint32_t j = i * 32 + lane;
-            if (i < (int)E && j < n) s_pay[w][0][j] = j | (plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax) << 16);
+            if (i < (int)E && j < n) s_pay[w][j] = j | (plane_counts(ccx[i], ccy[i], ccz[i], cmin, cmax) << 16);
         }
         __syncwarp();
 
-        // ---- 3. shuffles ----
+        // ---- 3. shuffles: closed form of partition_shuffle, in place on [s0, n) (see k_t2) ----
         uint32_t last_up = 0;
-        auto shuffle = [&](int cur, uint32_t a, uint32_t b) -> uint32_t {
+        auto shuffle = [&](uint32_t a, uint32_t b, uint32_t s0) -> uint32_t {
+            uint32_t* const p = s_pay[w] + s0;
+            const uint32_t act = n - s0;
+            const uint32_t Ea = (act + 31) >> 5;  // chunks in use
             const uint32_t sh = 16 + 3 * a;
-            uint32_t bal[EPL], LFv[EPL];
+            uint32_t bal[EPL], pay[EPL];
             uint32_t nL = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
                 bal[i] = 0;
-                LFv[i] = 0;
-                if (i < (int)E) {
+                pay[i] = 0;
+                if (i < (int)Ea) {
                     const uint32_t j = i * 32 + lane;
-                    const bool L = (j < n) && (((s_pay[w][cur][j] >> sh) & 7u) < b);
+                    if (j < act) pay[i] = p[j];
+                    const bool L = (j < act) && (((pay[i] >> sh) & 7u) < b);
                     bal[i] = __ballot_sync(FULL_MASK, L);
                     nL += __popc(bal[i]);
                 }
             }
             // boundary element in closed form (see p_t1_table): f is nL-1, nL or nL+1, decided by three flags
             auto l_at = [&](uint32_t j) -> uint32_t {  // one broadcast shared-memory read
-                return (j < n && (((s_pay[w][cur][j < n ? j : 0] >> sh) & 7u) < b)) ? 1u : 0u;
+                return (j < act && (((p[j < act ? j : 0] >> sh) & 7u) < b)) ? 1u : 0u;
             };
             uint32_t f, Lf;
             {
                 const uint32_t l0 = nL ? l_at(nL - 1) : 0u, l1 = l_at(nL), l2 = l_at(nL + 1);
-                if (nL >= 1 && !(nL + 1 <= n && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
-                else if (!(nL + 2 <= n && l1 + l2 == 0)) { f = nL; Lf = l1; }
+                if (nL >= 1 && !(nL + 1 <= act && l0 + l1 <= 1)) { f = nL - 1; Lf = l0; }
+                else if (!(nL + 2 <= act && l1 + l2 == 0)) { f = nL; Lf = l1; }
                 else { f = nL + 1; Lf = l2; }
             }
             const uint32_t pivot = nL - Lf;
             uint32_t running = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
-                if (i >= (int)E) break;
+                if (i >= (int)Ea) break;
                 const uint32_t j = i * 32 + lane;
                 const uint32_t LF = running + __popc(bal[i] & lt_mask);
-                LFv[i] = LF;
-                if (j < n) {
-                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[w][n - 1 - (nL - LF - 1)] = (uint16_t)j; }
+                if (j < act) {
+                    if ((bal[i] >> lane) & 1u) { if (j >= nL) s_tab[w][act - 1 - (nL - LF - 1)] = (uint16_t)j; }
                     else if (j <= nL) s_tab[w][j - LF] = (uint16_t)j;
                 }
                 running += __popc(bal[i]);
             }
-            __syncwarp();
+            __syncwarp();  // table complete; every read of p (counting pass, boundary flags) is done
             uint32_t upay = 0;
+            running = 0;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
-                if (i >= (int)E) break;
+                if (i >= (int)Ea) break;
                 const uint32_t j = i * 32 + lane;
-                if (j < n) {
-                    uint32_t pay = s_pay[w][cur][j];
+                const uint32_t LF = running + __popc(bal[i] & lt_mask);
+                running += __popc(bal[i]);
+                if (j < act) {
                     const uint32_t Lbit = (bal[i] >> lane) & 1u;
-                    const uint32_t LF = LFv[i], RF = j - LF;
-                    uint32_t dest;
-                    if (j < f) dest = Lbit ? j : (RF == 0 ? n - 1 : (uint32_t)s_tab[w][n - RF] - 1u);
-                    else if (j == f) { dest = pivot; pay |= 0x80000000u; upay = pay; }
-                    else dest = Lbit ? (uint32_t)s_tab[w][nL - LF - 1] : j - 1;
-                    s_pay[w][cur ^ 1][dest] = pay;
+                    const uint32_t RF = j - LF;
+                    if (j < f) {
+                        if (!Lbit) p[RF == 0 ? act - 1 : (uint32_t)s_tab[w][act - RF] - 1u] = pay[i];  // front L's stay
+                    } else if (j == f) {
+                        upay = pay[i] | 0x80000000u;
+                        p[pivot] = upay;
+                    } else p[Lbit ? (uint32_t)s_tab[w][nL - LF - 1] : j - 1] = pay[i];
                 }
             }
             __syncwarp();
@@ -566,12 +581,16 @@ __global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t*
             return pivot;
         };
 
-        int cur = 0;
         uint32_t my_u = 0xFFFFFFFFu, my_kb = 0, my_piv = 0;
-        for (uint32_t c = 0; c < 21; ++c) {
-            const uint32_t pivot = shuffle(cur, c / 7, c % 7 + 1);
-            cur ^= 1;
-            if (lane == c) { my_u = last_up & 0xFFFFu; my_kb = (last_up >> 16) & 0x1FFu; my_piv = pivot; }
+        {
+            uint32_t s0 = 0;
+            for (uint32_t c = 0; c < 21; ++c) {
+                const uint32_t b = c % 7 + 1;
+                if (b == 1) s0 = 0;  // a new axis starts on the whole range
+                const uint32_t pivot = s0 + shuffle(c / 7, b, s0);
+                if (lane == c) { my_u = last_up & 0xFFFFu; my_kb = (last_up >> 16) & 0x1FFu; my_piv = pivot; }
+                s0 = pivot;
+            }
         }
 
         // ---- 4. exact bins over the non-special primitives; lane a*8+k keeps bin (a,k) ----
@@ -588,7 +607,7 @@ __global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t*
                 lo[i][0] = lo[i][1] = lo[i][2] = ENC_POS_INIT;
                 hi[i][0] = hi[i][1] = hi[i][2] = ENC_NEG_INIT;
                 if (i < (int)E && j < n) {
-                    const uint32_t pay = s_pay[w][cur][j];
+                    const uint32_t pay = s_pay[w][j];
                     if (!(pay & 0x80000000u)) {
                         const uint32_t g = s_gid[w][pay & 0xFFFFu];
                         const float4 b0 = box[2 * (size_t)g], b1 = box[2 * (size_t)g + 1];
@@ -674,12 +693,11 @@ __global__ void __launch_bounds__(256, T2W_MIN_BLOCKS) k_t2w(Queues Q, uint32_t*
         const uint32_t win = __ffs(__ballot_sync(FULL_MASK, key == mk)) - 1;
         const uint32_t p = __shfl_sync(FULL_MASK, my_piv, win);
         // ---- 6. final shuffle (blas.rs:164), write the order back ----
-        shuffle(cur, win / 7, win % 7 + 1);
-        cur ^= 1;
+        shuffle(win / 7, win % 7 + 1, 0);
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
             const uint32_t j = i * 32 + lane;
-            if (i < (int)E && j < n) ids[start + j] = s_gid[w][s_pay[w][cur][j] & 0xFFFFu];
+            if (i < (int)E && j < n) ids[start + j] = s_gid[w][s_pay[w][j] & 0xFFFFu];
         }
         __threadfence();
         __syncwarp();

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "t4_seq.cuh"
 
+#include <cooperative_groups.h>
 #include <cstdlib>
 #include <atomic>
 
@@ -115,7 +116,9 @@ struct BuildState {
     uint32_t t3_inline;
     uint32_t neg_zero;  // some referenced vertex coordinate is -0.0: box zeros need the reference's first-encounter sign
     uint32_t t4_count;
-    uint32_t grid_nodes;            // interior nodes split by the grid tier ...
+    uint32_t c_head, c_tail, c_pending;  // cluster-tier queue
+    uint32_t tc_done;
+    uint32_t grid_nodes;            // interior nodes split by the grid and cluster tiers ...
     unsigned long long sum_grid;    // ... and the sum of their primitive counts (statistics for the roofline)
 };
 
@@ -213,12 +216,14 @@ __global__ void __launch_bounds__(256) k_setup(const float* __restrict__ V, uint
 
 // Device task lists, by node size (see the tier table in DESIGN.md).
 struct Queues {
+    Task* qc;   // cluster tasks (T2B_CAP < n <= tc_cap)
     Task* qb;   // big-block tasks (T2_CAP < n <= T2B_CAP)
     Task* q;    // block-per-node tasks (T2W_CAP < n <= T2_CAP)
     Task* qw;   // warp-per-node tasks  (T3_MAX < n <= T2W_CAP)
     Task* t3;   // warp-per-sub-tree tasks (T4_MAX < n <= T3_MAX)
     Task* t4;   // thread-per-sub-tree tasks (n <= T4_MAX)
-    uint32_t qb_cap, q_cap, qw_cap, t3_cap, t4_cap;
+    uint32_t qc_cap, qb_cap, q_cap, qw_cap, t3_cap, t4_cap;
+    uint32_t tc_cap;  // largest node the cluster tier takes (T2B_CAP when the tier is off: then the grid tier keeps them)
 };
 
 __device__ __forceinline__ void push_t4(const Queues& Q, BuildState* st, uint32_t start, uint32_t n, uint32_t leftrun,
@@ -232,13 +237,14 @@ __device__ __forceinline__ void push_t4(const Queues& Q, BuildState* st, uint32_
 
 #include "blas_small.cuh"
 #include "blas_block.cuh"
+#include "blas_cluster.cuh"
 #include "blas_grid.cuh"
 #include "blas_emit.cuh"
 
 }  // namespace
 
-constexpr size_t T2_SMEM = (size_t)T2_CAP * 10;    // 2 x u32 payload + u16 table per slot
-constexpr size_t T2B_SMEM = (size_t)T2B_CAP * 10;
+constexpr size_t T2_SMEM = (size_t)T2_CAP * 6;    // u32 payload (shuffled in place) + u16 table per slot
+constexpr size_t T2B_SMEM = (size_t)T2B_CAP * 6;
 constexpr size_t T4_SMEM = (size_t)8 * T4_CAP * T4_THREADS * 4;  // 6 float + 2 u32 words per slot per thread
 
 int blas_t2_occupancy() {
@@ -281,10 +287,60 @@ int blas_t1_blocks(unsigned long long* out2048) {
 #endif
 }
 
+// debug (library built with -DBVH_TC_TIMING): copies and clears the cluster tier's per-node time stamps
+int blas_tc_log(unsigned long long* out, unsigned int cap_rows) {
+#ifdef BVH_TC_TIMING
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_tc_logn, sizeof(n));
+    if (n > 4096) n = 4096;
+    if (n > cap_rows) n = cap_rows;
+    if (n) cudaMemcpyFromSymbol(out, g_tc_log, sizeof(unsigned long long) * 8 * n);
+    const unsigned int z = 0;
+    cudaMemcpyToSymbol(g_tc_logn, &z, sizeof(z));
+    if (cap_rows > n + 1) {  // one extra row: the per-phase cycle sums of the shuffles
+        cudaMemcpyFromSymbol(out + 8 * (size_t)n, g_tc_phase, sizeof(unsigned long long) * 8);
+        const unsigned long long zz[8] = {};
+        cudaMemcpyToSymbol(g_tc_phase, zz, sizeof(zz));
+    }
+    return (int)n;
+#else
+    (void)out; (void)cap_rows;
+    return -1;
+#endif
+}
+
 int blas_t1_coop_occupancy() {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop, T1_THREADS, 0) != cudaSuccess) occ = 1;
     return occ < 1 ? 1 : occ;
+}
+
+// Cluster tier: co-resident clusters of `cluster_size` CTAs (0 when such a cluster cannot be placed on this device).
+int blas_tc_setup(int cluster_size) {
+    static_assert(TS_SMEM >= TC_SMEM, "the two cluster-tier kernels are launched with the same configuration (the larger one)");
+    if (cudaFuncSetAttribute(k_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tcs, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tcs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size * 64);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TS_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, k_tc, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ncs = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncs, k_tcs, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nc < ncs ? nc : ncs;
 }
 
 int blas_t2w_occupancy() {
@@ -323,6 +379,11 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t max_large = N / T2B_CAP + 2;
     // (a level uses tiles smaller than T1_TILE only when it then has no more tiles than the grid has blocks)
     const uint32_t max_tiles = N / T1_TILE + max_large + 2 + (uint32_t)ctx->sm_count * 16;
+    // cluster tier: on unless the device cannot place the clusters or BVH_CUDA_NO_CLUSTER is set (A/B runs)
+    static const bool tc_off = [] { const char* e = getenv("BVH_CUDA_NO_CLUSTER"); return e && e[0] == '1'; }();
+    const bool use_tc = !tc_off && ctx->tc_clusters > 0 && ctx->tc_cluster_size > 0;
+    const uint32_t tc_cap = use_tc ? (uint32_t)ctx->tc_cluster_size * (uint32_t)TC_SLOTS : (uint32_t)T2B_CAP;
+    const uint32_t qc_cap = N / 4096 + NM + 64;   // nodes with 16385..tc_cap primitives
     const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
     const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
     const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
@@ -342,7 +403,9 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
              *scan_sums = nullptr, *scan_total = nullptr, *tbase = nullptr, *voff = nullptr, *node_base = nullptr, *mscan_sums = nullptr;
     uint16_t *fl0 = nullptr, *fl1 = nullptr;
     uint4* recs = nullptr;
-    Task *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr;
+    Task *qc = nullptr, *qb = nullptr, *q = nullptr, *qw = nullptr, *t3 = nullptr, *t4 = nullptr;
+    unsigned long long* items = nullptr;
+    TcScratch* tcs = nullptr;
     LevelNode* lv[2] = {nullptr, nullptr};
     NodeScratch* sc = nullptr;
     BuildState* st = nullptr;
@@ -358,6 +421,9 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         table = c.take<uint32_t>(N);
         A = c.take<uint32_t>(scan_n);
         recs = c.take<uint4>(3 * 2 * (size_t)N);
+        items = c.take<unsigned long long>(use_tc ? N : 1);
+        tcs = c.take<TcScratch>(use_tc ? (size_t)ctx->tc_clusters : 1);
+        qc = c.take<Task>(qc_cap);
         qb = c.take<Task>(qb_cap);
         q = c.take<Task>(q_cap);
         qw = c.take<Task>(qw_cap);
@@ -392,12 +458,12 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
 
     // The three task queues are contiguous; clearing them makes every `ready` word differ from the epoch even when
     // the workspace still holds other data of an earlier, differently sized build.
-    CU_CHECK(ctx, cudaMemsetAsync(qb, 0, (size_t)((char*)(qw + qw_cap) - (char*)qb), stream));
+    CU_CHECK(ctx, cudaMemsetAsync(qc, 0, (size_t)((char*)(qw + qw_cap) - (char*)qc), stream));
     CU_CHECK(ctx, cudaMemsetAsync(A, 0, sizeof(uint32_t) * scan_n, stream));
     CU_CHECK(ctx, cudaMemsetAsync(recs, 0, sizeof(uint4) * 3 * 2 * (size_t)N, stream));
     const bool prof = ctx->profiling;
     if (prof) cudaEventRecord(ctx->ev[0], stream);
-    Queues Q{qb, q, qw, t3, t4, qb_cap, q_cap, qw_cap, t3_cap, t4_cap};
+    Queues Q{qc, qb, q, qw, t3, t4, qc_cap, qb_cap, q_cap, qw_cap, t3_cap, t4_cap, tc_cap};
     k_init_state<<<1, 32, 0, stream>>>(st);
     if (d_mesh_info) k_mesh_table<<<(NM + 1 + 255) / 256, 256, 0, stream>>>(d_mesh_info, NM, 3 * N, tbase, voff, st);
     else k_single_mesh_table<<<1, 32, 0, stream>>>(N, tbase, voff);
@@ -415,7 +481,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     if (prof) cudaEventRecord(ctx->ev[1], stream);
 
     // ---- T1: grid-wide tier, one cooperative persistent launch (exits at once when no node is that large) ----
-    if (N > (uint32_t)T2B_CAP) {
+    if (N > tc_cap) {
         CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, 256, stream));
         T1Args g;
         g.nodes = lv[0]; g.sc = sc; g.n_nodes = 0; g.n_tiles = 0;
@@ -433,6 +499,31 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         launches += 1;
     }
 
+    if (prof) cudaEventRecord(ctx->ev[9], stream);
+    // ---- TC: one node per thread-block cluster, persistent clusters on their own task queue ----
+    if (use_tc && N > (uint32_t)T2B_CAP) {
+        cudaLaunchConfig_t cfg = {};
+        uint32_t n_cl = (uint32_t)ctx->tc_clusters;
+        if (n_cl > N / (uint32_t)T2B_CAP + NM) n_cl = N / (uint32_t)T2B_CAP + NM;  // never more clusters than possible tasks
+        cfg.gridDim = dim3(n_cl * (uint32_t)ctx->tc_cluster_size);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TS_SMEM;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)ctx->tc_cluster_size;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // BVH_CUDA_TC=global: the variant that keeps the node's order in global memory (k_tc); default: distributed shared memory
+        static const bool tc_global = [] { const char* e = getenv("BVH_CUDA_TC"); return e && e[0] == 'g'; }();
+        if (tc_global)
+            CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_tc, Q, ids0, items, table, (const float4*)cent, (const float4*)box, recs, A, tcs, st, epoch));
+        else
+            CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_tcs, Q, ids0, ids1, (const float4*)cent, (const float4*)box, recs, A, st, epoch));
+        launches++;
+    }
     if (prof) cudaEventRecord(ctx->ev[2], stream);
     // ---- T2: persistent blocks on the device task queues ----
     {
@@ -516,11 +607,13 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     stats.warp_tasks = hs->t3_count;
     stats.thread_tasks = hs->t4_count;
     stats.kernel_launches = launches;
+    stats.cluster_tasks = hs->tc_done;
     stats.grid_nodes = hs->grid_nodes;
     stats.grid_interior_prims = hs->sum_grid;
     if (prof) {
         cudaEventElapsedTime(&stats.ms_setup, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&stats.ms_grid, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&stats.ms_grid, ctx->ev[1], ctx->ev[9]);
+        cudaEventElapsedTime(&stats.ms_cluster, ctx->ev[9], ctx->ev[2]);
         cudaEventElapsedTime(&stats.ms_big_block, ctx->ev[2], ctx->ev[7]);
         cudaEventElapsedTime(&stats.ms_block, ctx->ev[7], ctx->ev[6]);
         cudaEventElapsedTime(&stats.ms_warp_node, ctx->ev[6], ctx->ev[3]);

@@ -203,13 +203,13 @@ __global__ void __launch_bounds__(256) k_roots(const uint32_t* __restrict__ tbas
     const uint32_t start = tbase[m], n = tbase[m + 1] - tbase[m];
     const uint32_t flags = TF_ROOT | (m << TF_MESH_SHIFT);
     if (n == 0 || tbase[m + 1] < start) { atomicOr(&st->err, DERR_BAD_INDEX); return; }
-    if (n > T2B_CAP) {
+    if (n > Q.tc_cap) {
         const uint32_t idx = atomicAdd(&st->lv_count[0], 1u);
         if (idx >= lv_cap) { atomicOr(&st->err, DERR_QUEUE); return; }
         LevelNode l;
         l.start = start; l.n = n; l.leftrun = 0; l.pstart = start; l.pleftrun = 0; l.flags = flags; l.tile_base = 0; l.pad = 0;
         lv0[idx] = l;
     } else {
-        push_child(Q, st, epoch, start, n, 0, start, 0, flags);
+        push_any(Q, st, epoch, start, n, 0, start, 0, flags);
     }
 }

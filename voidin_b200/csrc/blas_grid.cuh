@@ -611,7 +611,7 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
             const uint32_t cn = side ? nd.n - p : p;
             const uint32_t clr = side ? 0 : nd.leftrun + 1;
             const uint32_t cfl = (side ? TF_RIGHT : 0u) | (nd.flags & ~3u);
-            if (cn > T2B_CAP) {
+            if (cn > Q.tc_cap) {
                 const uint32_t idx = atomicAdd(&g.st->lv_count[next_slot], 1u);
                 if (idx >= next_cap) { atomicOr(&g.st->err, DERR_QUEUE); continue; }
                 LevelNode c;
@@ -619,7 +619,7 @@ __device__ __forceinline__ void p_t1_children(const T1Args& g, LevelNode* next_n
                 c.tile_base = 0; c.pad = 0;
                 next_nodes[idx] = c;
             } else {
-                push_child(Q, g.st, epoch, cs, cn, clr, nd.start, nd.leftrun, cfl);
+                push_any(Q, g.st, epoch, cs, cn, clr, nd.start, nd.leftrun, cfl);
             }
         }
     }

@@ -39,6 +39,8 @@ struct bvh_cuda_ctx {
     int t2_blocks_per_sm = 0;
     int t2w_blocks_per_sm = 0;
     int t1_blocks_per_sm = 0;
+    int tc_cluster_size = 0;  // CTAs per cluster of the cluster tier (0: tier unavailable on this device)
+    int tc_clusters = 0;      // co-resident clusters of that size
     // host-API staging arena (grow-only, so repeated host calls do not cudaMalloc)
     void* stage = nullptr;
     size_t stage_bytes = 0;
@@ -47,7 +49,7 @@ struct bvh_cuda_ctx {
     size_t defer_cap = 0;
     // optional per-phase timing
     bool profiling = false;
-    cudaEvent_t ev[9] = {};
+    cudaEvent_t ev[10] = {};
     bool t4_ready = false;  // k_t4's dynamic shared-memory limit has been raised on this context's device
 };
 
