@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json's metric on its config 2: dragon-class SAH BLAS build (Mtris/s) followed by 16 M any-hit
-shadow rays toward a rect area light (Mrays/s), on N B200s of one node.
+shadow rays toward a rect area light (Mrays/s), on N B200s of one node; plus a config-5 leg (1 024 meshes, builds
+sharded over the ranks + NCCL all-gather, 1 Gi rays ray-sharded) in the same JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -10,9 +11,11 @@ A step = one pass of the hot path over one batch of synthetic input, inputs resi
     TLAS build over the 2 instances
     16 M any-hit shadow rays through the two-level BVH                                         -> `rays.value`
 Top-level `metric` is the first half of BASELINE.json's metric (build Mtris/s on dragon); the second half (shadow-ray
-Mrays/s) is the `rays` object with the same sub-keys.  N > 1: the single-mesh build does not shard ("replicas
-only": every rank builds its own copy, which it needs anyway to trace), rays are sharded (each rank traces its own
-16 M-ray shard, no data-path collective) -> "scaling": "weak".
+Mrays/s) is the `rays` object with the same sub-keys.  N > 1: a single BLAS does not shard, so the job is N DISTINCT
+dragon-class meshes, one built per rank in place inside its slot of the pooled scene arrays, followed by NCCL
+all-gathers (nodes, permuted indices, vertices) so that every GPU holds every mesh: `value` = N x tris / (build +
+all-gather), "scaling": "weak" (never a replicated build multiplied by N).  Rays: the FIXED 16 Mi batch is split over
+the ranks (strong scaling, no collective) -> `rays.value`; `rays.weak` repeats round 1's 16 Mi rays per GPU.
 
 `e2e` repeats the measurement through the host-pointer C ABI (bvh_cuda_blas_build / bvh_cuda_trace_any) with
 pinned HOST buffers, H2D/D2H copies inside the timed region.  `--impl reference` times the CPU oracle port
@@ -56,10 +59,13 @@ def build_inputs(rank: int, n_rays: int):
 
 
 def measured_traffic():
-    """DRAM bytes per launch measured with ncu --set full (profiles/r01_traffic.json, written from the committed
-    summaries); None when the file is missing."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else None
+    """Per-launch ncu figures (DRAM bytes, L2 peak, issue-slot use) written from the committed summaries under profiles/
+    (r02_traffic.json, else round 1's); None when neither exists."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
+    return None
 
 
 def build_bytes(n_tris, n_verts, S_sum, M):
@@ -130,7 +136,9 @@ class ClockSampler:
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference's Rust on the host cores.  Rank 0 only."""
+    """CPU arm: the oracle port of the reference's Rust on the host cores, on the SAME workload and `config` as the GPU arm:
+    every step builds the full dragon-class mesh (single-threaded, like the reference) and traces a bounded 1 Mi-ray
+    sample of the 16 Mi batch on all host threads.  Rank 0 only."""
     if rank != 0:
         return
     from oracle import oracle as O
@@ -138,18 +146,14 @@ def run_reference(args, rank, world):
 
     threads = O.max_threads()
     total = args.steps + args.warmup
-    full = total <= 6
-    if full:
-        dv, di = S.dragon_class()
-        sample = "full dragon_class mesh (871422 tris) per step"
-    else:
-        dv, di = S.displaced_sphere(165, 330, 2)
-        sample = f"displaced_sphere(165,330) = {di.size // 3} tris per step (1/8 of the dragon-class mesh; Mtris/s is near size-independent)"
+    dv, di = S.dragon_class()
     pv, pi = S.make_plane_mesh()
     mats, mesh_ids = S.dragon_scene_instances()
     inst = S.make_instances(mats, mesh_ids)
     n_rays = 1 << 20
     ro, rd = S.gbuffer_shadow_rays(n_rays, S.world_triangles(dv, di, mats[1]), S.rect_light_corners(), seed=12)
+    sample = (f"every step: one full dragon_class + plane build ({di.size // 3 + 2} tris, 1 thread, as the reference builds) and "
+              f"{n_rays} of the {args.rays} any-hit rays on {threads} threads (std::thread over rays; the reference itself is single-threaded)")
     bt, rt = [], []
     for step in range(total):
         t0 = time.perf_counter()
@@ -172,12 +176,11 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "dragon_blas_build_Mtris_per_s", "value": val, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": b_ms + r_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config2_dict(n_tris, args.rays, world),
         "cpu_baseline": {"value": val, "unit": "Mtris/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rays": {"metric": "shadow_ray_Mrays_per_s", "value": rval, "unit": "Mrays/s", "ms": r_ms,
-                 "cpu_baseline": {"value": rval, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                  "sample": f"{n_rays} any-hit rays per step, std::thread over rays (the reference itself is single-threaded)"},
+                 "cpu_baseline": {"value": rval, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
                  "e2e": {"value": rval, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
         "phase_ms": {"build": b_ms, "trace": r_ms},
         "note": "reference = C++ oracle port of crates/bvh (Rust toolchain absent, so oracle/_ref cannot exist); build is single-threaded like the reference",
@@ -362,10 +365,44 @@ def run_small_configs(args, local_rank):
     print(json.dumps(out), flush=True)
 
 
-def run_scene1024(args, rank, local_rank, world):
+def device_spheres(mids, vside, dev, side):
+    """Config-5 meshes generated ON THE DEVICE (1 024 numpy meshes would cost a minute of host time per run): displaced UV
+    spheres like scenes.displaced_sphere — same topology and triangle order (scenes._uv_sphere_indices), radius modulated by
+    12 random lobes whose parameters come from a CPU generator seeded with 5000 + mesh id — each authored at its lattice
+    cell (spacing 3), see the note on Tlas::build's local-box seed in run_scene1024.  Returns ({id: (verts, idx)}, bounds)."""
+    import torch
+
+    from voidin_b200 import scenes as S
+
+    uside = 2 * vside
+    v = (torch.arange(vside + 1, dtype=torch.float64, device=dev) / vside)[:, None]
+    u = (torch.arange(uside + 1, dtype=torch.float64, device=dev) / uside)[None, :]
+    theta, phi = 2 * np.pi * u + np.pi, np.pi * v
+    d = torch.stack([torch.cos(theta) * torch.sin(phi), (-torch.cos(phi)).expand(vside + 1, uside + 1),
+                     torch.sin(theta) * torch.sin(phi)], dim=-1).reshape(-1, 3)          # [V,3]
+    idx = torch.from_numpy(S._uv_sphere_indices(vside, uside).view(np.int32)).to(dev)
+    stretch = torch.tensor([1.0, 0.7, 1.35], dtype=torch.float64, device=dev)
+    out, bounds = {}, {}
+    for mid in mids:
+        g = np.random.default_rng(5000 + mid)
+        w = g.normal(size=(12, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+        freq, ph = g.uniform(1.5, 9.0, size=12), g.uniform(0, 2 * np.pi, size=12)
+        amp = 0.25 / (1.5 + 0.5 * np.arange(12))
+        wt = torch.from_numpy(w).to(dev)
+        rad = 1.0 + (torch.from_numpy(amp).to(dev)[None, :] * torch.sin(torch.from_numpy(freq).to(dev)[None, :] * (d @ wt.T) * np.pi
+                                                                          + torch.from_numpy(ph).to(dev)[None, :])).sum(dim=1)
+        cell = torch.tensor([3.0 * (mid % side), 0.0, 3.0 * (mid // side)], dtype=torch.float64, device=dev)
+        verts = (d * rad[:, None] * stretch + cell).to(torch.float32).contiguous()
+        bounds[mid] = (verts.min(dim=0)[0].cpu().numpy(), verts.max(dim=0)[0].cpu().numpy())
+        out[mid] = (verts.view(-1), idx)
+    return out, bounds
+
+
+def config5_leg(args, ctx, rank, world, dev, stream, steps, warm):
     """BASELINE config 5: `--meshes` distinct synthetic meshes; BLAS builds sharded over the ranks (LPT), ONE all-gather
     of {vertices | permuted indices | nodes} slabs over NCCL so every GPU holds the pooled scene, TLAS per rank, then
-    any-hit shadow rays sharded by contiguous ranges (no collective)."""
+    `--c5-rays` any-hit shadow rays (TOTAL, split over the ranks in contiguous ranges: strong scaling, no collective).
+    Returns the leg's dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
@@ -373,54 +410,50 @@ def run_scene1024(args, rank, local_rank, world):
     from voidin_b200 import multi_gpu as MG
     from voidin_b200 import scenes as S
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = vb.Context(local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
     n_meshes, vside = args.meshes, args.mesh_res
     uside = 2 * vside
     tri_counts = [2 * uside * vside - uside] * n_meshes
     vert_counts = [(uside + 1) * (vside + 1)] * n_meshes
     plan = MG.lpt_assignment(tri_counts, world)
-    mine, bounds_local = {}, np.zeros((n_meshes, 2, 3), dtype=np.float32)
     side = int(np.ceil(np.sqrt(n_meshes)))
-    for mid in plan[rank]:
-        v, idx = S.displaced_sphere(vside, uside, 5000 + mid)
-        # Each mesh is authored at its lattice cell (spacing 3) and instanced with the identity.  Tlas::build seeds every
-        # leaf box with the UNTRANSFORMED local mesh box (tlas.rs:39), so translating centred meshes by their instance
-        # transform instead would stretch every leaf box from the origin to the instance and make the TLAS useless
-        # (measured with the oracle: ~200 instance entries per ray on this scene).
-        v = (v + np.array([3.0 * (mid % side), 0.0, 3.0 * (mid // side)], dtype=np.float32)).astype(np.float32)
-        bounds_local[mid, 0], bounds_local[mid, 1] = v.min(0), v.max(0)
-        mine[mid] = (torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(idx.view(np.int32)).to(dev))
+    # Each mesh is authored at its lattice cell (spacing 3) and instanced with the identity.  Tlas::build seeds every
+    # leaf box with the UNTRANSFORMED local mesh box (tlas.rs:39), so translating centred meshes by their instance
+    # transform instead would stretch every leaf box from the origin to the instance and make the TLAS useless
+    # (measured with the oracle: ~200 instance entries per ray on this scene).
+    mine, bnd = device_spheres(plan[rank], vside, dev, side)
+    bounds_local = np.zeros((n_meshes, 2, 3), dtype=np.float32)
+    for mid, (lo, hi) in bnd.items():
+        bounds_local[mid, 0], bounds_local[mid, 1] = lo, hi
     b_t = torch.from_numpy(bounds_local).to(dev)
     if world > 1:
         dist.all_reduce(b_t, op=dist.ReduceOp.SUM)  # every mesh is owned by exactly one rank
     bounds = b_t.cpu().numpy()
-    mats = np.stack([np.eye(4)] * n_meshes)
-    inst = S.make_instances(mats, np.arange(n_meshes))
+    inst = S.make_instances(np.stack([np.eye(4)] * n_meshes), np.arange(n_meshes))
     d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
     d_tlas = torch.zeros((2 * n_meshes + 1) * 8, dtype=torch.int32, device=dev)
     d_kids = torch.zeros((2 * n_meshes + 1) * 2, dtype=torch.int32, device=dev)
-    # rays of this rank's contiguous shard, generated on the device from the global ray index
-    n_total = args.rays * world if args.rays != N_RAYS else (1 << 26) * world
+    # rays of this rank's contiguous shard of the fixed total, generated on the device from the global ray index
+    n_total = args.c5_rays
     rb, re_ = MG.ray_range(rank, world, n_total)
-    gi = torch.arange(rb, re_, device=dev, dtype=torch.int64)
-
-    def u01(salt):
-        x = (gi * 6364136223846793005 + (salt * 1442695040888963407) % (1 << 62)) & 0x7FFFFFFFFFFFFFFF
-        x = ((x >> 29) ^ x) * 0x2545F4914F6CDD1D & 0x7FFFFFFFFFFFFFFF
-        return ((x >> 11) & 0xFFFFFF).to(torch.float32) / 16777216.0
-
-    ext = 3.0 * side
-    o = torch.stack([u01(15) * (ext + 6) - 4.5, torch.full_like(u01(1), -1.6), u01(16) * (ext + 6) - 4.5], dim=1)
-    tgt = torch.stack([ext / 2 - 1.5 + (u01(17) - 0.5) * 20, torch.full_like(u01(1), 30.0), ext / 2 - 1.5 + (u01(18) - 0.5) * 20], dim=1)
-    d_ro = o.contiguous().view(-1)
-    d_rd = (tgt - o).contiguous().view(-1)
     n_rays = re_ - rb
-    del gi, o, tgt
+    d_ro = torch.empty(3 * n_rays, dtype=torch.float32, device=dev)
+    d_rd = torch.empty(3 * n_rays, dtype=torch.float32, device=dev)
+    ext = 3.0 * side
+    for c0 in range(0, n_rays, 1 << 24):  # in chunks: the int64 hashing temporaries are 8x the ray bytes
+        c1 = min(n_rays, c0 + (1 << 24))
+        gi = torch.arange(rb + c0, rb + c1, device=dev, dtype=torch.int64)
+
+        def u01(salt):
+            x = (gi * 6364136223846793005 + (salt * 1442695040888963407) % (1 << 62)) & 0x7FFFFFFFFFFFFFFF
+            x = ((x >> 29) ^ x) * 0x2545F4914F6CDD1D & 0x7FFFFFFFFFFFFFFF
+            return ((x >> 11) & 0xFFFFFF).to(torch.float32) / 16777216.0
+
+        o = torch.stack([u01(15) * (ext + 6) - 4.5, torch.full((c1 - c0,), -1.6, device=dev), u01(16) * (ext + 6) - 4.5], dim=1)
+        tgt = torch.stack([ext / 2 - 1.5 + (u01(17) - 0.5) * 20, torch.full((c1 - c0,), 30.0, device=dev),
+                           ext / 2 - 1.5 + (u01(18) - 0.5) * 20], dim=1)
+        d_ro[3 * c0:3 * c1] = o.reshape(-1)
+        d_rd[3 * c0:3 * c1] = (tgt - o).reshape(-1)
+        del gi, o, tgt
     d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
     build_fn = MG.cuda_build_fn(ctx, stream)
     build_batch_fn = MG.cuda_build_batch_fn(ctx, stream)
@@ -438,13 +471,14 @@ def run_scene1024(args, rank, local_rank, world):
                          sc.vertices.data_ptr(), sc.indices.data_ptr(), ctx, device_ptrs=True,
                          counts={"tlas_nodes": 2 * n_meshes + 1, "instances": n_meshes, "meshes": n_meshes,
                                  "bvh_nodes": sum(sc.n_nodes), "vertices": sum(vert_counts), "indices": 3 * sum(tri_counts)}, stream=stream)
-        scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
         if ev: ev[3].record()
+        scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
+        if ev: ev[4].record()
         torch.cuda.synchronize()
-        state["tm"] = tm
-        state["gather_ms"] = tm["after_build"].elapsed_time(tm["after_gather"]) if "after_build" in tm else 0.0
+        state["gather_ms"] = tm["after_build"].elapsed_time(tm["after_gather"])
+        state["assemble_ms"] = tm["after_gather"].elapsed_time(tm["after_assemble"])
+        state["gather_bytes"] = tm["gather_bytes_received"]
         scene.close()
-        state["sc"] = None
         del sc
 
     def barrier():
@@ -452,39 +486,75 @@ def run_scene1024(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(warm):
         step()
     barrier()
-    steps = max(1, min(args.steps, 5))
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
-    gms = []
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
+    gms, ams = [], []
     l0 = ctx.launch_count
     for k in range(steps):
         barrier()
         step(evs[k])
-        gms.append(state["gather_ms"])
+        gms.append(state["gather_ms"]); ams.append(state["assemble_ms"])
     barrier()
     launches = ctx.launch_count - l0
     tot = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in evs), sum(e[1].elapsed_time(e[2]) for e in evs),
-                        sum(e[2].elapsed_time(e[3]) for e in evs), sum(gms)], dtype=torch.float64, device=dev)
+                        sum(e[2].elapsed_time(e[3]) for e in evs), sum(e[3].elapsed_time(e[4]) for e in evs), sum(gms), sum(ams)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    b_ms, t_ms, r_ms, g_ms = [float(x) / steps for x in tot.tolist()]
+    b_ms, t_ms, k_ms, r_ms, g_ms, a_ms = [float(x) / steps for x in tot.tolist()]
     occ = float(d_occ.float().mean().item())
+    del d_ro, d_rd, d_occ, mine
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    total_tris = sum(tri_counts)
+    gbytes = state["gather_bytes"]
+    return {
+        "workload": f"config5: {n_meshes} meshes x {tri_counts[0]} tris, BLAS builds sharded (LPT) + one NCCL all-gather, {n_total} any-hit rays in total, ray-sharded",
+        "scaling": "strong (fixed scene and fixed ray batch split over the ranks)",
+        "build": {"metric": "multi_mesh_blas_build_Mtris_per_s", "value": total_tris / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s",
+                  "ms_build_plus_gather": b_ms, "ms_local_forest_build": b_ms - g_ms - a_ms, "ms_all_gather": g_ms, "ms_assemble": a_ms,
+                  "all_gather_bytes_received_per_gpu": int(gbytes),
+                  "all_gather_GBps_per_gpu": (gbytes / (g_ms * 1e-3) / 1e9) if (world > 1 and g_ms > 0) else None,
+                  "collective": "torch.distributed all_gather_into_tensor (NCCL over NVLink), zero-padded per-rank slabs" if world > 1 else "none (one rank)"},
+        "tlas_ms": t_ms, "scene_bake_ms": k_ms,
+        "rays": {"metric": "shadow_ray_Mrays_per_s", "value": n_total / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms": r_ms,
+                 "rays_total": n_total, "occluded_frac_rank0": occ},
+        "steps": steps, "warmup": warm, "gpu_launches": int(launches), "tris": total_tris}
+
+
+def run_scene1024(args, rank, local_rank, world):
+    """--workload scene1024: the config-5 leg alone, one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import voidin_b200 as vb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = vb.Context(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    leg = config5_leg(args, ctx, rank, world, dev, stream, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
     if rank == 0:
-        total_tris = sum(tri_counts)
-        print(json.dumps({
-            "metric": "multi_mesh_blas_build_Mtris_per_s", "value": total_tris / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "n_gpus": world,
-            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": b_ms + t_ms + r_ms, "higher_is_better": True,
-            "scaling": "strong (build: fixed 1024-mesh scene sharded over ranks) / weak (rays: fixed rays per GPU)", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config5: {n_meshes} meshes x {tri_counts[0]} tris, BLAS builds sharded (LPT) + one NCCL all-gather, {n_total} any-hit rays ray-sharded",
-                       "tris": total_tris, "rays_total": n_total},
-            "phase_ms": {"build_plus_gather": b_ms, "gather_and_assemble": g_ms, "tlas": t_ms, "trace_incl_scene_bake": r_ms},
-            "rays": {"metric": "shadow_ray_Mrays_per_s", "value": n_total / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s", "occluded_frac": occ},
-            "gpu_launches": int(launches)}), flush=True)
+        print(json.dumps({"metric": leg["build"]["metric"], "value": leg["build"]["value"], "unit": "Mtris/s", "n_gpus": world,
+                          "steps": leg["steps"], "warmup": leg["warmup"], "ms_per_step": leg["build"]["ms_build_plus_gather"] + leg["tlas_ms"] + leg["scene_bake_ms"] + leg["rays"]["ms"],
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": leg["workload"]}, "config5": leg}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config2_dict(n_tris, n_rays, world):
+    """`config` of the headline line; the reference arm prints the same dict (it times the same workload on the CPU)."""
+    return {"workload": WORKLOAD, "tris": n_tris, "rays": n_rays, "l2": "flushed between timed iterations (256 MiB fill)",
+            "multi_gpu": ("one rank" if world == 1 else
+                          f"build: {world} distinct dragon-class meshes, one per rank (a single BLAS does not shard), then NCCL all-gather of "
+                          "vertices / permuted indices / nodes so that every GPU holds all of them (weak scaling); rays: the fixed "
+                          f"{n_rays}-ray batch split over the ranks, scene replicated, no collective (strong scaling)")}
 
 
 def main():
@@ -500,6 +570,8 @@ def main():
     ap.add_argument("--meshes", type=int, default=1024)
     ap.add_argument("--instances", type=int, default=32767, help="instances workload (config 3): instance count")
     ap.add_argument("--mesh-res", type=int, default=181, help="scene1024: vside of each displaced sphere (181 -> 130682 tris)")
+    ap.add_argument("--c5-rays", type=int, default=1 << 30, help="config-5 leg: any-hit rays in TOTAL (split over the ranks)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 leg of the default workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -516,11 +588,19 @@ def main():
     if args.workload in ("bunny", "instances", "soup"):
         run_small_configs(args, local_rank)
         return
+    run_dragon(args, rank, local_rank, world)
+
+
+def run_dragon(args, rank, local_rank, world):
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
 
     import voidin_b200 as vb
+    from voidin_b200 import multi_gpu as MG
+    from voidin_b200 import scenes as S
+    from voidin_b200.types import MESH_INFO
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -529,10 +609,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    dv, di, pv, pi, inst, ro, rd = build_inputs(rank, args.rays)
+    # ---- inputs.  Mesh 2+rank is built by this rank; mesh 2 (rank 0's) is the one every rank traces. ----
+    dv0, di0, pv, pi, inst, ro, rd = build_inputs(0, args.rays)
+    dv, di = (dv0, di0) if rank == 0 else S.dragon_class(seed=2 + rank)
+    assert dv.shape == dv0.shape and di.shape == di0.shape
     n_dtris, n_ptris = di.size // 3, pi.size // 3
     n_tris = n_dtris + n_ptris
     n_rays = ro.shape[0]
+    # this rank's shard of the fixed batch: block-cyclic 64 Ki-ray chunks (contiguous halves would give one rank all the
+    # rays that start on the model and the other the cheap ground rays), packed once, untimed, as a renderer's ray
+    # generation would emit them
+    shard_idx = np.concatenate([np.arange(b0, e0) for b0, e0 in MG.ray_chunks(rank, world, n_rays)]) if world > 1 else None
+    ro_s, rd_s = (ro, rd) if world == 1 else (np.ascontiguousarray(ro[shard_idx]), np.ascontiguousarray(rd[shard_idx]))
+    n_shard = ro_s.shape[0]
     ctx = vb.Context(local_rank)
     ctx.set_profiling(True)
     stream = torch.cuda.current_stream().cuda_stream
@@ -540,23 +629,14 @@ def main():
     def dev_t(a, dtype):
         return torch.from_numpy(np.ascontiguousarray(a).view(dtype).reshape(-1)).to(dev)
 
-    d_dv, d_pv = dev_t(dv, np.float32), dev_t(pv, np.float32)
-    d_di_src, d_pi_src = dev_t(di, np.int32), dev_t(pi, np.int32)
-    d_ro, d_rd = dev_t(ro, np.float32), dev_t(rd, np.float32)
-    d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
-    # pooled scene buffers laid out as MeshPool::add does (mesh/mod.rs:309-351): plane first, then the dragon
     n_verts = pv.shape[0] + dv.shape[0]
-    d_verts = torch.cat([d_pv, d_dv])
-    d_inds = torch.empty(3 * n_tris, dtype=torch.int32, device=dev)
-    nodes_cap = 2 * n_ptris + 2 * n_dtris
+    nodes_cap = 2 * n_tris
+    d_pi_src, d_di_src = dev_t(pi, np.int32), dev_t(di, np.int32)
+    # The builder wants room for 2N nodes (blas.rs:52) and uses ~0.9N: nodes are built into a private buffer, and only the
+    # used part travels.  Node counts differ between the ranks' meshes; the slot is sized for the largest (one throw-away
+    # build + a scalar all-reduce, before anything is timed; builds are deterministic).
     d_nodes = torch.zeros(nodes_cap * 8, dtype=torch.int32, device=dev)
-    d_tlas = torch.zeros((2 * 2 + 1) * 8, dtype=torch.int32, device=dev)
-    d_kids = torch.zeros((2 * 2 + 1) * 2, dtype=torch.int32, device=dev)
-    d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
     d_infos = torch.zeros(2 * 48, dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    from voidin_b200.types import MESH_INFO
     infos = np.zeros(2, dtype=MESH_INFO)
     infos["min"][0], infos["max"][0] = pv.min(0), pv.max(0)
     infos["min"][1], infos["max"][1] = dv.min(0), dv.max(0)
@@ -564,31 +644,76 @@ def main():
     infos["base_index"] = [0, pi.size]
     infos["vertex_offset"] = [0, pv.shape[0]]
     infos_dev_src = torch.from_numpy(infos.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_infos.copy_(infos_dev_src)
+    tmp_v = torch.cat([dev_t(pv, np.float32), dev_t(dv, np.float32)])
+    tmp_i = torch.cat([d_pi_src, d_di_src])
+    m_own = ctx.blas_build_batch_dev(tmp_v.data_ptr(), n_verts, tmp_i.data_ptr(), 3 * n_tris, d_infos.data_ptr(), 2, d_nodes.data_ptr(), nodes_cap, stream)
+    m_t = torch.tensor([m_own], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(m_t, op=dist.ReduceOp.MAX)
+    m_max = int(m_t.item())
+    # Pooled arrays of the whole job: one slot per rank, [vertices | indices | nodes] (MeshPool::add order inside a slot:
+    # plane, dragon).  Vertices and indices are built on IN PLACE inside the rank's slot and the used nodes are copied
+    # next to them, so ONE all-gather sends straight from the slot and delivers straight into the arrays the traversal
+    # reads: no packing or re-assembly passes on either side.
+    off_i = 3 * n_verts
+    off_n = (off_i + 3 * n_tris + 7) // 8 * 8          # nodes 32-byte aligned inside the slot
+    slot_w = (off_n + 8 * m_max + 23) // 24 * 24        # slots start 32-byte aligned and on a whole vertex
+    pool = torch.zeros(world * slot_w, dtype=torch.int32, device=dev)
+    slot = pool[rank * slot_w:(rank + 1) * slot_w]
+    d_verts = slot[:off_i].view(torch.float32)
+    d_inds = slot[off_i:off_i + 3 * n_tris]
+    d_slot_nodes = slot[off_n:off_n + 8 * m_max]
+    d_verts.copy_(tmp_v)
+    del tmp_v, tmp_i
+    d_ro, d_rd = dev_t(ro, np.float32), dev_t(rd, np.float32)
+    d_ro_s, d_rd_s = (d_ro, d_rd) if world == 1 else (dev_t(ro_s, np.float32), dev_t(rd_s, np.float32))
+    d_inst = torch.from_numpy(inst.view(np.uint8).reshape(-1)).to(dev)
+    d_tlas = torch.zeros((2 * 2 + 1) * 8, dtype=torch.int32, device=dev)
+    d_kids = torch.zeros((2 * 2 + 1) * 2, dtype=torch.int32, device=dev)
+    d_occ = torch.empty(n_rays, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # MeshInfo of rank 0's two meshes inside slot 0 of the pooled array, for the traversal (offsets relative to the slot's
+    # vertex / index / node regions; the dragon's nodes follow the plane's two, blas.rs:93): the scene of BASELINE
+    # config 2, identical on every rank
+    tinfos = np.zeros(2, dtype=MESH_INFO)
+    tinfos["min"][0], tinfos["max"][0] = pv.min(0), pv.max(0)
+    tinfos["min"][1], tinfos["max"][1] = dv0.min(0), dv0.max(0)
+    tinfos["index_count"] = [pi.size, di0.size]
+    tinfos["base_index"] = [0, pi.size]
+    tinfos["vertex_offset"] = [0, pv.shape[0]]
+    tinfos["bvh_index"] = [0, 2]
+    d_tinfos = torch.from_numpy(tinfos.view(np.uint8).reshape(-1).copy()).to(dev)
 
     state = {}
 
     def step_dev(ev=None):
-        """One step on device-resident inputs.  ev: optional list of 4 torch events."""
+        """One step on device-resident inputs.  ev: optional list of 5 torch events."""
         d_inds[: 3 * n_ptris].copy_(d_pi_src)      # builds permute indices in place: restore the unpermuted input
         d_inds[3 * n_ptris:].copy_(d_di_src)
         if ev: ev[0].record()
-        # MeshPool::add x 2 as ONE forest build over the pooled buffers (fills MeshInfo.bvh_index on the device)
+        # MeshPool::add x 2 as ONE forest build over the rank's slot (fills MeshInfo.bvh_index on the device)
         d_infos.copy_(infos_dev_src)
         m_total = ctx.blas_build_batch_dev(d_verts.data_ptr(), n_verts, d_inds.data_ptr(), 3 * n_tris, d_infos.data_ptr(), 2,
                                            d_nodes.data_ptr(), nodes_cap, stream)
         state["stats"] = ctx.last_build_stats()
         if ev: ev[1].record()
-        ctx.tlas_build_dev(d_inst.data_ptr(), 2, d_infos.data_ptr(), 2, d_tlas.data_ptr(), d_kids.data_ptr(), stream)
+        d_slot_nodes.copy_(d_nodes[: 8 * m_max])
+        if world > 1:  # every GPU gets every rank's BLAS (and its geometry): one in-place all-gather, slot to slot
+            dist.all_gather_into_tensor(pool, slot)
         if ev: ev[2].record()
+        ctx.tlas_build_dev(d_inst.data_ptr(), 2, d_tinfos.data_ptr(), 2, d_tlas.data_ptr(), d_kids.data_ptr(), stream)
+        if ev: ev[3].record()
         if "scene" not in state:
-            state["scene"] = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_infos.data_ptr(), d_nodes.data_ptr(),
-                                      d_verts.data_ptr(), d_inds.data_ptr(), ctx, device_ptrs=True,
-                                      counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": m_total, "vertices": n_verts,
+            state["scene"] = vb.Scene(d_tlas.data_ptr(), d_kids.data_ptr(), d_inst.data_ptr(), d_tinfos.data_ptr(), pool.data_ptr() + 4 * off_n,
+                                      pool.data_ptr(), pool.data_ptr() + 4 * off_i, ctx, device_ptrs=True,
+                                      counts={"tlas_nodes": 5, "instances": 2, "meshes": 2, "bvh_nodes": m_max, "vertices": n_verts,
                                               "indices": 3 * n_tris}, stream=stream)
         else:
-            state["scene"].refresh_dev(m_total, stream)  # re-bake the traversal copy of the freshly permuted triangles
-        state["scene"].occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream)
-        if ev: ev[3].record()
+            state["scene"].refresh_dev(m_max, stream)  # re-bake the traversal copy of the freshly permuted triangles
+        state["scene"].occluded_dev(d_ro_s.data_ptr(), d_rd_s.data_ptr(), n_shard, d_occ.data_ptr(), 1e30, stream)
+        if ev: ev[4].record()
         state["M"] = m_total
 
     def barrier():
@@ -608,7 +733,7 @@ def main():
     barrier()
 
     # ---- device-resident timing ----
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches0 = ctx.launch_count
     barrier()
     t_wall0 = time.perf_counter()
@@ -621,15 +746,48 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = ctx.launch_count - launches0
     sampler.window(t_wall0, t_wall0 + t_wall)
-    b_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
-    t_ms = np.array([e[1].elapsed_time(e[2]) for e in evs])
-    r_ms = np.array([e[2].elapsed_time(e[3]) for e in evs])
-    s_ms = np.array([e[0].elapsed_time(e[3]) for e in evs])
-    tot = torch.tensor([b_ms.sum(), r_ms.sum(), s_ms.sum(), t_ms.sum()], dtype=torch.float64, device=dev)
+    el = lambda a, b: float(np.sum([e[a].elapsed_time(e[b]) for e in evs]))
+    tot = torch.tensor([el(0, 1), el(1, 2), el(2, 3), el(3, 4), el(0, 4), el(0, 2)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    b_tot, r_tot, s_tot, t_tot = [float(x) for x in tot.tolist()]
-    occ_frac = float(d_occ.float().mean().item())
+    b_tot, g_tot, t_tot, r_tot, s_tot, bg_tot = [float(x) for x in tot.tolist()]
+    occ_frac = float(d_occ[:n_shard].float().mean().item())
+    host_scene = state["scene"]
+
+    def timed_trace(d_o, d_d, n, reps=4):
+        ts = []
+        for k in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); host_scene.occluded_dev(d_o, d_d, n, d_occ.data_ptr(), 1e30, stream); e1.record()
+            torch.cuda.synchronize()
+            if k > 0: ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # the collective alone, back to back (no build in front of it): what NCCL needs for this message size
+    bare_ms = None
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(pool, slot)
+        e1.record(); torch.cuda.synchronize()
+        bt_ = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(bt_, op=dist.ReduceOp.MAX)
+        bare_ms = float(bt_.item())
+    # weak-scaled rays (N > 1 only): every rank traces the whole batch
+    weak_ms = timed_trace(d_ro.data_ptr(), d_rd.data_ptr(), n_rays) if world > 1 else None
+    # incoherent variant: the rank's shard under one fixed random permutation (device-side gather, untimed)
+    gperm = torch.Generator(device="cpu"); gperm.manual_seed(2012 + rank)
+    perm = torch.randperm(n_shard, generator=gperm).to(dev)
+    d_ro_i = d_ro_s.view(-1, 3)[perm].contiguous().view(-1); d_rd_i = d_rd_s.view(-1, 3)[perm].contiguous().view(-1)
+    del perm
+    inc_ms = timed_trace(d_ro_i.data_ptr(), d_rd_i.data_ptr(), n_shard)
+    del d_ro_i, d_rd_i
 
     # ---- end-to-end through the host-pointer C ABI, pinned host buffers ----
     h_dv = torch.from_numpy(dv.reshape(-1)).pin_memory()
@@ -637,28 +795,11 @@ def main():
     h_di_work = torch.empty_like(h_di).pin_memory()
     h_nodes = torch.empty(2 * n_dtris * 8, dtype=torch.int32).pin_memory()
     h_ro, h_rd = torch.from_numpy(ro.reshape(-1)).pin_memory(), torch.from_numpy(rd.reshape(-1)).pin_memory()
+    h_ro_s, h_rd_s = (h_ro, h_rd) if world == 1 else (torch.from_numpy(ro_s.reshape(-1)).pin_memory(), torch.from_numpy(rd_s.reshape(-1)).pin_memory())
     h_occ = torch.empty(n_rays, dtype=torch.uint8).pin_memory()
-    import ctypes as C
     lib = ctx.lib
-    host_scene = state["scene"]
-    # incoherent variant: the same rays under one fixed random permutation (device-side gather, untimed)
-    gperm = torch.Generator(device="cpu"); gperm.manual_seed(2012 + rank)
-    perm = torch.randperm(n_rays, generator=gperm).to(dev)
-    d_ro_i = d_ro.view(-1, 3)[perm].contiguous().view(-1); d_rd_i = d_rd.view(-1, 3)[perm].contiguous().view(-1)
-    del perm
-    inc = []
-    for k in range(4):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); host_scene.occluded_dev(d_ro_i.data_ptr(), d_rd_i.data_ptr(), n_rays, d_occ.data_ptr(), 1e30, stream); e1.record()
-        torch.cuda.synchronize()
-        if k > 0: inc.append(e0.elapsed_time(e1))
-    inc_t = torch.tensor([float(np.mean(inc))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(inc_t, op=dist.ReduceOp.MAX)
-    inc_ms = float(inc_t.item())
-    del d_ro_i, d_rd_i
     e2e_steps = max(3, min(args.steps, 5))
-    eb, er = [], []
+    eb, er, ew = [], [], []
     for k in range(e2e_steps + 1):
         h_di_work.copy_(h_di)
         m = C.c_uint32(0)
@@ -667,26 +808,40 @@ def main():
         ctx.check(lib.bvh_cuda_blas_build(ctx.h, h_dv.data_ptr(), dv.shape[0], h_di_work.data_ptr(), n_dtris, h_nodes.data_ptr(),
                                           2 * n_dtris, C.byref(m)))
         t1 = time.perf_counter()
-        ctx.check(lib.bvh_cuda_trace_any(ctx.h, host_scene.h, h_ro.data_ptr(), h_rd.data_ptr(), n_rays, 1e30, h_occ.data_ptr()))
+        ctx.check(lib.bvh_cuda_trace_any(ctx.h, host_scene.h, h_ro_s.data_ptr(), h_rd_s.data_ptr(), n_shard, 1e30, h_occ.data_ptr()))
         t2 = time.perf_counter()
+        if world > 1:
+            barrier()
+            t3 = time.perf_counter()
+            ctx.check(lib.bvh_cuda_trace_any(ctx.h, host_scene.h, h_ro.data_ptr(), h_rd.data_ptr(), n_rays, 1e30, h_occ.data_ptr()))
+            t4 = time.perf_counter()
+        else:
+            t3 = t4 = 0.0
         if k > 0:
-            eb.append(t1 - t0); er.append(t2 - t1)
-    e2e_t = torch.tensor([float(np.mean(eb)), float(np.mean(er))], dtype=torch.float64, device=dev)
+            eb.append(t1 - t0); er.append(t2 - t1); ew.append(t4 - t3)
+    e2e_t = torch.tensor([float(np.mean(eb)), float(np.mean(er)), float(np.mean(ew))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_b, e2e_r = [float(x) for x in e2e_t.tolist()]
+    e2e_b, e2e_r, e2e_w = [float(x) for x in e2e_t.tolist()]
     m_dragon = int(m.value)
     clocks = sampler.stop()
+
+    # ---- config-5 leg (sharded multi-mesh build + all-gather, strong-scaled rays) ----
+    host_scene.close()
+    del d_ro, d_rd, d_ro_s, d_rd_s, flush
+    torch.cuda.empty_cache()
+    c5 = None if args.no_config5 else config5_leg(args, ctx, rank, world, dev, stream, steps=2, warm=1)
 
     if rank == 0:
         peak, peak_src = peaks()
         st = phase_lib[-1]  # stats of the step's forest build (ground plane + dragon-class mesh)
         bb = build_bytes(n_tris, n_verts, st["sum_interior_prims"], st["n_nodes"])
-        b_ms_step = b_tot / args.steps
+        b_ms_step, g_ms_step = b_tot / args.steps, g_tot / args.steps
+        bg_ms_step = bg_tot / args.steps
         r_ms_step = r_tot / args.steps
-        value = world * n_tris / (b_ms_step * 1e-3) / 1e6
-        rvalue = world * n_rays / (r_ms_step * 1e-3) / 1e6
-        lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_big_block", "ms_block", "ms_warp_node", "ms_warp", "ms_thread", "ms_emit", "ms_total")}
+        value = world * n_tris / (bg_ms_step * 1e-3) / 1e6
+        rvalue = n_rays / (r_ms_step * 1e-3) / 1e6
+        lib_ms = {k: float(np.mean([p[k] for p in phase_lib])) for k in ("ms_setup", "ms_grid", "ms_cluster", "ms_big_block", "ms_block", "ms_warp_node", "ms_warp", "ms_thread", "ms_emit", "ms_total")}
         tr = measured_traffic()
         # Dominant kernel = k_t1_coop (grid tier, one launch per build).  Its algorithmic bytes: per level and per primitive
         # of the nodes it splits, id 4 + centroid 12 + AABB 24 read, id 4 written (44 B), plus one 48-byte record
@@ -694,11 +849,12 @@ def main():
         s_grid = float(np.mean([p["grid_interior_prims"] for p in phase_lib]))
         n_grid = float(np.mean([p["grid_nodes"] for p in phase_lib]))
         grid_bytes = 44.0 * s_grid + 48.0 * n_grid
-        grid_gbps = grid_bytes / (lib_ms["ms_grid"] * 1e-3) / 1e9
+        grid_ms = lib_ms["ms_grid"] + lib_ms["ms_cluster"]
+        grid_gbps = grid_bytes / (grid_ms * 1e-3) / 1e9
         build_roof = {"bound": "hbm", "achieved": grid_gbps, "peak": peak, "unit": "GB/s", "frac": grid_gbps / peak,
                       "traffic": (tr["k_t1_coop"] if tr else None), "peak_source": peak_src,
                       "kernel": "k_t1_coop (grid tier: every node above 16384 triangles, one cooperative launch per build)",
-                      "launch_ms": lib_ms["ms_grid"], "share_of_build": lib_ms["ms_grid"] / lib_ms["ms_total"],
+                      "launch_ms": grid_ms, "share_of_build": grid_ms / lib_ms["ms_total"],
                       "algorithmic_bytes": grid_bytes, "S_grid": s_grid, "nodes_grid": n_grid,
                       "traffic_note": "ncu DRAM bytes of that launch; far below the algorithmic bytes because the working set stays in L2",
                       "whole_build": {"achieved": bb / (lib_ms["ms_total"] * 1e-3) / 1e9, "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak,
@@ -709,40 +865,68 @@ def main():
             rb_note = "visit counters unavailable (CPU leg skipped): compulsory bytes only"
         else:
             rb_note = "per-ray visit counters from the oracle on a 2^19-ray sample of the same distribution"
-        rb = ray_bytes(per_ray, 1)
+        rbytes = ray_bytes(per_ray, 1)
         scene_bytes = 32 * state["M"] + 12 * n_verts + 12 * n_tris + 5 * 32 + 2 * 192
-        ray_roof = {"bound": "hbm", "achieved": rb * n_rays / (r_ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": rb * n_rays / (r_ms_step * 1e-3) / 1e9 / peak,
-                    "traffic": (tr.get("k_trace_any_16Mi") if (tr and n_rays == N_RAYS) else None), "peak_source": peak_src,
-                    "kernel": "k_trace_any (one launch per step; the exact-order kernel that takes deferred rays runs empty)", "bytes_per_ray": rb, "counters_per_ray": per_ray,
-                    "compulsory_GBps": ((25 * n_rays + scene_bytes) / (r_ms_step * 1e-3) / 1e9), "note": rb_note}
+        ray_ms_1gpu = r_ms_step  # the shard's launch
+        ray_roof = ray_roofline(rbytes, per_ray, n_shard, ray_ms_1gpu, scene_bytes, tr, peak, peak_src, rb_note)
+        gather_bytes = 4 * (world - 1) * slot_w
         line = {
             "metric": "dragon_blas_build_Mtris_per_s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": s_tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tris": n_tris, "rays_per_gpu": n_rays, "l2": "flushed between timed iterations (256 MiB fill)",
-                       "multi_gpu": "build: replicas only; rays: sharded, no collective"},
-            "phase_ms": {"build": b_ms_step, "tlas": t_tot / args.steps, "trace": r_ms_step},
+            "config": config2_dict(n_tris, n_rays, world),
+            "phase_ms": {"build": b_ms_step, "all_gather": g_ms_step, "tlas": t_tot / args.steps, "trace_shard": r_ms_step},
             "phase_ms_dragon": lib_ms,
             "roofline": build_roof,
             "cpu_baseline": cpu_build,
             "e2e": {"value": world * n_dtris / e2e_b / 1e6, "unit": "Mtris/s", "ms": e2e_b * 1e3,
                     "h2d_bytes_per_step": int(dv.nbytes + di.nbytes), "d2h_bytes_per_step": int(32 * m_dragon + di.nbytes),
-                    "api": "bvh_cuda_blas_build (host pointers, pinned)"},
+                    "api": "bvh_cuda_blas_build (host pointers, pinned), one distinct mesh per rank"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "multi_gpu": None if world == 1 else {
+                "what": "per step every rank builds its own dragon-class mesh in place inside its slot of the pooled array, then ONE in-place NCCL all-gather (vertices | permuted indices | used nodes) gives every GPU all meshes; `value` = world x tris / (build + all-gather)",
+                "bare_all_gather_ms": bare_ms,
+                "all_gather_ms": g_ms_step, "all_gather_bytes_received_per_gpu": int(gather_bytes),
+                "all_gather_GBps_per_gpu": gather_bytes / (g_ms_step * 1e-3) / 1e9 if g_ms_step > 0 else None,
+                "build_only_Mtris_per_s_per_gpu": n_tris / (b_ms_step * 1e-3) / 1e6},
             "rays": {"metric": "shadow_ray_Mrays_per_s", "value": rvalue, "unit": "Mrays/s", "ms": r_ms_step, "occluded_frac": occ_frac,
+                     "scaling": "strong: the fixed batch of %d rays split over %d rank(s) in block-cyclic 64 Ki-ray chunks, max over ranks" % (n_rays, world),
                      "order": "surface-raster (G-buffer-like) ray order; incoherent = same rays, one fixed random permutation",
-                     "incoherent": {"value": world * n_rays / (inc_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms": inc_ms},
+                     "incoherent": {"value": n_rays / (inc_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms": inc_ms},
+                     "weak": None if world == 1 else {"value": world * n_rays / (weak_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms": weak_ms,
+                                                      "what": "every rank traces the whole batch (work per GPU fixed)",
+                                                      "e2e": {"value": world * n_rays / e2e_w / 1e6, "unit": "Mrays/s", "ms": e2e_w * 1e3,
+                                                              "h2d_bytes_per_step": int(ro.nbytes + rd.nbytes), "d2h_bytes_per_step": int(n_rays)}},
                      "roofline": ray_roof, "cpu_baseline": cpu_rays,
-                     "e2e": {"value": world * n_rays / e2e_r / 1e6, "unit": "Mrays/s", "ms": e2e_r * 1e3,
-                             "h2d_bytes_per_step": int(ro.nbytes + rd.nbytes), "d2h_bytes_per_step": int(n_rays),
-                             "api": "bvh_cuda_trace_any (host pointers, pinned)"}},
+                     "e2e": {"value": n_rays / e2e_r / 1e6, "unit": "Mrays/s", "ms": e2e_r * 1e3,
+                             "h2d_bytes_per_step": int(24 * n_shard), "d2h_bytes_per_step": int(n_shard),
+                             "api": "bvh_cuda_trace_any (host pointers, pinned), the rank's shard of the batch"}},
+            "config5": c5,
             "wall_s_timed_region_incl_flush": t_wall,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ray_roofline(rbytes, per_ray, n_rays, ms, scene_bytes, tr, peak, peak_src, note):
+    """Traversal is served from L2 (the 60 MB scene is resident), so the byte model of SURVEY 8(d) is compared with the
+    L2 bandwidth, and the DRAM side is reported separately as measured bytes against the HBM peak; the issue-slot
+    fraction (ncu) says how close the kernel is to its real bound, instruction issue."""
+    l2 = tr.get("l2_peak_GBps") if tr else None
+    model_gbps = rbytes * n_rays / (ms * 1e-3) / 1e9
+    dram = tr.get("k_trace_any_16Mi") if (tr and n_rays == N_RAYS) else None
+    out = {"bound": "hbm", "achieved": ((dram / (ms * 1e-3) / 1e9) if dram else (25 * n_rays + scene_bytes) / (ms * 1e-3) / 1e9),
+           "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": dram,
+           "achieved_is": "measured DRAM bytes of one launch (ncu) / launch time" if dram else "compulsory bytes (24 B in + 1 B out per ray + the scene once) / launch time",
+           "kernel": "k_trace_any (one launch per step; the exact-order kernel that takes deferred rays runs empty)",
+           "l2_model": {"bytes_per_ray": rbytes, "GBps": model_gbps, "l2_peak_GBps": l2, "frac_of_l2": (model_gbps / l2) if l2 else None,
+                        "note": "SURVEY 8(d) byte model x rays / time: node and triangle fetches are L2 hits, so this is L2 traffic, not HBM"},
+           "issue": (tr.get("k_trace_any_issue") if tr else None),
+           "counters_per_ray": per_ray, "note": note}
+    out["frac"] = out["achieved"] / peak
+    return out
 
 
 if __name__ == "__main__":

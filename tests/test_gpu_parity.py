@@ -46,8 +46,7 @@ def test_blas_bit_exact_grid_tier(ctx, oracle, n, seed, edge):
     rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
     assert rc == 0 and bvh.nodes.tobytes() == onodes.tobytes() and (gi == oidx).all()
     st = ctx.last_build_stats()
-    # nodes above 16 384 triangles: cluster tier up to 262 144, grid tier (level-synchronous) above that
-    assert st["cluster_tasks"] >= (2 if n >= 100_000 else 1) and st["grid_levels"] >= (1 if n > 262_144 else 0)
+    assert st["grid_levels"] >= (2 if n >= 100_000 else 1) and st["cluster_tasks"] == 0  # (the cluster tier is opt-in)
     assert st["big_block_tasks"] > 0 and st["block_tasks"] > 0
     assert st["warp_node_tasks"] > 0 and st["warp_tasks"] > 0 and st["thread_tasks"] > 0
 
@@ -68,18 +67,25 @@ def _build_in_child(meshes, mode, env):
         return outs, json.loads(bytes(d["stats"]).decode())
 
 
-def test_blas_grid_tier_alone_still_exact_without_the_cluster_tier(oracle):
-    """BVH_CUDA_NO_CLUSTER=1 (A/B switch, read once per process): every node above 16 384 triangles goes through the
-    level-synchronous grid tier, as in round 1 — a single mesh, and a forest whose grid-tier levels have more tiles
-    than the cooperative kernel has blocks (every block walks several tiles per phase)."""
-    v, idx = S.soup(150_000, 7, 0.01)
-    outs, st = _build_in_child([(v, idx)], "single", {"BVH_CUDA_NO_CLUSTER": "1"})
-    rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
-    assert st["cluster_tasks"] == 0 and st["grid_levels"] >= 2, st
-    assert rc == 0 and outs[0][0].tobytes() == onodes.tobytes() and (outs[0][1] == oidx).all()
-    meshes = [S.soup(30_000 + 997 * k, 400 + k, 0.02) for k in range(36)]  # 36 x ~15 tiles of 2048 > 444 blocks
-    outs, st = _build_in_child(meshes, "forest", {"BVH_CUDA_NO_CLUSTER": "1"})
-    assert st["cluster_tasks"] == 0 and st["grid_levels"] >= 1 and st["grid_nodes"] >= len(meshes), st
+@pytest.mark.parametrize("mode", ["smem", "global"])
+def test_blas_cluster_tier_variants_bit_exact(oracle, mode):
+    """BVH_CUDA_TC=smem|global (read once per process, hence the child process) routes nodes of 16 385..262 144 triangles
+    to the opt-in cluster tier: one node per 16-CTA thread-block cluster, order resident in distributed shared memory
+    (k_tcs) or in global memory (k_tc).  Same bytes as the oracle for single meshes around the tier's boundaries (one
+    with -0.0 coordinates) and for a forest with five times more cluster tasks than co-resident clusters."""
+    nz = S.soup(40_000, 12, 0.02)
+    q = np.float32(1 / 64)
+    nzv = (np.round(nz[0] / q) * q).astype(np.float32) - np.float32(0.5)
+    nzv[nzv == 0] = np.float32(-0.0)
+    singles = [S.soup(17_000, 5, 0.02), S.soup(150_000, 7, 0.01), S.soup(300_000, 21, 0.01), (nzv, nz[1])]
+    outs, st = _build_in_child(singles, "single", {"BVH_CUDA_TC": mode})
+    assert st["cluster_tasks"] >= 1, st
+    for (v, idx), (nodes, perm) in zip(singles, outs):
+        rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+        assert rc == 0 and nodes.tobytes() == onodes.tobytes() and (perm == oidx).all()
+    meshes = [S.soup(30_000 + 997 * k, 400 + k, 0.02) for k in range(36)]
+    outs, st = _build_in_child(meshes, "forest", {"BVH_CUDA_TC": mode})
+    assert st["cluster_tasks"] >= len(meshes) and st["grid_levels"] == 0, st
     for (v, idx), (nodes, perm) in zip(meshes, outs):
         rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
         assert rc == 0 and nodes.tobytes() == onodes.tobytes() and (perm == oidx).all()
@@ -391,9 +397,9 @@ def test_blas_batch_forest_build_equals_per_mesh_builds(ctx, oracle):
     assert (sc.indices.cpu().numpy().view(np.uint32) == inds).all()
 
 
-def test_blas_forest_with_more_cluster_tasks_than_clusters(ctx, oracle):
-    """A forest of 36 roots of 30-65 K triangles: five times more cluster-tier tasks than co-resident clusters, all posted
-    at once by k_roots (the grid-tier twin of this case runs in test_blas_grid_tier_alone_still_exact_without_the_cluster_tier)."""
+def test_blas_forest_with_more_grid_tiles_than_blocks(ctx, oracle):
+    """A forest whose grid-tier levels have more tiles than the cooperative kernel has blocks while no single node is large
+    enough for the tile-scan path: every block walks several tiles per phase (PA leaves each tile's ballots for PB)."""
     import torch
     from voidin_b200 import multi_gpu as MG
 
@@ -402,7 +408,7 @@ def test_blas_forest_with_more_cluster_tasks_than_clusters(ctx, oracle):
     tm = [(torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(i.view(np.int32)).to(dev)) for v, i in meshes]
     outs = MG.cuda_build_batch_fn(ctx)(tm)
     st = ctx.last_build_stats()
-    assert st["cluster_tasks"] >= len(meshes) and st["grid_nodes"] >= len(meshes)
+    assert st["grid_levels"] >= 1 and st["grid_nodes"] >= len(meshes)
     for (v, idx), (nodes, perm) in zip(meshes, outs):
         rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
         assert rc == 0

@@ -78,6 +78,19 @@ def test_ray_ranges_partition_the_batch():
         assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
 
 
+def test_ray_chunks_are_a_block_cyclic_partition():
+    for n, w, c in [(10, 3, 4), (1 << 20, 8, 1 << 16), (100, 2, 7), (5, 8, 64), (0, 2, 16)]:
+        seen = np.zeros(n, dtype=np.int32)
+        sizes = []
+        for r in range(w):
+            ch = MG.ray_chunks(r, w, n, c)
+            assert all(b % c == 0 and (b // c) % w == r and b < e <= min(n, b + c) for b, e in ch)
+            for b, e in ch:
+                seen[b:e] += 1
+            sizes.append(sum(e - b for b, e in ch))
+        assert (seen == 1).all() and max(sizes) - min(sizes) <= c
+
+
 @pytest.mark.timeout(180)
 def test_sharded_build_world2_equals_single_process():
     from oracle import oracle as O

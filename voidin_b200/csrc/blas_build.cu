@@ -71,8 +71,16 @@ constexpr int T2_THREADS = 256;
 #endif
 constexpr int T2B_CAP = 16384;  // big-block tier: 2049..16384 (1024 threads, one block per SM)
 constexpr int T2B_THREADS = 1024;
-constexpr int T1_TILE = 2048;  // largest tile (8 slots per thread); levels that fit the grid with smaller tiles use them
-constexpr int T1_THREADS = 256;
+// Grid tier block shape: threads per block and blocks per SM.  Measured on the dragon-class build (grid tier ms):
+// see scripts/variants.py rows t1_512x2 / t1_1024x1 in profiles/r02_build_variants_ab.txt.
+#ifndef T1_THREADS_V
+#define T1_THREADS_V 256
+#endif
+#ifndef T1_MIN_BLOCKS
+#define T1_MIN_BLOCKS 3
+#endif
+constexpr int T1_THREADS = T1_THREADS_V;
+constexpr int T1_TILE = T1_THREADS * 8;  // largest tile (8 slots per thread); levels that fit the grid with smaller tiles use them
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 #define TF_RIGHT 1u
@@ -379,9 +387,12 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t max_large = N / T2B_CAP + 2;
     // (a level uses tiles smaller than T1_TILE only when it then has no more tiles than the grid has blocks)
     const uint32_t max_tiles = N / T1_TILE + max_large + 2 + (uint32_t)ctx->sm_count * 16;
-    // cluster tier: on unless the device cannot place the clusters or BVH_CUDA_NO_CLUSTER is set (A/B runs)
-    static const bool tc_off = [] { const char* e = getenv("BVH_CUDA_NO_CLUSTER"); return e && e[0] == '1'; }();
-    const bool use_tc = !tc_off && ctx->tc_clusters > 0 && ctx->tc_cluster_size > 0;
+    // Cluster tier (one node of 16K-262K triangles per thread-block cluster): built, bit-exact and measured SLOWER than
+    // the level-synchronous grid tier on every workload tried (dragon-class: 6.12 / 6.32 ms against 6.00 ms; a forest of many
+    // mid-size meshes is far worse, 7 clusters take 7 nodes at a time), see DESIGN.md section 4 and profiles/r02_cluster_tier_*.
+    // It therefore stays opt-in: BVH_CUDA_TC=smem (order resident in distributed shared memory, k_tcs) or =global (k_tc).
+    static const int tc_mode = [] { const char* e = getenv("BVH_CUDA_TC"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'g' ? 2 : 0)); }();
+    const bool use_tc = tc_mode != 0 && ctx->tc_clusters > 0 && ctx->tc_cluster_size > 0;
     const uint32_t tc_cap = use_tc ? (uint32_t)ctx->tc_cluster_size * (uint32_t)TC_SLOTS : (uint32_t)T2B_CAP;
     const uint32_t qc_cap = N / 4096 + NM + 64;   // nodes with 16385..tc_cap primitives
     const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
@@ -516,9 +527,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        // BVH_CUDA_TC=global: the variant that keeps the node's order in global memory (k_tc); default: distributed shared memory
-        static const bool tc_global = [] { const char* e = getenv("BVH_CUDA_TC"); return e && e[0] == 'g'; }();
-        if (tc_global)
+        if (tc_mode == 2)
             CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_tc, Q, ids0, items, table, (const float4*)cent, (const float4*)box, recs, A, tcs, st, epoch));
         else
             CU_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_tcs, Q, ids0, ids1, (const float4*)cent, (const float4*)box, recs, A, st, epoch));

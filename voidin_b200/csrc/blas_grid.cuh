@@ -721,7 +721,7 @@ __device__ __forceinline__ void t1_level(const T1Args& g, const bool scanned, ui
 // of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (first form in
 // commit ac13e1f): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
 // descriptor read once per level (3.87 ms vs 3.70 ms); barriers restricted to the blocks that own a tile (3.67 vs 3.69).
-__global__ void __launch_bounds__(T1_THREADS, 3) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
+__global__ void __launch_bounds__(T1_THREADS, T1_MIN_BLOCKS) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
     LevelNode* lv[2] = {lv0, lv1};
     uint32_t gen = 0;

@@ -44,6 +44,16 @@ def ray_range(rank: int, world: int, n_rays: int) -> tuple[int, int]:
     return b, b + q + (1 if rank < rem else 0)
 
 
+def ray_chunks(rank: int, world: int, n_rays: int, chunk: int = 1 << 16) -> list[tuple[int, int]]:
+    """Block-cyclic shard of a ray batch: chunk k (rays [k*chunk, (k+1)*chunk)) goes to rank k % world.  A frame's rays are
+    not uniform in cost (pixels on the model against pixels on empty ground), so contiguous halves leave one rank with
+    all the expensive rays; chunks of 64 Ki rays keep the coherence inside a warp / block and balance the ranks."""
+    out = []
+    for k in range(rank, (n_rays + chunk - 1) // chunk, world):
+        out.append((k * chunk, min(n_rays, (k + 1) * chunk)))
+    return out
+
+
 @dataclass
 class PooledScene:
     vertices: torch.Tensor   # float32 [V*3]
@@ -123,6 +133,11 @@ def build_sharded(meshes_of_rank: dict[int, tuple[torch.Tensor, torch.Tensor]], 
     vertices = torch.cat(vs).view(torch.float32)
     indices = torch.cat(is_)
     bvh_nodes = torch.cat(ns)
+    if timings is not None:
+        timings["gather_bytes_received"] = 4 * (world - 1) * pad  # what the collective delivered to this rank
+        if dev.type == "cuda":
+            timings["after_assemble"] = torch.cuda.Event(enable_timing=True)
+            timings["after_assemble"].record()
     info = np.zeros(n_meshes, dtype=MESH_INFO)
     info["min"] = mesh_bounds[:, 0]
     info["max"] = mesh_bounds[:, 1]
