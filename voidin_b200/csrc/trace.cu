@@ -8,7 +8,8 @@
 //                  exactly traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102).
 //   k_trace_any    the same any-hit answer without the reference's visit order (see the comment above the kernel);
 //                  this is what bvh_cuda_trace_any runs, k_trace_scene<true> takes the rays it defers.
-// One thread per ray; nodes are fetched as two 16-byte loads (32-byte aligned); per-ray stacks live in
+// One thread per ray; nodes are fetched as two 16-byte loads (32-byte aligned), the top of the TLAS from a copy in
+// shared memory (TlasTop); per-ray stacks live in
 // local memory (64 entries; the reference's 32 / 24-entry stacks overflow silently on deeper trees).
 // Compiled with -fmad=false: hit ids depend on exact, unfused float arithmetic in the reference's order.
 #include "common.cuh"
@@ -39,6 +40,37 @@ __device__ __forceinline__ NodeW ld_node(const void* base, uint32_t i) {
     n.a = __ldg(p);
     n.b = __ldg(p + 1);
     return n;
+}
+
+// ---- top of the TLAS in shared memory -------------------------------------------------------------------
+// Tlas::build appends every merged node (tlas.rs:64-73), so the nodes nearest the root are the LAST ones of the array
+// (plus node 0, the copy of the root, tlas.rs:84).  Every ray starts there and every block walks them all the time:
+// each block of the two-level kernels stages the last TLAS_TOP nodes (and node 0, and their unpacked child pairs when
+// the side buffer exists) in shared memory once and serves those fetches from there; deeper nodes come through L1/L2.
+constexpr int TLAS_TOP = 255;  // + node 0 = 256 staged nodes: 8 KB of nodes + 2 KB of child pairs per block
+struct TlasTop {
+    float4 n[2 * (TLAS_TOP + 1)];
+    uint2 kids[TLAS_TOP + 1];
+};
+__device__ __forceinline__ uint32_t tlas_top_first(size_t n_tlas_nodes) {
+    return n_tlas_nodes > (size_t)TLAS_TOP + 1 ? (uint32_t)(n_tlas_nodes - TLAS_TOP) : 1u;
+}
+__device__ __forceinline__ void tlas_top_load(TlasTop& t, const BvhCudaSceneDesc& sc) {
+    const uint32_t first = tlas_top_first(sc.n_tlas_nodes);
+    const uint32_t cnt = (uint32_t)sc.n_tlas_nodes - first;  // nodes [first, n) -> slots [1, cnt]; node 0 -> slot 0
+    const float4* g = reinterpret_cast<const float4*>(sc.tlas_nodes);
+    for (uint32_t i = threadIdx.x; i < 2 * (cnt + 1); i += blockDim.x) {
+        const uint32_t slot = i >> 1, node = slot == 0 ? 0u : first + slot - 1;
+        t.n[i] = __ldg(g + 2 * (size_t)node + (i & 1));
+    }
+    if (sc.tlas_children)
+        for (uint32_t slot = threadIdx.x; slot <= cnt; slot += blockDim.x)
+            t.kids[slot] = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + (slot == 0 ? 0u : first + slot - 1));
+    __syncthreads();
+}
+// slot of TLAS node ni in the staged copy, or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t tlas_top_slot(uint32_t ni, uint32_t first) {
+    return ni >= first ? ni - first + 1 : (ni == 0 ? 0u : 0xFFFFFFFFu);
 }
 
 // ---- Rust-mode tests --------------------------------------------------------------------------------
@@ -305,6 +337,9 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
         if (list_ctl[2] != 0) list = nullptr;
         else R = (size_t)list_ctl[0];
     }
+    __shared__ TlasTop s_top;
+    tlas_top_load(s_top, sc);
+    const uint32_t top_first = tlas_top_first(sc.n_tlas_nodes);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t tstack[TLAS_STACK_CAP], bstack[STACK_CAP];
@@ -382,7 +417,10 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
             if (want_tlas) {
                 // traverse_tlas (bvh.wgsl:89-123): one pop
                 const uint32_t ni = tstack[--th];
-                const NodeW node = ld_node(sc.tlas_nodes, ni);
+                const uint32_t nslot = tlas_top_slot(ni, top_first);
+                NodeW node;
+                if (nslot != 0xFFFFFFFFu) { node.a = s_top.n[2 * nslot]; node.b = s_top.n[2 * nslot + 1]; }
+                else node = ld_node(sc.tlas_nodes, ni);
                 const uint32_t left_right = __float_as_uint(node.a.w);
                 if (left_right == 0) {
                     // instance_intersect (bvh.wgsl:78-87)
@@ -400,7 +438,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                 } else {
                     uint32_t min_index, max_index;
                     if (sc.tlas_children) {
-                        const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        const uint2 k = nslot != 0xFFFFFFFFu ? s_top.kids[nslot] : __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
                         min_index = k.x; max_index = k.y;
                     } else {
                         min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
@@ -409,7 +447,12 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                     // node.  Its second traversal can never accept a triangle (same boxes, hit only shrinks,
                     // acceptance is strict t < hit), so it is skipped: results are identical.
                     const bool twin = (min_index == max_index);
-                    const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
+                    NodeW ca, cb;
+                    {
+                        const uint32_t sa = tlas_top_slot(min_index, top_first), sb = tlas_top_slot(max_index, top_first);
+                        if (sa != 0xFFFFFFFFu) { ca.a = s_top.n[2 * sa]; ca.b = s_top.n[2 * sa + 1]; } else ca = ld_node(sc.tlas_nodes, min_index);
+                        if (sb != 0xFFFFFFFFu) { cb.a = s_top.n[2 * sb]; cb.b = s_top.n[2 * sb + 1]; } else cb = ld_node(sc.tlas_nodes, max_index);
+                    }
                     float min_dist = aabb_w(eye, inv, ca.a, ca.b, dist);
                     float max_dist = aabb_w(eye, inv, cb.a, cb.b, dist);
                     if (min_dist > max_dist) {
@@ -491,6 +534,9 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                                                    const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                    float tmax, uint8_t* occ_out, unsigned long long* ctl,
                                                    uint32_t* defer_list) {
+    __shared__ TlasTop s_top;
+    tlas_top_load(s_top, sc);
+    const uint32_t top_first = tlas_top_first(sc.n_tlas_nodes);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool pair_rule = tmax >= MAXD;  // a missed far child is pushed iff 1e30 <= hit (bvh.wgsl:71)
@@ -590,7 +636,10 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                 finished = true;
             } else {
                 const uint32_t ni = tstack[--th];
-                const NodeW node = ld_node(sc.tlas_nodes, ni);
+                const uint32_t nslot = tlas_top_slot(ni, top_first);
+                NodeW node;
+                if (nslot != 0xFFFFFFFFu) { node.a = s_top.n[2 * nslot]; node.b = s_top.n[2 * nslot + 1]; }
+                else node = ld_node(sc.tlas_nodes, ni);
                 const uint32_t left_right = __float_as_uint(node.a.w);
                 if (left_right == 0) {
                     // instance_intersect (bvh.wgsl:78-87): the BLAS root is visited without a box test
@@ -612,13 +661,18 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                 } else {
                     uint32_t min_index, max_index;
                     if (sc.tlas_children) {
-                        const uint2 k = __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        const uint2 k = nslot != 0xFFFFFFFFu ? s_top.kids[nslot] : __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
                         min_index = k.x; max_index = k.y;
                     } else {
                         min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
                     }
                     const bool twin = (min_index == max_index);
-                    const NodeW ca = ld_node(sc.tlas_nodes, min_index), cb = ld_node(sc.tlas_nodes, max_index);
+                    NodeW ca, cb;
+                    {
+                        const uint32_t sa = tlas_top_slot(min_index, top_first), sb = tlas_top_slot(max_index, top_first);
+                        if (sa != 0xFFFFFFFFu) { ca.a = s_top.n[2 * sa]; ca.b = s_top.n[2 * sa + 1]; } else ca = ld_node(sc.tlas_nodes, min_index);
+                        if (sb != 0xFFFFFFFFu) { cb.a = s_top.n[2 * sb]; cb.b = s_top.n[2 * sb + 1]; } else cb = ld_node(sc.tlas_nodes, max_index);
+                    }
                     const float d0 = aabb_w(eye, inv, ca.a, ca.b, tmax);
                     const float d1 = aabb_w(eye, inv, cb.a, cb.b, tmax);
                     // traverse_tlas pushes a child iff its distance is below `dist` (bvh.wgsl:116-119), == tmax here
