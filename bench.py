@@ -37,7 +37,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_RAYS = 16 * 1024 * 1024
-WORKLOAD = "config2: dragon_class BLAS build (871422 tris, stand-in for assets/dragon.obj) + 16Mi any-hit shadow rays toward a rect area light"
+def workload_label():
+    from voidin_b200 import models as M
+    mesh = "assets/dragon.obj (read by the product's OBJ loader)" if M.find_asset("dragon.obj") else "dragon_class (871422 tris, stand-in for assets/dragon.obj)"
+    return f"config2: {mesh} BLAS build + 16Mi any-hit shadow rays toward a rect area light"
 
 
 def peaks():
@@ -47,10 +50,31 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def asset_or_standin(name: str, seed=None):
+    """(vertices, indices, label): a dropped-in voidin asset ($VOIDIN_ASSETS/<name> or <repo>/assets/<name>) read by the
+    product's own loader (ObjModel.import_ = tobj GPU_LOAD_OPTIONS, crates/app/src/models/mod.rs:24), else the synthetic
+    stand-in of the same size class (the reference checkout lists bunny.obj / dragon.obj in .MISSING_LARGE_BLOBS).
+    seed: a distinct mesh of the same size (weak-scaled builds): the asset uniformly rescaled, or the stand-in reseeded."""
+    from voidin_b200 import models as M
+    from voidin_b200 import scenes as S
+
+    path = M.find_asset(name)
+    if path:
+        v, i = M.load_single_mesh(path)
+        if seed is not None:
+            v = (v * np.float32(1.0 + 1e-3 * seed)).astype(np.float32)
+        return v, i, f"assets/{name} ({i.size // 3} tris, loaded by bvh_cuda_model_load_obj)"
+    if name == "dragon.obj":
+        v, i = S.dragon_class() if seed is None else S.dragon_class(seed=seed)
+        return v, i, f"dragon_class ({i.size // 3} tris, stand-in for assets/dragon.obj)"
+    v, i = S.bunny_class()
+    return v, i, f"bunny_class ({i.size // 3} tris, stand-in for assets/bunny.obj)"
+
+
 def build_inputs(rank: int, n_rays: int):
     from voidin_b200 import scenes as S
 
-    dv, di = S.dragon_class()
+    dv, di, _ = asset_or_standin("dragon.obj")
     pv, pi = S.make_plane_mesh()
     mats, mesh_ids = S.dragon_scene_instances()
     inst = S.make_instances(mats, mesh_ids)
@@ -146,7 +170,7 @@ def run_reference(args, rank, world):
 
     threads = O.max_threads()
     total = args.steps + args.warmup
-    dv, di = S.dragon_class()
+    dv, di, _ = asset_or_standin("dragon.obj")
     pv, pi = S.make_plane_mesh()
     mats, mesh_ids = S.dragon_scene_instances()
     inst = S.make_instances(mats, mesh_ids)
@@ -277,7 +301,7 @@ def run_small_configs(args, local_rank):
                     "roofline": {"bound": "hbm", "achieved": bb / (b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": bb / (b_ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes": bb}})
     elif args.workload == "bunny":
-        v, idx = S.bunny_class()
+        v, idx, bunny_label = asset_or_standin("bunny.obj")
         n = idx.size // 3
         d_v, d_i0 = up(v, np.float32), up(idx, np.int32)
         d_i = d_i0.clone()
@@ -297,12 +321,12 @@ def run_small_configs(args, local_rank):
         r_ms = timed(lambda: ctx.trace_blas_dev(d_nodes.data_ptr(), d_v.data_ptr(), d_i.data_ptr(), d_ro.data_ptr(), d_rd.data_ptr(),
                                                 n_rays, d_t.data_ptr(), d_tri.data_ptr(), stream), steps)
         out.update({"metric": "bunny_blas_build_Mtris_per_s", "value": n / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": b_ms + r_ms,
-                    "config": {"workload": f"config1: bunny_class BLAS ({n} tris) + {n_rays} closest-hit rays, Bvh::traverse_iter semantics"},
+                    "config": {"workload": f"config1: {bunny_label} BLAS + {n_rays} closest-hit rays, Bvh::traverse_iter semantics"},
                     "phase_ms": {"build": b_ms, "trace": r_ms},
                     "rays": {"metric": "closest_hit_Mrays_per_s", "value": n_rays / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                              "hit_frac": float((d_tri != -1).float().mean().item())}})
     else:
-        meshes = [S.bunny_class(), S.dragon_class(), S.displaced_sphere(62, 124, 3)]  # third = DamagedHelmet-sized stand-in
+        meshes = [asset_or_standin("bunny.obj")[:2], asset_or_standin("dragon.obj")[:2], S.displaced_sphere(62, 124, 3)]  # third = DamagedHelmet-sized stand-in for ferris3d
         n_inst = args.instances
         tm = [(up(v, np.float32), up(i, np.int32)) for v, i in meshes]
         info = np.zeros(len(meshes), dtype=MESH_INFO)
@@ -550,7 +574,7 @@ def run_scene1024(args, rank, local_rank, world):
 
 def config2_dict(n_tris, n_rays, world):
     """`config` of the headline line; the reference arm prints the same dict (it times the same workload on the CPU)."""
-    return {"workload": WORKLOAD, "tris": n_tris, "rays": n_rays, "l2": "flushed between timed iterations (256 MiB fill)",
+    return {"workload": workload_label(), "tris": n_tris, "rays": n_rays, "l2": "flushed between timed iterations (256 MiB fill)",
             "multi_gpu": ("one rank" if world == 1 else
                           f"build: {world} distinct dragon-class meshes, one per rank (a single BLAS does not shard), then NCCL all-gather of "
                           "vertices / permuted indices / nodes so that every GPU holds all of them (weak scaling); rays: the fixed "
@@ -611,7 +635,7 @@ def run_dragon(args, rank, local_rank, world):
 
     # ---- inputs.  Mesh 2+rank is built by this rank; mesh 2 (rank 0's) is the one every rank traces. ----
     dv0, di0, pv, pi, inst, ro, rd = build_inputs(0, args.rays)
-    dv, di = (dv0, di0) if rank == 0 else S.dragon_class(seed=2 + rank)
+    dv, di = (dv0, di0) if rank == 0 else asset_or_standin("dragon.obj", seed=2 + rank)[:2]
     assert dv.shape == dv0.shape and di.shape == di0.shape
     n_dtris, n_ptris = di.size // 3, pi.size // 3
     n_tris = n_dtris + n_ptris

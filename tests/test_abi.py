@@ -13,8 +13,8 @@ from voidin_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_functions():
-    src = open(os.path.join(ROOT, "include", "bvh_cuda.h")).read()
+def _declared_functions(header="bvh_cuda.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(bvh_cuda_[a-z_0-9]+)\s*\(", src)))
 
@@ -27,6 +27,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/bvh_cuda.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
     assert lib.bvh_cuda_abi_version() == 4
+    model_names = _declared_functions("bvh_cuda_models.h")
+    assert len(model_names) == 10
+    for n in model_names:
+        assert hasattr(lib, n), f"{n} declared in include/bvh_cuda_models.h but not exported"
 
 
 def test_struct_layouts_match_the_reference():
@@ -80,7 +84,7 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
 
     inc = os.path.join(ROOT, "include")
     c_src = tmp_path / "t.c"
-    c_src.write_text('#include "bvh_cuda.h"\nint main(void){ return sizeof(BvhNode)==32 && sizeof(TlasNode)==32 && sizeof(Instance)==144 && sizeof(MeshInfo)==48 ? 0 : 1; }\n')
+    c_src.write_text('#include "bvh_cuda.h"\n#include "bvh_cuda_models.h"\nint main(void){ return sizeof(BvhNode)==32 && sizeof(TlasNode)==32 && sizeof(Instance)==144 && sizeof(MeshInfo)==48 ? 0 : 1; }\n')
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, str(c_src), "-o", str(tmp_path / "t_c")])
     assert subprocess.call([str(tmp_path / "t_c")]) == 0
     cxx_src = tmp_path / "t.cpp"

@@ -72,6 +72,25 @@ __device__ __forceinline__ void tlas_top_load(TlasTop& t, const BvhCudaSceneDesc
 __device__ __forceinline__ uint32_t tlas_top_slot(uint32_t ni, uint32_t first) {
     return ni >= first ? ni - first + 1 : (ni == 0 ? 0u : 0xFFFFFFFFu);
 }
+// TOP = false: the instantiation for scenes whose TLAS is a handful of nodes (BASELINE config 2 has 5): staging cannot
+// save anything there and the slot arithmetic costs ~4 % of the any-hit kernel, so those launches skip it.
+template <bool TOP>
+__device__ __forceinline__ NodeW tlas_node(const TlasTop& t, const BvhCudaSceneDesc& sc, uint32_t ni, uint32_t first) {
+    if (TOP) {
+        const uint32_t s = tlas_top_slot(ni, first);
+        if (s != 0xFFFFFFFFu) { NodeW n; n.a = t.n[2 * s]; n.b = t.n[2 * s + 1]; return n; }
+    }
+    return ld_node(sc.tlas_nodes, ni);
+}
+template <bool TOP>
+__device__ __forceinline__ uint2 tlas_kids(const TlasTop& t, const BvhCudaSceneDesc& sc, uint32_t ni, uint32_t first) {
+    if (TOP) {
+        const uint32_t s = tlas_top_slot(ni, first);
+        if (s != 0xFFFFFFFFu) return t.kids[s];
+    }
+    return __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+}
+constexpr size_t TLAS_TOP_MIN_NODES = 64;  // stage from this many TLAS nodes on
 
 // ---- Rust-mode tests --------------------------------------------------------------------------------
 struct RDist {
@@ -324,7 +343,7 @@ __device__ __forceinline__ uint32_t pack_meta(const NodeW& n) {
 // triangle test — so no lane waits for another ray's loop to end.  At the top of each iteration (a converged point)
 // idle lanes grab the next unprocessed rays from a global counter (one warp-aggregated atomicAdd).  The per-ray
 // visit order is exactly the reference's; only the lane/ray assignment is dynamic.
-template <bool ANY>
+template <bool ANY, bool TOP>
 __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                      const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                      float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out,
@@ -338,7 +357,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
         else R = (size_t)list_ctl[0];
     }
     __shared__ TlasTop s_top;
-    tlas_top_load(s_top, sc);
+    if (TOP) tlas_top_load(s_top, sc);
     const uint32_t top_first = tlas_top_first(sc.n_tlas_nodes);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -417,10 +436,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
             if (want_tlas) {
                 // traverse_tlas (bvh.wgsl:89-123): one pop
                 const uint32_t ni = tstack[--th];
-                const uint32_t nslot = tlas_top_slot(ni, top_first);
-                NodeW node;
-                if (nslot != 0xFFFFFFFFu) { node.a = s_top.n[2 * nslot]; node.b = s_top.n[2 * nslot + 1]; }
-                else node = ld_node(sc.tlas_nodes, ni);
+                const NodeW node = tlas_node<TOP>(s_top, sc, ni, top_first);
                 const uint32_t left_right = __float_as_uint(node.a.w);
                 if (left_right == 0) {
                     // instance_intersect (bvh.wgsl:78-87)
@@ -438,7 +454,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                 } else {
                     uint32_t min_index, max_index;
                     if (sc.tlas_children) {
-                        const uint2 k = nslot != 0xFFFFFFFFu ? s_top.kids[nslot] : __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        const uint2 k = tlas_kids<TOP>(s_top, sc, ni, top_first);
                         min_index = k.x; max_index = k.y;
                     } else {
                         min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
@@ -447,12 +463,7 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                     // node.  Its second traversal can never accept a triangle (same boxes, hit only shrinks,
                     // acceptance is strict t < hit), so it is skipped: results are identical.
                     const bool twin = (min_index == max_index);
-                    NodeW ca, cb;
-                    {
-                        const uint32_t sa = tlas_top_slot(min_index, top_first), sb = tlas_top_slot(max_index, top_first);
-                        if (sa != 0xFFFFFFFFu) { ca.a = s_top.n[2 * sa]; ca.b = s_top.n[2 * sa + 1]; } else ca = ld_node(sc.tlas_nodes, min_index);
-                        if (sb != 0xFFFFFFFFu) { cb.a = s_top.n[2 * sb]; cb.b = s_top.n[2 * sb + 1]; } else cb = ld_node(sc.tlas_nodes, max_index);
-                    }
+                    const NodeW ca = tlas_node<TOP>(s_top, sc, min_index, top_first), cb = tlas_node<TOP>(s_top, sc, max_index, top_first);
                     float min_dist = aabb_w(eye, inv, ca.a, ca.b, dist);
                     float max_dist = aabb_w(eye, inv, cb.a, cb.b, dist);
                     if (min_dist > max_dist) {
@@ -530,12 +541,13 @@ __device__ __forceinline__ bool inv_usable(const float* inv) {
     return isfinite(inv[0]) && isfinite(inv[1]) && isfinite(inv[2]) && inv[0] != 0.0f && inv[1] != 0.0f && inv[2] != 0.0f;
 }
 
+template <bool TOP>
 __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                    const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                    float tmax, uint8_t* occ_out, unsigned long long* ctl,
                                                    uint32_t* defer_list) {
     __shared__ TlasTop s_top;
-    tlas_top_load(s_top, sc);
+    if (TOP) tlas_top_load(s_top, sc);
     const uint32_t top_first = tlas_top_first(sc.n_tlas_nodes);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -636,10 +648,7 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                 finished = true;
             } else {
                 const uint32_t ni = tstack[--th];
-                const uint32_t nslot = tlas_top_slot(ni, top_first);
-                NodeW node;
-                if (nslot != 0xFFFFFFFFu) { node.a = s_top.n[2 * nslot]; node.b = s_top.n[2 * nslot + 1]; }
-                else node = ld_node(sc.tlas_nodes, ni);
+                const NodeW node = tlas_node<TOP>(s_top, sc, ni, top_first);
                 const uint32_t left_right = __float_as_uint(node.a.w);
                 if (left_right == 0) {
                     // instance_intersect (bvh.wgsl:78-87): the BLAS root is visited without a box test
@@ -661,18 +670,13 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                 } else {
                     uint32_t min_index, max_index;
                     if (sc.tlas_children) {
-                        const uint2 k = nslot != 0xFFFFFFFFu ? s_top.kids[nslot] : __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
+                        const uint2 k = tlas_kids<TOP>(s_top, sc, ni, top_first);
                         min_index = k.x; max_index = k.y;
                     } else {
                         min_index = left_right & 0xFFFFu; max_index = left_right >> 16;
                     }
                     const bool twin = (min_index == max_index);
-                    NodeW ca, cb;
-                    {
-                        const uint32_t sa = tlas_top_slot(min_index, top_first), sb = tlas_top_slot(max_index, top_first);
-                        if (sa != 0xFFFFFFFFu) { ca.a = s_top.n[2 * sa]; ca.b = s_top.n[2 * sa + 1]; } else ca = ld_node(sc.tlas_nodes, min_index);
-                        if (sb != 0xFFFFFFFFu) { cb.a = s_top.n[2 * sb]; cb.b = s_top.n[2 * sb + 1]; } else cb = ld_node(sc.tlas_nodes, max_index);
-                    }
+                    const NodeW ca = tlas_node<TOP>(s_top, sc, min_index, top_first), cb = tlas_node<TOP>(s_top, sc, max_index, top_first);
                     const float d0 = aabb_w(eye, inv, ca.a, ca.b, tmax);
                     const float d1 = aabb_w(eye, inv, cb.a, cb.b, tmax);
                     // traverse_tlas pushes a child iff its distance is below `dist` (bvh.wgsl:116-119), == tmax here
@@ -760,6 +764,9 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     static const bool wide_off = [] { const char* e = getenv("BVH_CUDA_ANYHIT"); return e && !strcmp(e, "exact"); }();
+    // top of the TLAS in shared memory (TlasTop): on from TLAS_TOP_MIN_NODES nodes; BVH_CUDA_TLAS_TOP=0 / 1 forces it (A/B)
+    static const int top_env = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e ? atoi(e) : -1; }();
+    const bool top = top_env >= 0 ? top_env != 0 : scene->d.n_tlas_nodes >= TLAS_TOP_MIN_NODES;
     if (any_hit && !wide_off && tmax <= MAXD && n_rays < 0xFFFFFFFFull) {
         // order-free kernel first; whatever it defers (normally nothing) goes through the exact kernel
         if (ctx->defer_cap < n_rays) {
@@ -771,20 +778,26 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
         }
         // persistent grid: exactly the resident blocks (more warps than that only start when the rays are gone)
         static const int any_bps = [] {
-            int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_any, 128, 0) != cudaSuccess || occ < 1) occ = 8;
-            return occ;
+            int occ = 0, occ_top = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_trace_any<false>, 128, 0) != cudaSuccess || occ < 1) occ = 8;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_top, k_trace_any<true>, 128, 0) != cudaSuccess || occ_top < 1) occ_top = 8;
+            return occ < occ_top ? occ : occ_top;
         }();
         const size_t cap_any = (size_t)ctx->sm_count * any_bps;
-        k_trace_any<<<(unsigned)(want < cap_any ? want : cap_any), 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ,
-                                                                                      counter, ctx->defer_list);
+        const unsigned blocks_any = (unsigned)(want < cap_any ? want : cap_any);
+        if (top) k_trace_any<true><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list);
+        else k_trace_any<false><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list);
         ctx->launches++;
-        k_trace_scene<true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
-                                                         counter + CTL_DEFER_RAY, ctx->defer_list, counter + CTL_DEFER_N);
-    } else if (any_hit)
-        k_trace_scene<true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
-    else
-        k_trace_scene<false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
+        // (the deferral pass normally finds an empty list: it runs without staging)
+        k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
+                                                                counter + CTL_DEFER_RAY, ctx->defer_list, counter + CTL_DEFER_N);
+    } else if (any_hit) {
+        if (top) k_trace_scene<true, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
+        else k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
+    } else {
+        if (top) k_trace_scene<false, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
+        else k_trace_scene<false, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
+    }
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return BVH_CUDA_OK;
