@@ -10,7 +10,7 @@ d_v = torch.from_numpy(dv.reshape(-1)).to(dev); d_i0 = torch.from_numpy(di.view(
 n = di.size // 3
 d_nodes = torch.zeros(2 * n * 8, dtype=torch.int32, device=dev)
 buf = (C.c_ulonglong * 32)()
-names = ["init", "bounds", "flags", "bins", "select", "count_final", "tilescan", "table", "scatter", "children", "nextlevel"]
+names = ["init", "bounds", "flags", "bins", "select", "count_final", "tilescan", "table", "scatter", "children", "nextlevel", "pull"]
 for k in range(3):
     d_i = d_i0.clone(); torch.cuda.synchronize()
     ctx.blas_build_dev(d_v.data_ptr(), dv.shape[0], d_i.data_ptr(), n, d_nodes.data_ptr(), 2 * n, 0)
@@ -22,6 +22,12 @@ for k in range(3):
         print(f"   {nm:12s} work {buf[2*i]/1e3:9.1f} us   barrier {buf[2*i+1]/1e3:9.1f} us")
         tw += buf[2*i]; tb += buf[2*i+1]
     print(f"   total work {tw/1e3:.1f} us, barrier {tb/1e3:.1f} us")
+    pl = (C.c_ulonglong * 4096)()
+    if hasattr(ctx.lib, "bvh_cuda_debug_t1_pull") and ctx.lib.bvh_cuda_debug_t1_pull(pl):
+        a = np.array(pl[:], dtype=np.float64).reshape(8, 512)[:, :444] / 22e3  # us per shuffle, level 0, thread 0 of every block
+        for k, nm in enumerate(["prefix", "partner cache", "pass 1 (select)", "pass 2 (gather+store)"]):
+            print(f"   level-0 pull {nm:22s}: per-block us/shuffle med {np.median(a[k]):.2f} p90 {np.percentile(a[k], 90):.2f} max {a[k].max():.2f}  by decile "
+                  f"{[round(float(a[k][i*42:(i+1)*42].mean()), 2) for i in range(10)]}")
     blk = (C.c_ulonglong * 2048)()
     if ctx.lib.bvh_cuda_debug_t1_blocks(blk):
         for kind, nm in enumerate(["table", "scatter"]):

@@ -205,3 +205,81 @@ def one_phase(flags, tile):
                     if p is not None and p < f:
                         put(p, q - 1)
     return dest, pivot, loads, moved
+
+
+def pull_form(flags, tile, warp_slots=None):
+    """The form the grid tier's resident-tile path runs (`t1_level_pull`): ONE barrier per shuffle.
+    Before the barrier every tile publishes its L count and its ballot words (+ the exclusive L prefix of each of its warps);
+    after it, every tile builds its own OUTPUT slots: src[p] = input position of the element that lands at p.  A slot is
+    either kept (front L), shifted (the back R one to the right), the boundary element f (at `pivot`), or a hole that is
+    filled by a rank-select in the ballots of a tile on the other side of f:
+        p <  f, R(p)                         <-  the L that has RF(p) L's after it            (a back L)
+        q = p+1 > f, L(q)  (or p == n-1)     <-  the R that has (L's after q) + 1 R's before it  (a front R; RF 0 for p = n-1)
+    Only per-tile counts, the boundary flags and the partner's ballots are used.  Returns (src, pivot, partner tiles
+    touched per tile)."""
+    n = len(flags)
+    L = np.asarray(flags, dtype=bool)
+    nt = (n + tile - 1) // tile
+    cnt = np.array([int(L[t * tile:(t + 1) * tile].sum()) for t in range(nt)], dtype=np.int64)
+    pre = np.concatenate([[0], np.cumsum(cnt)])
+    nL = int(pre[-1])
+    f, pivot = boundary(L, n, nL)
+    ws = warp_slots or max(1, tile // 8)  # slots per "warp" inside a tile: meta = per-warp exclusive L prefix + the bits
+
+    def select_in_tile(t, r, want_L):
+        """position of the r-th (0-based, from the tile's front) L (or R) of tile t, from its meta only"""
+        lo, hi = t * tile, min(n, (t + 1) * tile)
+        bits = L[lo:hi]
+        nw = (tile + ws - 1) // ws
+        wpre = [int(bits[:w * ws].sum()) for w in range(nw)]  # published: exclusive L prefix per warp
+        if not want_L:
+            wpre = [w * ws - wpre[w] for w in range(nw)]        # R prefix follows from it (tail slots beyond n count as R,
+        w = max(i for i in range(nw) if wpre[i] <= r)           #  but ranks never reach them)
+        r -= wpre[w]
+        for j in range(lo + w * ws, min(lo + (w + 1) * ws, hi)):
+            if bool(L[j]) == want_L:
+                if r == 0:
+                    return j
+                r -= 1
+        raise AssertionError("select past the end of the warp")
+
+    def pos_L_with_after(k):  # the L that has k L's after it
+        # tile t holds the L's whose L's-after count lies in [nL - pre[t+1], nL - pre[t])
+        t = int(np.searchsorted(pre, nL - k, side="left")) - 1   # largest t with pre[t] < nL - k  <=>  nL - pre[t] > k
+        assert nL - pre[t + 1] <= k < nL - pre[t]
+        kk = k - (nL - pre[t + 1])                 # from the tile's back
+        return select_in_tile(t, int(cnt[t]) - 1 - kk, True), t
+
+    rpre = np.array([t * tile for t in range(nt)] + [n], dtype=np.int64) - pre  # R's before tile t
+
+    def pos_R_with_before(k):  # the R that has k R's before it
+        t = int(np.searchsorted(rpre, k, side="right")) - 1      # largest t with rpre[t] <= k
+        assert rpre[t] <= k < rpre[t + 1]
+        return select_in_tile(t, k - int(rpre[t]), False), t
+
+    src = np.full(n, -1, dtype=np.int64)
+    partners = np.zeros(nt, dtype=np.int64)
+    for x in range(nt):
+        seen = set()
+        lf = int(pre[x])  # L's before p
+        for p in range(x * tile, min(n, (x + 1) * tile)):
+            lp = bool(L[p])
+            q = p + 1
+            if p == pivot:
+                src[p] = f
+            elif p < f and lp:
+                src[p] = p
+            elif p < f:
+                src[p], t = pos_L_with_after(p - lf)
+                seen.add(t)
+            elif q < n and q > f and not L[q]:
+                src[p] = q
+            else:
+                assert q == n or (q > f and L[q]), (p, f, pivot, n)
+                k = 0 if q == n else (nL - (lf + int(lp)) - 1) + 1
+                src[p], t = pos_R_with_before(k)
+                seen.add(t)
+            lf += int(lp)
+        seen.discard(x)
+        partners[x] = len(seen)
+    return src, pivot, partners

@@ -206,6 +206,32 @@ def test_tiled_shuffle_models_equal_sequential(oracle):
     assert worst <= 6, worst
 
 
+def test_pull_form_equals_sequential(oracle):
+    """The one-barrier form the grid tier runs when every tile has a block of its own (csrc/blas_grid_pull.cuh): every
+    OUTPUT slot finds its source from per-tile counts, the boundary flags and a rank-select in the partner tile's ballots.
+    Exhaustive over all flag vectors up to 11 elements, then random ones at any left fraction."""
+    import itertools
+    import shuffle_models as M
+    for n in range(1, 12):
+        for bits in itertools.product([0, 1], repeat=n):
+            flags = np.array(bits, np.uint8)
+            piv, ids = oracle.shuffle_seq(np.arange(n, dtype=np.uint32), flags)
+            src, p, _ = M.pull_form(flags, 4, warp_slots=2)
+            assert p == piv and (src == ids).all(), (bits, src, ids)
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n = int(rng.integers(1, 600))
+        tile = int(rng.choice([8, 16, 32, 64]))
+        if trial % 2:
+            flags = (rng.random(n) < rng.choice([0.01, 0.125, 0.5, 0.875, 0.99, rng.random()])).astype(np.uint8)
+        else:
+            cut = int(rng.integers(0, n + 1))
+            flags = np.concatenate([np.ones(cut, np.uint8), (rng.random(n - cut) < rng.random()).astype(np.uint8)])
+        piv, ids = oracle.shuffle_seq(np.arange(n, dtype=np.uint32), flags)
+        src, p, _ = M.pull_form(flags, tile)
+        assert p == piv and (src == ids).all(), (flags, tile)
+
+
 def test_empty_and_invalid_inputs(oracle):
     v, idx = S.soup(4, 1, 0.05)
     rc, *_ = oracle.blas_build(v, np.zeros(0, dtype=np.uint32))

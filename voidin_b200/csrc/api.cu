@@ -17,6 +17,7 @@ int blas_tc_setup(int cluster_size);
 int blas_tc_log(unsigned long long* out, unsigned int cap_rows);
 int blas_t1_timing(unsigned long long* out32);
 int blas_t1_blocks(unsigned long long* out2048);
+int blas_t1_pull(unsigned long long* out4096);
 
 int ctx_fail(bvh_cuda_ctx* ctx, int code, const char* what) {
     if (ctx) ctx->err = what ? what : "";
@@ -157,6 +158,7 @@ uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx) { return ctx ? ctx->laun
 // Debug only (library built with -DBVH_T1_TIMING): per-phase-kind work / barrier-wait ns of block 0 in the grid tier.
 int bvh_cuda_debug_t1_timing(unsigned long long* out32) { return blas_t1_timing(out32); }
 int bvh_cuda_debug_t1_blocks(unsigned long long* out2048) { return blas_t1_blocks(out2048); }
+int bvh_cuda_debug_t1_pull(unsigned long long* out4096) { return blas_t1_pull(out4096); }
 // Debug only (-DBVH_TC_TIMING): per-node time stamps of the cluster tier; returns the number of rows (8 u64 each), -1 if not built in.
 int bvh_cuda_debug_tc_log(unsigned long long* out, unsigned int cap_rows) { return blas_tc_log(out, cap_rows); }
 

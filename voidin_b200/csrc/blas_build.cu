@@ -283,6 +283,18 @@ int blas_t1_timing(unsigned long long* out32) {
 #endif
 }
 
+int blas_t1_pull(unsigned long long* out4096) {
+#ifdef BVH_T1_TIMING
+    static unsigned long long z[8 * 512];
+    cudaMemcpyFromSymbol(out4096, g_t1_pull, sizeof(z));
+    cudaMemcpyToSymbol(g_t1_pull, z, sizeof(z));
+    return 1;
+#else
+    (void)out4096;
+    return 0;
+#endif
+}
+
 int blas_t1_blocks(unsigned long long* out2048) {
 #ifdef BVH_T1_TIMING
     static unsigned long long z[2048];
@@ -319,7 +331,10 @@ int blas_tc_log(unsigned long long* out, unsigned int cap_rows) {
 
 int blas_t1_coop_occupancy() {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop, T1_THREADS, 0) != cudaSuccess) occ = 1;
+    int occ_pull = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop<false>, T1_THREADS, 0) != cudaSuccess) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pull, k_t1_coop<true>, T1_THREADS, 0) != cudaSuccess) occ_pull = 1;
+    if (occ_pull < occ) occ = occ_pull;  // one grid size for both instantiations (BVH_CUDA_T1_PULL selects at run time)
     return occ < 1 ? 1 : occ;
 }
 
@@ -445,9 +460,9 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         sc = c.take<NodeScratch>(max_large);
         tileL = c.take<uint32_t>(22 * (size_t)max_tiles);
         tileLF = c.take<uint32_t>(max_tiles);
-        pbal = c.take<uint32_t>((size_t)max_tiles * (T1_THREADS / 32) * 9);
+        pbal = c.take<uint32_t>(2 * (size_t)max_tiles * T1_META);  // PA -> PB ballots (two-phase form) / tile meta, double buffered (pull form)
         tile_desc = c.take<uint4>(max_tiles);
-        barrier = c.take<uint32_t>(64);
+        barrier = c.take<uint32_t>(T1_BARRIER_WORDS);
         scan_sums = c.take<uint32_t>(scan_blocks + 1);
         scan_total = c.take<uint32_t>(4);
         tbase = c.take<uint32_t>(NM + 1);
@@ -493,7 +508,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
 
     // ---- T1: grid-wide tier, one cooperative persistent launch (exits at once when no node is that large) ----
     if (N > tc_cap) {
-        CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, 256, stream));
+        CU_CHECK(ctx, cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * T1_BARRIER_WORDS, stream));
         T1Args g;
         g.nodes = lv[0]; g.sc = sc; g.n_nodes = 0; g.n_tiles = 0;
         g.ids0 = ids0; g.ids1 = ids1; g.fl0 = fl0; g.fl1 = fl1;
@@ -504,9 +519,11 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         uint32_t lv_cap = max_large, ep = epoch, max_levels = 4096;
         uint4* recs_p = recs;
         uint32_t* A_p = A;
+        static const uint32_t pull_env = [] { const char* e = getenv("BVH_CUDA_T1_PULL"); return e ? (uint32_t)atoi(e) : 0u; }();
         void* args[] = {&g, &lv0, &lv1, &lv_cap, &Q, &recs_p, &A_p, &ep, &max_levels};
         const uint32_t grid = t1_grid;
-        CU_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_t1_coop, dim3(grid), dim3(T1_THREADS), args, 0, stream));
+        const void* kfn = pull_env ? (const void*)k_t1_coop<true> : (const void*)k_t1_coop<false>;
+        CU_CHECK(ctx, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(T1_THREADS), args, 0, stream));
         launches += 1;
     }
 

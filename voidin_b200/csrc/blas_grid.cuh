@@ -30,6 +30,7 @@ struct T1Args {
 // grows, so there is no reset race; generation g completes when it reaches g * gridDim.x.
 #ifdef BVH_T1_TIMING
 __device__ unsigned long long g_t1_time[32];  // [2*kind] work ns, [2*kind+1] barrier wait ns (block 0)
+__device__ unsigned long long g_t1_pull[8][512];   // level 0, per block: ns in the sub-phases of the pull step (blas_grid_pull.cuh)
 __device__ unsigned long long g_t1_blk[2][1024];  // level 0: per-block work ns of the table / scatter phases
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
@@ -59,15 +60,43 @@ __device__ __forceinline__ unsigned long long gtimer() {
     } while (0)
 #endif
 
+// T1_BARRIER_GROUPS > 1: two-level arrival.  Blocks arrive on one of G group counters (own cache line each); the last
+// block of a group arrives on the top counter, the last of those releases every group by writing the generation into the
+// group's flag line, which is the only line that group's blocks poll.  One counter for all 444 blocks serialises 444
+// atomics and 444 pollers on a single L2 line; with 16 groups it is 28 + 16.  MEASURED SLOWER on B200 (dragon-class build,
+// grid tier 3.18 ms flat vs 3.87 / 3.85 / 3.82 ms with 8 / 16 / 37 groups, profiles/r02_build_variants_ab.txt): the flat
+// barrier is two dependent L2 round trips (atomic, poll), the two-level one is four, and same-address atomics are not the
+// bottleneck.  Kept as a compile-time option; the default is the flat counter.
+#ifndef T1_BARRIER_GROUPS
+#define T1_BARRIER_GROUPS 1
+#endif
+constexpr uint32_t T1_BARRIER_WORDS = 32u * (1u + 2u * T1_BARRIER_GROUPS);
 __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
         gen += 1;
+#if T1_BARRIER_GROUPS > 1
+        constexpr uint32_t NG = T1_BARRIER_GROUPS;
+        const uint32_t grp = blockIdx.x % NG;
+        const uint32_t ng = min(NG, gridDim.x);
+        const uint32_t gsz = (gridDim.x - grp + NG - 1) / NG;
+        __threadfence();
+        if (atomicAdd(counter + 32 * (1 + grp), 1u) + 1 == gen * gsz) {
+            __threadfence();
+            if (atomicAdd(counter, 1u) + 1 == gen * ng) {
+                __threadfence();
+                for (uint32_t k = 0; k < ng; ++k) *(volatile uint32_t*)(counter + 32 * (1 + NG + k)) = gen;
+            }
+        }
+        while (ld_vol(counter + 32 * (1 + NG + grp)) < gen) { }
+        __threadfence();
+#else
         const uint32_t target = gen * gridDim.x;
         __threadfence();
         atomicAdd(counter, 1u);
         while (ld_vol(counter) < target) { }
         __threadfence();
+#endif
     }
     __syncthreads();
 }
@@ -690,6 +719,8 @@ __global__ void __launch_bounds__(1024) k_t1_level0(LevelNode* nodes, BuildState
     p_t1_nextlevel(nodes, st, 0, 1, grid_blocks, false);
 }
 
+#include "blas_grid_pull.cuh"
+
 // All shuffles of one level with EPT slots per thread (tile = T1_THREADS * EPT slots).
 template <int EPT>
 __device__ __forceinline__ void t1_level(const T1Args& g, const bool scanned, uint32_t& gen, const uint32_t level) {
@@ -721,6 +752,9 @@ __device__ __forceinline__ void t1_level(const T1Args& g, const bool scanned, ui
 // of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (first form in
 // commit ac13e1f): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
 // descriptor read once per level (3.87 ms vs 3.70 ms); barriers restricted to the blocks that own a tile (3.67 vs 3.69).
+// PULL = true is a second instantiation with the resident-tile path of blas_grid_pull.cuh (45 KB of static shared memory);
+// the default build launches PULL = false, whose code and resources are exactly the two-phase tier.
+template <bool PULL>
 __global__ void __launch_bounds__(T1_THREADS, T1_MIN_BLOCKS) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
     LevelNode* lv[2] = {lv0, lv1};
@@ -742,11 +776,27 @@ __global__ void __launch_bounds__(T1_THREADS, T1_MIN_BLOCKS) k_t1_coop(T1Args g,
         g.nodes = lv[slot];
         g.n_nodes = n_nodes;
         g.n_tiles = n_tiles;
-        switch (g.ept) {
-            case 1: t1_level<1>(g, scanned, gen, level); break;
-            case 2: t1_level<2>(g, scanned, gen, level); break;
-            case 4: t1_level<4>(g, scanned, gen, level); break;
-            default: t1_level<8>(g, scanned, gen, level); break;
+        bool done = false;
+        if constexpr (PULL) {
+            // every tile has its own block: the tile stays in shared memory and a shuffle is one barrier (blas_grid_pull.cuh)
+            __shared__ __align__(16) T1Smem s_pull;
+            if (n_tiles <= gridDim.x && gridDim.x <= (uint32_t)T1_MAX_NT) {
+                switch (g.ept) {
+                    case 1: t1_level_pull<1>(g, s_pull, gen, level); break;
+                    case 2: t1_level_pull<2>(g, s_pull, gen, level); break;
+                    case 4: t1_level_pull<4>(g, s_pull, gen, level); break;
+                    default: t1_level_pull<8>(g, s_pull, gen, level); break;
+                }
+                done = true;
+            }
+        }
+        if (!done) {
+            switch (g.ept) {
+                case 1: t1_level<1>(g, scanned, gen, level); break;
+                case 2: t1_level<2>(g, scanned, gen, level); break;
+                case 4: t1_level<4>(g, scanned, gen, level); break;
+                default: t1_level<8>(g, scanned, gen, level); break;
+            }
         }
         const int next = slot ^ 1;
         T1_PHASE(9, p_t1_children(g, lv[next], lv_cap, next, Q, recs, A, epoch));
