@@ -296,10 +296,39 @@ def run_small_configs(args, local_rank):
         # order must be a permutation and every leaf range covered exactly once: cheap device-side property checks
         order = torch.sort(d_i.view(-1, 3)[:, 0] // 3)[0]
         ok_perm = bool((order == torch.arange(n, device=dev, dtype=torch.int32)).all().item())
+        tr = measured_traffic() or {}
+        soup_tr = tr.get("k_t1_coop_soup8Mi") if n == (1 << 23) else None
+        grid_bytes = 44.0 * st["grid_interior_prims"] + 48.0 * st["grid_nodes"]
+        grid_gbps = grid_bytes / (max(st["ms_grid"], 1e-9) * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            # bounded sample: the oracle on a 2^20-triangle soup of the same distribution (the 2^26 one takes 83 minutes,
+            # tests/golden/oracle_hashes_large.json)
+            from oracle import oracle as O
+            ns = 1 << 20
+            gs = torch.Generator(device=dev); gs.manual_seed(4)
+            sv0 = torch.rand((ns, 1, 3), generator=gs, device=dev, dtype=torch.float32)
+            se = (torch.rand((ns, 2, 3), generator=gs, device=dev, dtype=torch.float32) * 2 - 1) * 0.005
+            sv = torch.cat([sv0, sv0 + se], dim=1).reshape(-1, 3).cpu().numpy()
+            t0 = time.perf_counter()
+            rc, _, _, _, _ = O.blas_build(sv, np.arange(3 * ns, dtype=np.uint32))
+            dt = time.perf_counter() - t0
+            cpu = {"value": ns / dt / 1e6, "unit": "Mtris/s", "cores": 1, "kind": "port",
+                   "sample": f"one {ns}-triangle soup of the same distribution, single thread, {dt:.2f} s (rc {rc})"}
         out.update({"metric": "soup_blas_build_Mtris_per_s", "value": n / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": b_ms,
-                    "config": {"workload": f"config4: {n}-triangle random soup, single BLAS"}, "stats": st, "permutation_ok": ok_perm,
-                    "roofline": {"bound": "hbm", "achieved": bb / (b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": bb / (b_ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes": bb}})
+                    "higher_is_better": True,
+                    "config": {"workload": f"config4: {n}-triangle random soup, single BLAS",
+                               "parity": "nodes / primitive order / permuted indices of the 2^25 and 2^26 soups are pinned to oracle SHA-256 digests "
+                                         "(tests/test_gpu_fullsize.py::test_soup_above_2_pow_24_matches_oracle_hash)"},
+                    "stats": st, "permutation_ok": ok_perm,
+                    "roofline": {"bound": "hbm", "kernel": "k_t1_coop (grid tier)", "achieved": grid_gbps, "peak": peak, "unit": "GB/s",
+                                 "frac": grid_gbps / peak, "peak_source": src, "algorithmic_bytes": grid_bytes, "launch_ms": st["ms_grid"],
+                                 "share_of_build": st["ms_grid"] / st["ms_total"],
+                                 "traffic": (soup_tr["dram_bytes"] if soup_tr else None),
+                                 "traffic_over_algorithmic": (soup_tr["dram_bytes"] / grid_bytes if soup_tr else None),
+                                 "traffic_note": (soup_tr["reading"] if soup_tr else "ncu DRAM bytes are kept for the 2^23-triangle soup (profiles/r02o_k_t1_coop_soup8M_ncu_summary.txt)"),
+                                 "whole_build": {"achieved": bb / (b_ms * 1e-3) / 1e9, "frac": bb / (b_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bb}},
+                    "cpu_baseline": cpu})
     elif args.workload == "bunny":
         v, idx, bunny_label = asset_or_standin("bunny.obj")
         n = idx.size // 3
@@ -320,11 +349,36 @@ def run_small_configs(args, local_rank):
         d_tri = torch.empty(n_rays, dtype=torch.int32, device=dev)
         r_ms = timed(lambda: ctx.trace_blas_dev(d_nodes.data_ptr(), d_v.data_ptr(), d_i.data_ptr(), d_ro.data_ptr(), d_rd.data_ptr(),
                                                 n_rays, d_t.data_ptr(), d_tri.data_ptr(), stream), steps)
+        st = ctx.last_build_stats()
+        peak, src = peaks()
+        bb = build_bytes(n, v.shape[0], st["sum_interior_prims"], st["n_nodes"])
+        cpu = cpu_rays = None
+        per_ray = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            rc, on, oi, _, _ = O.blas_build(v, idx)
+            t1 = time.perf_counter()
+            nsr = min(n_rays, 1 << 18)
+            _, otri, rst = O.trace_blas(on, v, oi, ro[:nsr], rd[:nsr])
+            t2 = time.perf_counter()
+            cpu = {"value": n / (t1 - t0) / 1e6, "unit": "Mtris/s", "cores": 1, "kind": "port",
+                   "sample": f"one full build of the same mesh ({n} tris), single thread, {t1 - t0:.2f} s (rc {rc})"}
+            cpu_rays = {"value": nsr / (t2 - t1) / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                        "sample": f"{nsr} of the {n_rays} closest-hit rays, Bvh::traverse_iter, single thread, {t2 - t1:.2f} s",
+                        "ids_equal_gpu": bool((d_tri[:nsr].cpu().numpy().view(np.uint32) == otri).all())}
+            per_ray = {k: rst[k] / nsr for k in rst if isinstance(rst[k], (int, float))}
         out.update({"metric": "bunny_blas_build_Mtris_per_s", "value": n / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": b_ms + r_ms,
+                    "higher_is_better": True,
                     "config": {"workload": f"config1: {bunny_label} BLAS + {n_rays} closest-hit rays, Bvh::traverse_iter semantics"},
-                    "phase_ms": {"build": b_ms, "trace": r_ms},
+                    "phase_ms": {"build": b_ms, "trace": r_ms}, "stats": st,
+                    "roofline": {"bound": "hbm", "kernel": "whole build (all tiers; a 69 K-triangle mesh spends 4 of its ~20 levels in the grid tier)",
+                                 "achieved": bb / (b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bb / (b_ms * 1e-3) / 1e9 / peak,
+                                 "peak_source": src, "algorithmic_bytes": bb, "traffic": None},
+                    "cpu_baseline": cpu,
                     "rays": {"metric": "closest_hit_Mrays_per_s", "value": n_rays / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-                             "hit_frac": float((d_tri != -1).float().mean().item())}})
+                             "hit_frac": float((d_tri != -1).float().mean().item()), "cpu_baseline": cpu_rays,
+                             "oracle_counters_per_ray": per_ray}})
     else:
         meshes = [asset_or_standin("bunny.obj")[:2], asset_or_standin("dragon.obj")[:2], S.displaced_sphere(62, 124, 3)]  # third = DamagedHelmet-sized stand-in for ferris3d
         n_inst = args.instances
@@ -366,6 +420,29 @@ def run_small_configs(args, local_rank):
         d_ins = torch.empty(n_rays, dtype=torch.int32, device=dev)
         r_ms = timed(lambda: scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr(),
                                                      1e30, stream), max(1, min(steps, 3)))
+        cpu = cpu_rays = None
+        pairs = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+            ns = min(n_inst, 32767)  # the oracle's chain is O(I^2): 12 s at 32 767, 116 s at 100 000
+            t0 = time.perf_counter()
+            rc, otl, okids, calls, opairs = O.tlas_build(inst[:ns], info)
+            dt = time.perf_counter() - t0
+            cpu = {"value": dt * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                   "sample": f"Tlas::build over the first {ns} of the {n_inst} instances, single thread (rc {rc}), {opairs / dt / 1e9:.2f} G pair evaluations/s"}
+            if ns == n_inst:
+                pairs = int(opairs)
+                cpu["tlas_bytes_equal_gpu"] = bool(d_tlas.cpu().numpy().view(np.uint8).tobytes() == otl.tobytes())
+                # two-level closest hit on a bounded sample of the rays (every ray enters a large share of the stretched boxes)
+                nsr = min(n_rays, 1 << 13)
+                hn = d_nodes[: 8 * mm[0]].cpu().numpy().view(vb.BVH_NODE)
+                t1 = time.perf_counter()
+                _, otri, oins, _, _ = O.trace_scene(otl, okids, inst, d_info.cpu().numpy().view(MESH_INFO).reshape(-1), hn, d_verts.cpu().numpy().reshape(-1, 3), d_inds.cpu().numpy().view(np.uint32),
+                                                   ro[:nsr], rd[:nsr])
+                dtr = time.perf_counter() - t1
+                cpu_rays = {"value": nsr / dtr / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                            "sample": f"{nsr} of the {n_rays} two-level closest-hit rays, single thread, {dtr:.2f} s",
+                            "ids_equal_gpu": bool((d_tri[:nsr].cpu().numpy().view(np.uint32) == otri).all() and (d_ins[:nsr].cpu().numpy().view(np.uint32) == oins).all())}
         # per-frame loop of the `model` demo (compute_update.wgsl + the TLAS rebuild the reference lacks)
         frame = [0]
 
@@ -379,13 +456,22 @@ def run_small_configs(args, local_rank):
 
         f_ms = timed(animated_frame, max(1, min(steps, 3)))
         out["animated_frame"] = {"ms": f_ms, "what": "rotate all instances (compute_update.wgsl) + TLAS rebuild + the same closest-hit rays"}
+        peak, src = peaks()
+        tlas_bytes = 144 * n_inst + 48 * len(meshes) + 32 * (2 * n_inst + 1)
+        out["roofline"] = {"bound": "hbm", "kernel": "k_tlas_chain / k_tlas_chain_cluster (Tlas::build: ~3.1 I dependent arg-mins over the live slots)",
+                           "achieved": tlas_bytes / (t_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": tlas_bytes / (t_ms * 1e-3) / 1e9 / peak,
+                           "peak_source": src, "algorithmic_bytes": tlas_bytes, "traffic": None,
+                           "pair_evaluations": pairs, "pair_evaluations_per_s": (pairs / (t_ms * 1e-3) if pairs else None),
+                           "note": "SURVEY 8(d): B_tlas = 144 I + 48 n_mesh + 32 (2I+1); a latency-bound dependent chain, so the HBM fraction says nothing "
+                                   "and pair evaluations/s is the throughput figure"}
+        out["cpu_baseline"] = cpu
         out.update({"metric": "tlas_build_ms", "value": t_ms, "unit": "ms", "higher_is_better": False, "ms_per_step": b_ms + t_ms + r_ms,
                     "config": {"workload": f"config3: TLAS over {n_inst} random instances of 3 meshes ({n_tris} tris, forest BLAS build) + {n_rays} two-level closest-hit rays",
                                "note": "Tlas::build seeds every leaf box with the untransformed local mesh box (tlas.rs:39), so instances far from the origin get boxes stretched to the origin and most rays enter a large share of them: reference behaviour, reproduced bit-exactly"},
                     "phase_ms": {"blas_forest_build": b_ms, "tlas_build": t_ms, "trace": r_ms},
                     "blas": {"value": n_tris / (b_ms * 1e-3) / 1e6, "unit": "Mtris/s"},
                     "rays": {"metric": "closest_hit_Mrays_per_s", "value": n_rays / (r_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-                             "hit_frac": float((d_tri != -1).float().mean().item())}})
+                             "hit_frac": float((d_tri != -1).float().mean().item()), "cpu_baseline": cpu_rays}})
     print(json.dumps(out), flush=True)
 
 

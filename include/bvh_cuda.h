@@ -113,7 +113,7 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx);
 const char* bvh_cuda_last_error(const bvh_cuda_ctx* ctx);
 /* Total kernels launched through this context since creation. */
 uint64_t bvh_cuda_launch_count(const bvh_cuda_ctx* ctx);
-int bvh_cuda_abi_version(void); /* 4 */
+int bvh_cuda_abi_version(void); /* 5 */
 /* enable != 0: later BLAS builds record per-phase CUDA-event timings into BvhCudaBuildStats (a few extra event
  * records per build, no extra synchronisation). */
 int bvh_cuda_set_profiling(bvh_cuda_ctx* ctx, int enable);
@@ -141,6 +141,18 @@ int bvh_cuda_blas_build_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n
 int bvh_cuda_blas_build_batch_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
                                   size_t n_indices, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out,
                                   size_t nodes_cap, uint32_t* n_nodes_out, void* stream);
+/* The same build, STREAM-ORDERED: every kernel of the build is enqueued on `stream` and the call returns without waiting, so
+ * the caller can queue the TLAS build and the first trace behind it, or run a second build on ANOTHER context and stream at
+ * the same time (a context owns one workspace: one build in flight per context).  d_mesh_info may be NULL for a single
+ * mesh.  d_result (device, 4 words, may be NULL) receives {total nodes, device status bits (0 = ok), interior nodes, 0} when
+ * the build completes on the stream.  bvh_cuda_blas_build_finish waits for that build, returns its status (EINVAL /
+ * EDEGENERATE as for the synchronous calls), fills *n_nodes_out (host, may be NULL) and the statistics; it must be called
+ * before the next build on the same context.  Replaces nothing in the reference (its build is a blocking CPU call,
+ * crates/pools/src/mesh/mod.rs:320-321); this is what lets a renderer keep the frame's stream busy. */
+int bvh_cuda_blas_build_batch_async_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                                        size_t n_indices, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out,
+                                        size_t nodes_cap, uint32_t* d_result, void* stream);
+int bvh_cuda_blas_build_finish(bvh_cuda_ctx* ctx, uint32_t* n_nodes_out);
 /* Optional: final triangle_indices of the last build (original triangle id per slot), n_tris entries, device->host. */
 int bvh_cuda_blas_last_order(bvh_cuda_ctx* ctx, uint32_t* order_out, size_t n_tris);
 int bvh_cuda_blas_last_stats(const bvh_cuda_ctx* ctx, BvhCudaBuildStats* out);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bvh_cuda.h but not exported"
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.bvh_cuda_abi_version() == 4
+    assert lib.bvh_cuda_abi_version() == 5
     model_names = _declared_functions("bvh_cuda_models.h")
     assert len(model_names) == 10
     for n in model_names:
@@ -91,7 +91,7 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
     cxx_src.write_text(
         '#include "bvh_cuda.hpp"\n#include <cstdio>\n'
         "int main(){ try { bvh_cuda::Context c(0); std::puts(\"ctx\"); } catch (const bvh_cuda::Error& e) { std::puts(\"nogpu\"); }\n"
-        " return bvh_cuda_abi_version() == 4 ? 0 : 1; }\n")
+        " return bvh_cuda_abi_version() == 5 ? 0 : 1; }\n")
     libdir = os.path.join(ROOT, "voidin_b200")
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", inc, str(cxx_src), "-o", str(tmp_path / "t_cxx"), "-L", libdir,
                            "-lbvh_cuda", f"-Wl,-rpath,{libdir}"])

@@ -264,6 +264,84 @@ def test_trace_two_level_ids_exact(ctx, oracle):
     assert (tri3 == otri[:20000]).all() and (ins3 == oins[:20000]).all()
 
 
+def test_async_builds_on_two_contexts_overlap_and_match(oracle):
+    """bvh_cuda_blas_build_batch_async_dev: two builds enqueued on two contexts / two streams before either is collected;
+    d_result is valid on the stream; nodes and permuted indices equal the oracle's; a second enqueue on a context whose
+    build is still pending is refused; a degenerate mesh reports EDEGENERATE from finish()."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    meshes = [S.soup(60_000, 31, 0.01), S.displaced_sphere(70, 140, 9)]
+    ctxs = [vb.Context(0), vb.Context(0)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    bufs = []
+    torch.cuda.synchronize()
+    for (v, idx), c, st in zip(meshes, ctxs, streams):
+        n = idx.size // 3
+        with torch.cuda.stream(st):
+            d_v = torch.from_numpy(v.reshape(-1)).to(dev, non_blocking=False)
+            d_i = torch.from_numpy(idx.view(np.int32).copy()).to(dev)
+            d_n = torch.zeros(2 * n * 8, dtype=torch.int32, device=dev)
+            d_r = torch.full((4,), -1, dtype=torch.int32, device=dev)
+        st.synchronize()
+        c.blas_build_batch_async_dev(d_v.data_ptr(), v.shape[0], d_i.data_ptr(), 3 * n, 0, 1, d_n.data_ptr(), 2 * n, d_r.data_ptr(), st.cuda_stream)
+        bufs.append((d_v, d_i, d_n, d_r, n))
+    with pytest.raises(vb.BvhCudaError):  # one build in flight per context
+        ctxs[0].blas_build_batch_async_dev(bufs[0][0].data_ptr(), meshes[0][0].shape[0], bufs[0][1].data_ptr(), 3 * bufs[0][4], 0, 1,
+                                           bufs[0][2].data_ptr(), 2 * bufs[0][4], 0, streams[0].cuda_stream)
+    for (v, idx), c, st, (d_v, d_i, d_n, d_r, n) in zip(meshes, ctxs, streams, bufs):
+        # the result words are stream-ordered: readable on the build's stream without calling finish first
+        with torch.cuda.stream(st):
+            res = d_r.clone()
+        st.synchronize()
+        m = c.blas_build_finish()
+        rc, onodes, oidx, _, _ = oracle.blas_build(v, idx)
+        assert rc == 0 and int(res[0]) == m == len(onodes) and int(res[1]) == 0
+        assert d_n[: 8 * m].cpu().numpy().tobytes() == onodes.tobytes()
+        assert (d_i.cpu().numpy().view(np.uint32) == oidx).all()
+    # degenerate input: eight coincident triangles (the reference would not terminate, blas.rs:115,139)
+    v = np.zeros((3, 3), dtype=np.float32)
+    idx = np.tile(np.arange(3, dtype=np.uint32), 8)
+    d_v, d_i = torch.from_numpy(v.reshape(-1)).to(dev), torch.from_numpy(idx.view(np.int32)).to(dev)
+    d_n = torch.zeros(16 * 8, dtype=torch.int32, device=dev)
+    ctxs[0].blas_build_batch_async_dev(d_v.data_ptr(), 3, d_i.data_ptr(), 24, 0, 1, d_n.data_ptr(), 16, 0, 0)
+    with pytest.raises(vb.BvhCudaError) as e:
+        ctxs[0].blas_build_finish()
+    assert e.value.code == -2
+
+
+def test_trace_with_staged_tlas_top_equals_default(ctx, oracle):
+    """BVH_CUDA_TLAS_TOP=1 (read once per process, hence the child) serves the 255 TLAS nodes nearest the root, node 0 and
+    their child pairs from shared memory (csrc/trace.cu TlasTop; off by default because it measured slower,
+    profiles/r02_tlas_top_ab.txt).  Same hit ids, same bits of t, same occlusion flags as the default kernels and the
+    oracle, with a TLAS larger than the staged part (1 201 nodes) and with the side `children` buffer in use."""
+    import subprocess
+    import sys
+    import tempfile
+
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=600)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    ro, rd = S.rays_toward_box(100_000, [-20, -20, -20], [20, 20, 20], seed=78)
+    t, tri, ins = scene.traverse_tlas(ro, rd)
+    occ = scene.occluded(ro, rd)
+    _, otri, oins, _, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
+    assert (tri == otri).all() and (ins == oins).all()
+    with tempfile.TemporaryDirectory() as td:
+        src, dst = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
+        np.savez(src, tlas=tl.nodes, kids=tl.children, inst=inst.view(np.uint8), infos=infos.view(np.uint8), nodes=nodes, verts=verts,
+                 inds=inds, ro=ro, rd=rd)
+        subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "_child_trace.py"), src, dst],
+                       check=True, env=dict(os.environ, BVH_CUDA_TLAS_TOP="1"), timeout=600)
+        d = np.load(dst)
+        assert (d["tri"] == tri).all() and (d["ins"] == ins).all() and d["t"].tobytes() == t.tobytes() and (d["occ"] == occ).all()
+
+
 def test_any_hit_order_free_kernel_equals_reference_order(ctx, oracle):
     """trace_any runs an order-free kernel (separate interior / leaf stacks, missed interior children skipped) and hands
     rays with unusable reciprocals to the exact-order kernel.  Its answer must equal traverse_tlas(ray).hit of the

@@ -20,6 +20,8 @@ SYMBOLS = [
     "bvh_cuda_blas_build",
     "bvh_cuda_blas_build_dev",
     "bvh_cuda_blas_build_batch_dev",
+    "bvh_cuda_blas_build_batch_async_dev",
+    "bvh_cuda_blas_build_finish",
     "bvh_cuda_blas_last_order",
     "bvh_cuda_blas_last_stats",
     "bvh_cuda_tlas_build",
@@ -120,6 +122,8 @@ def load() -> C.CDLL:
     lib.bvh_cuda_blas_build.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p]
     lib.bvh_cuda_blas_build_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32p, vp]
     lib.bvh_cuda_blas_build_batch_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, u32p, vp]
+    lib.bvh_cuda_blas_build_batch_async_dev.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, vp]
+    lib.bvh_cuda_blas_build_finish.argtypes = [vp, u32p]
     lib.bvh_cuda_blas_last_order.argtypes = [vp, vp, sz]
     lib.bvh_cuda_blas_last_stats.argtypes = [vp, C.POINTER(BuildStats)]
     lib.bvh_cuda_tlas_build.argtypes = [vp, vp, sz, vp, sz, vp, vp]

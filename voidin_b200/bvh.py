@@ -85,6 +85,19 @@ class Context:
                                                           n_meshes, d_nodes, nodes_cap, C.byref(m), stream))
         return int(m.value)
 
+    def blas_build_batch_async_dev(self, d_vertices: int, n_vertices: int, d_indices: int, n_indices: int, d_mesh_info: int,
+                                   n_meshes: int, d_nodes: int, nodes_cap: int, d_result: int = 0, stream: int = 0) -> None:
+        """Stream-ordered forest build: enqueues the whole build on `stream` and returns; `blas_build_finish` collects it.
+        d_result (device, 4 x u32, optional): {nodes, status bits, interior nodes, 0} written when the build completes."""
+        self.check(self.lib.bvh_cuda_blas_build_batch_async_dev(self.h, d_vertices, n_vertices, d_indices, n_indices, d_mesh_info or None,
+                                                                n_meshes, d_nodes, nodes_cap, d_result or None, stream))
+
+    def blas_build_finish(self) -> int:
+        """Waits for the pending asynchronous build of this context; returns its total node count (raises on a failed build)."""
+        m = C.c_uint32(0)
+        self.check(self.lib.bvh_cuda_blas_build_finish(self.h, C.byref(m)))
+        return int(m.value)
+
     def tlas_build_dev(self, d_instances: int, n_inst: int, d_meshes: int, n_mesh: int, d_nodes: int,
                        d_children: int, stream: int = 0):
         self.check(self.lib.bvh_cuda_tlas_build_dev(self.h, d_instances, n_inst, d_meshes, n_mesh, d_nodes,

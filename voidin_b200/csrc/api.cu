@@ -95,7 +95,7 @@ struct DevBuf {
 
 extern "C" {
 
-int bvh_cuda_abi_version(void) { return 4; }  // 2: BvhCudaBuildStats grew (ms_thread, thread_tasks); 3: again (grid_nodes, grid_interior_prims); 4: cluster tier (cluster_tasks, ms_cluster)
+int bvh_cuda_abi_version(void) { return 5; }  // 5: stream-ordered builds (blas_build_batch_async_dev / blas_build_finish); 2: BvhCudaBuildStats grew (ms_thread, thread_tasks); 3: again (grid_nodes, grid_interior_prims); 4: cluster tier (cluster_tasks, ms_cluster)
 
 int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
     if (!out) return BVH_CUDA_EINVAL;
@@ -185,6 +185,22 @@ int bvh_cuda_blas_build_batch_dev(bvh_cuda_ctx* ctx, const float* d_vertices, si
     DeviceGuard g(ctx->device);
     return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_indices / 3, d_mesh_info, n_meshes, d_nodes_out, nodes_cap,
                              n_nodes_out, (cudaStream_t)stream);
+}
+
+int bvh_cuda_blas_build_batch_async_dev(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
+                                        size_t n_indices, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out,
+                                        size_t nodes_cap, uint32_t* d_result, void* stream) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    if (n_indices % 3 != 0) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build_batch_async: n_indices % 3 != 0");
+    DeviceGuard g(ctx->device);
+    return blas_build_device(ctx, d_vertices, n_vertices, d_indices, n_indices / 3, d_mesh_info, d_mesh_info ? n_meshes : 1, d_nodes_out,
+                             nodes_cap, nullptr, (cudaStream_t)stream, d_result, true);
+}
+
+int bvh_cuda_blas_build_finish(bvh_cuda_ctx* ctx, uint32_t* n_nodes_out) {
+    if (!ctx) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return blas_build_finish(ctx, n_nodes_out);
 }
 
 int bvh_cuda_blas_build(bvh_cuda_ctx* ctx, const float* vertices, size_t n_vertices, uint32_t* indices, size_t n_tris,

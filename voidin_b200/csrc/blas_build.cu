@@ -283,6 +283,13 @@ int blas_t1_timing(unsigned long long* out32) {
 #endif
 }
 
+// {total nodes, device error bits (DERR_*), interior nodes, 0} for callers that stay on the stream (async builds)
+namespace {
+__global__ void k_publish_result(const BuildState* st, const uint32_t* scan_total, uint32_t* out) {
+    if (threadIdx.x == 0) { out[0] = scan_total[1]; out[1] = st->err; out[2] = scan_total[0]; out[3] = 0; }
+}
+}  // namespace
+
 int blas_t1_pull(unsigned long long* out4096) {
 #ifdef BVH_T1_TIMING
     static unsigned long long z[8 * 512];
@@ -390,7 +397,8 @@ struct Carver {
 
 int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
                       size_t n_tris, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out, size_t nodes_cap,
-                      uint32_t* n_nodes_out, cudaStream_t stream) {
+                      uint32_t* n_nodes_out, cudaStream_t stream, uint32_t* d_result, bool async) {
+    if (ctx->pending) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: an asynchronous build of this context has not been finished (bvh_cuda_blas_build_finish)");
     if (!d_vertices || !d_indices || !d_nodes_out || n_tris == 0 || n_vertices == 0 || n_meshes == 0)
         return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: empty mesh or null pointer");
     if (n_tris > 0x7FFFFFFFull / 2 || n_vertices > 0xFFFFFFFFull || n_meshes > (1ull << 29) || n_meshes > n_tris)
@@ -480,7 +488,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const uint32_t epoch = 0x80000000u | (g_epoch.fetch_add(1) + 1);
     ctx->epoch = epoch;
     uint32_t launches = 0;
-    BvhCudaBuildStats stats{};
+
 
     // The three task queues are contiguous; clearing them makes every `ready` word differ from the epoch even when
     // the workspace still holds other data of an earlier, differently sized build.
@@ -610,13 +618,28 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     CU_CHECK(ctx, cudaMemcpyAsync(d_indices, tmp, sizeof(uint32_t) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, stream));
     launches += 6;
     if (prof) cudaEventRecord(ctx->ev[5], stream);
+    if (d_result) { k_publish_result<<<1, 32, 0, stream>>>(st, scan_total, d_result); launches++; }
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin, st, sizeof(BuildState), cudaMemcpyDeviceToHost, stream));
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_pin + 64, scan_total, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CU_CHECK(ctx, cudaStreamSynchronize(stream));
+    CU_CHECK(ctx, cudaGetLastError());
+    ctx->pending = true;
+    ctx->pend_n = N; ctx->pend_nm = NM; ctx->pend_launches = launches; ctx->pend_prof = prof; ctx->pend_stream = stream; ctx->pend_ids = ids0;
+    if (async) return BVH_CUDA_OK;  // everything is enqueued; status, node count and statistics are collected by blas_build_finish
+    return blas_build_finish(ctx, n_nodes_out);
+}
+
+// Second half of a build: waits for the stream, reads the device status back and fills the context's statistics.
+int blas_build_finish(bvh_cuda_ctx* ctx, uint32_t* n_nodes_out) {
+    if (!ctx->pending) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build_finish: no build is pending on this context");
+    ctx->pending = false;
+    const uint32_t N = ctx->pend_n, NM = ctx->pend_nm, launches = ctx->pend_launches;
+    const bool prof = ctx->pend_prof;
+    BvhCudaBuildStats stats{};
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->pend_stream));
     CU_CHECK(ctx, cudaGetLastError());
     const BuildState* hs = reinterpret_cast<const BuildState*>(ctx->h_pin);
     ctx->launches += launches;
-    ctx->d_last_order = ids0;
+    ctx->d_last_order = ctx->pend_ids;
     ctx->last_n = N;
     if (hs->err & DERR_BAD_INDEX) return ctx_fail(ctx, BVH_CUDA_EINVAL, "blas_build: vertex index out of range or inconsistent mesh table");
     if (hs->err & DERR_DEGENERATE)

@@ -51,6 +51,12 @@ struct bvh_cuda_ctx {
     bool profiling = false;
     cudaEvent_t ev[10] = {};
     bool t4_ready = false;  // k_t4's dynamic shared-memory limit has been raised on this context's device
+    // a stream-ordered build that has been enqueued but not yet collected (bvh_cuda_blas_build_batch_async_dev / _finish)
+    bool pending = false;
+    uint32_t pend_n = 0, pend_nm = 0, pend_launches = 0;
+    bool pend_prof = false;
+    cudaStream_t pend_stream = nullptr;
+    uint32_t* pend_ids = nullptr;
 };
 
 struct bvh_cuda_scene {
@@ -82,7 +88,8 @@ int ctx_stage_reserve(bvh_cuda_ctx* ctx, size_t bytes);
 // implemented in blas_build.cu / tlas.cu / trace.cu
 int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_vertices, uint32_t* d_indices,
                       size_t n_tris, MeshInfo* d_mesh_info, size_t n_meshes, BvhNode* d_nodes_out, size_t nodes_cap,
-                      uint32_t* n_nodes_out, cudaStream_t stream);
+                      uint32_t* n_nodes_out, cudaStream_t stream, uint32_t* d_result = nullptr, bool async = false);
+int blas_build_finish(bvh_cuda_ctx* ctx, uint32_t* n_nodes_out);
 int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
                       size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, cudaStream_t stream);
 int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t stream);

@@ -72,8 +72,11 @@ __device__ __forceinline__ void tlas_top_load(TlasTop& t, const BvhCudaSceneDesc
 __device__ __forceinline__ uint32_t tlas_top_slot(uint32_t ni, uint32_t first) {
     return ni >= first ? ni - first + 1 : (ni == 0 ? 0u : 0xFFFFFFFFu);
 }
-// TOP = false: the instantiation for scenes whose TLAS is a handful of nodes (BASELINE config 2 has 5): staging cannot
-// save anything there and the slot arithmetic costs ~4 % of the any-hit kernel, so those launches skip it.
+// TOP = false: the instantiation without the staged copy.  MEASURED (B200, profiles/r02_tlas_top_ab.txt): staging LOSES on
+// every configuration -- config 2 (5 TLAS nodes) 2 981 -> 2 870 Mrays/s, config 3 (65 535 nodes, 1 Mi closest-hit rays)
+// 256 -> 302 ms, config 5 (2 049 nodes, 128 Mi any-hit rays) 574 -> 551 Mrays/s: the nodes next to the root are L1 hits
+// already (l1tex hit rate 73 %), so the shared copy only adds the slot arithmetic and a divergent branch to every TLAS
+// step.  The staged kernels stay available (BVH_CUDA_TLAS_TOP=1) and are parity-tested; the default launches TOP = false.
 template <bool TOP>
 __device__ __forceinline__ NodeW tlas_node(const TlasTop& t, const BvhCudaSceneDesc& sc, uint32_t ni, uint32_t first) {
     if (TOP) {
@@ -90,7 +93,6 @@ __device__ __forceinline__ uint2 tlas_kids(const TlasTop& t, const BvhCudaSceneD
     }
     return __ldg(reinterpret_cast<const uint2*>(sc.tlas_children) + ni);
 }
-constexpr size_t TLAS_TOP_MIN_NODES = 64;  // stage from this many TLAS nodes on
 
 // ---- Rust-mode tests --------------------------------------------------------------------------------
 struct RDist {
@@ -764,9 +766,8 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     static const bool wide_off = [] { const char* e = getenv("BVH_CUDA_ANYHIT"); return e && !strcmp(e, "exact"); }();
-    // top of the TLAS in shared memory (TlasTop): on from TLAS_TOP_MIN_NODES nodes; BVH_CUDA_TLAS_TOP=0 / 1 forces it (A/B)
-    static const int top_env = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e ? atoi(e) : -1; }();
-    const bool top = top_env >= 0 ? top_env != 0 : scene->d.n_tlas_nodes >= TLAS_TOP_MIN_NODES;
+    // top of the TLAS in shared memory (TlasTop): off by default (measured slower, see tlas_node above); BVH_CUDA_TLAS_TOP=1 enables it
+    static const bool top = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e && atoi(e) != 0; }();
     if (any_hit && !wide_off && tmax <= MAXD && n_rays < 0xFFFFFFFFull) {
         // order-free kernel first; whatever it defers (normally nothing) goes through the exact kernel
         if (ctx->defer_cap < n_rays) {
