@@ -1025,6 +1025,7 @@ def ray_roofline(rbytes, per_ray, n_rays, ms, scene_bytes, tr, peak, peak_src, n
     L2 bandwidth, and the DRAM side is reported separately as measured bytes against the HBM peak; the issue-slot
     fraction (ncu) says how close the kernel is to its real bound, instruction issue."""
     l2 = tr.get("l2_peak_GBps") if tr else None
+    issue = tr.get("k_trace_any_issue") if tr else None
     model_gbps = rbytes * n_rays / (ms * 1e-3) / 1e9
     dram = tr.get("k_trace_any_16Mi") if (tr and n_rays == N_RAYS) else None
     out = {"bound": "hbm", "achieved": ((dram / (ms * 1e-3) / 1e9) if dram else (25 * n_rays + scene_bytes) / (ms * 1e-3) / 1e9),
@@ -1032,7 +1033,11 @@ def ray_roofline(rbytes, per_ray, n_rays, ms, scene_bytes, tr, peak, peak_src, n
            "achieved_is": "measured DRAM bytes of one launch (ncu) / launch time" if dram else "compulsory bytes (24 B in + 1 B out per ray + the scene once) / launch time",
            "kernel": "k_trace_any (one launch per step; the exact-order kernel that takes deferred rays runs empty)",
            "l2_model": {"bytes_per_ray": rbytes, "GBps": model_gbps, "l2_peak_GBps": l2, "frac_of_l2": (model_gbps / l2) if l2 else None,
-                        "note": "SURVEY 8(d) byte model x rays / time: node and triangle fetches are L2 hits, so this is L2 traffic, not HBM"},
+                        "note": "SURVEY 8(d) byte model x rays / time: what the kernel asks its L1 for; most of it is served by L1 (hit rate 73 %)"},
+           "l2_measured": (None if not (issue and l2 and n_rays == N_RAYS) else
+                           {"bytes_per_launch": issue["l2_bytes_per_launch"], "GBps": issue["l2_bytes_per_launch"] / (ms * 1e-3) / 1e9,
+                            "frac_of_l2_peak": issue["l2_bytes_per_launch"] / (ms * 1e-3) / 1e9 / l2,
+                            "note": "lts__t_sectors.sum x 32 B of one launch (ncu) / this run's launch time, against the measured L2 read peak"}),
            "issue": (tr.get("k_trace_any_issue") if tr else None),
            "counters_per_ray": per_ray, "note": note}
     out["frac"] = out["achieved"] / peak

@@ -547,7 +547,7 @@ template <bool TOP>
 __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const float4* __restrict__ tris,
                                                    const float* __restrict__ ro, const float* __restrict__ rd, size_t R,
                                                    float tmax, uint8_t* occ_out, unsigned long long* ctl,
-                                                   uint32_t* defer_list) {
+                                                   uint32_t* defer_list, uint32_t steal) {
     __shared__ TlasTop s_top;
     if (TOP) tlas_top_load(s_top, sc);
     const uint32_t top_first = tlas_top_first(sc.n_tlas_nodes);
@@ -584,6 +584,41 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
                 tstack[th++] = 0;
                 active = true;
                 if (!inv_usable(inv)) defer = true;
+            }
+        }
+        // ---- tail: no rays are left to fetch.  The answer does not depend on the order in which the entries of the
+        // interior stack are processed, so an idle lane takes the top entry of a busy lane's stack together with that
+        // ray's object-space state and works on it as if it were its own ray (it has no TLAS stack, so it stops when
+        // the sub-tree is done).  Only hits are written (the output is zeroed before the launch), so whoever finds
+        // one reports it.  Without this a launch ends with a few lanes walking >1000-node rays alone (0.3 ms floor).
+        if (exhausted && steal && idle != 0) {
+            const bool donor = active && !defer && nh >= 1;
+            const uint32_t D = __ballot_sync(FULL_MASK, donor);
+            const uint32_t I = __ballot_sync(FULL_MASK, !active);
+            if (D != 0 && I != 0) {
+                const uint32_t pairs = min((uint32_t)__popc(I), (uint32_t)__popc(D));
+                uint32_t given = 0;
+                if (donor && (uint32_t)__popc(D & lt_mask) < pairs) given = nstack[--nh];
+                const uint32_t my_rank = __popc(I & lt_mask);
+                const bool take = !active && my_rank < pairs;
+                const uint32_t src = take ? __fns(D, 0, my_rank + 1) : lane;
+                const uint32_t g_top = __shfl_sync(FULL_MASK, given, src);
+                const uint32_t g_tb = __shfl_sync(FULL_MASK, tri_base, src), g_bi = __shfl_sync(FULL_MASK, bvh_index, src);
+                const unsigned long long g_r = __shfl_sync(FULL_MASK, (unsigned long long)r, src);
+                float ge[3], gd[3], gi[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ge[k] = __shfl_sync(FULL_MASK, e2[k], src);
+                    gd[k] = __shfl_sync(FULL_MASK, d2[k], src);
+                    gi[k] = __shfl_sync(FULL_MASK, inv2[k], src);
+                }
+                if (take) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { e2[k] = ge[k]; d2[k] = gd[k]; inv2[k] = gi[k]; }
+                    tri_base = g_tb; bvh_index = g_bi; r = (size_t)g_r;
+                    top = g_top; th = 0; nh = 0; lh = 0; leaf_cnt = 0;
+                    active = true;
+                }
             }
         }
         if (__ballot_sync(FULL_MASK, active) == 0) {
@@ -696,7 +731,7 @@ __global__ void __launch_bounds__(128, 9) k_trace_any(BvhCudaSceneDesc sc, const
             defer_list[slot + __popc(dm & lt_mask)] = (uint32_t)r;
             active = false;
         } else if (finished) {
-            occ_out[r] = occluded ? 1 : 0;
+            if (occluded) occ_out[r] = 1;  // the output is zeroed before the launch; lanes working on stolen sub-trees report hits only
             active = false;
         }
     }
@@ -784,10 +819,13 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_top, k_trace_any<true>, 128, 0) != cudaSuccess || occ_top < 1) occ_top = 8;
             return occ < occ_top ? occ : occ_top;
         }();
+        CU_CHECK(ctx, cudaMemsetAsync(d_occ, 0, n_rays, stream));  // k_trace_any writes hits only
         const size_t cap_any = (size_t)ctx->sm_count * any_bps;
         const unsigned blocks_any = (unsigned)(want < cap_any ? want : cap_any);
-        if (top) k_trace_any<true><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list);
-        else k_trace_any<false><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list);
+        // BVH_CUDA_TRACE_STEAL=0 switches the tail's intra-warp work stealing off (A/B)
+        static const uint32_t steal = [] { const char* e = getenv("BVH_CUDA_TRACE_STEAL"); return (e && atoi(e) == 0) ? 0u : 1u; }();
+        if (top) k_trace_any<true><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list, steal);
+        else k_trace_any<false><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list, steal);
         ctx->launches++;
         // (the deferral pass normally finds an empty list: it runs without staging)
         k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
