@@ -110,7 +110,7 @@ if os.environ.get("SIZES"):
             scene.occluded_dev(d_ro.data_ptr() + 12 * off, d_rd.data_ptr() + 12 * off, cnt, d_occ.data_ptr(), 1e30, 0)
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
-    for cnt in [1 << 10, 1 << 14, 1 << 17, 1 << 20, 1 << 21, 1 << 22, n // 2, n]:
+    for cnt in [1, 32, 1 << 10, 1 << 14, 1 << 17, 1 << 20, 1 << 21, 1 << 22, n // 2, n]:
         if cnt <= n:
             print(f"  first {cnt:9d} rays: {timeit(0, cnt):.3f} ms", flush=True)
     print(f"  model half : {timeit(0, n // 2):.3f} ms   ground half: {timeit(n // 2, n // 2):.3f} ms", flush=True)
