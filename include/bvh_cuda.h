@@ -82,8 +82,8 @@ typedef struct BvhCudaBuildStats {
     uint64_t sum_interior_prims; /* S: sum over interior nodes of their triangle count */
     uint32_t n_nodes;            /* M = 2 + 2 * interior nodes */
     uint32_t interior_nodes;
-    uint32_t grid_levels;        /* levels handled by the grid-wide tier (nodes > 16384 triangles) */
-    uint32_t big_block_tasks;    /* nodes handled by one 1024-thread block each (2049..16384) */
+    uint32_t grid_levels;        /* levels handled by the grid-wide tier (nodes > 24576 triangles) */
+    uint32_t big_block_tasks;    /* nodes handled by one 1024-thread block each (2049..24576) */
     uint32_t block_tasks;        /* nodes handled one block each from the device task queue (257..2048) */
     uint32_t warp_node_tasks;    /* nodes handled one warp each from the second task queue (33..256) */
     uint32_t warp_tasks;         /* sub-trees (<= 32 triangles) handled one warp each; their small children go to the thread tier */
@@ -91,7 +91,7 @@ typedef struct BvhCudaBuildStats {
     /* Device time per phase in ms (CUDA events on the build's stream); all zero unless profiling is enabled. */
     float ms_setup;              /* k_setup: centroids, triangle boxes */
     float ms_grid;               /* grid-wide tier, all levels */
-    float ms_big_block;          /* k_t2<16384,1024>: big-block task-queue kernel (one launch) */
+    float ms_big_block;          /* k_t2<24576,1024>: big-block task-queue kernel (one launch) */
     float ms_block;              /* k_t2<2048,256>: block-per-node task-queue kernel (one launch) */
     float ms_warp_node;          /* k_t2w: warp-per-node task-queue kernel (one launch) */
     float ms_warp;               /* k_t3: warp-per-sub-tree kernel (one launch) */
@@ -99,7 +99,7 @@ typedef struct BvhCudaBuildStats {
     float ms_total;
     float ms_thread;             /* k_t4: thread-per-sub-tree kernel (one launch) */
     uint32_t thread_tasks;       /* small sub-trees handled one thread each (k_t4) */
-    uint32_t grid_nodes;         /* interior nodes split by the grid-wide and cluster tiers (n > 16384) */
+    uint32_t grid_nodes;         /* interior nodes split by the grid-wide and cluster tiers (n > 24576) */
     uint32_t cluster_tasks;      /* nodes handled one thread-block cluster each (16385..262144); also counted in grid_nodes */
     uint64_t grid_interior_prims;/* sum of their triangle counts (the S of the large-node tiers' algorithmic bytes) */
     float ms_cluster;            /* k_tc: cluster-per-node task-queue kernel (one launch) */

@@ -38,7 +38,7 @@ def test_blas_bit_exact(ctx, oracle, name, v, idx):
 
 # sizes chosen so that the root level runs on every tile size the grid tier picks per level on a 148-SM part
 # (256-slot tiles up to ~113 K triangles, then 512, 1024, 2048), plus one just above the grid-tier threshold
-@pytest.mark.parametrize("n,seed,edge", [(17_000, 5, 0.02), (100_000, 0, 0.01), (150_000, 7, 0.01), (300_000, 21, 0.01),
+@pytest.mark.parametrize("n,seed,edge", [(25_000, 5, 0.02), (100_000, 0, 0.01), (150_000, 7, 0.01), (300_000, 21, 0.01),
                                          (600_000, 9, 0.005)])
 def test_blas_bit_exact_grid_tier(ctx, oracle, n, seed, edge):
     v, idx = S.soup(n, seed, edge)
@@ -77,7 +77,7 @@ def test_blas_cluster_tier_variants_bit_exact(oracle, mode):
     q = np.float32(1 / 64)
     nzv = (np.round(nz[0] / q) * q).astype(np.float32) - np.float32(0.5)
     nzv[nzv == 0] = np.float32(-0.0)
-    singles = [S.soup(17_000, 5, 0.02), S.soup(150_000, 7, 0.01), S.soup(300_000, 21, 0.01), (nzv, nz[1])]
+    singles = [S.soup(25_000, 5, 0.02), S.soup(150_000, 7, 0.01), S.soup(300_000, 21, 0.01), (nzv, nz[1])]
     outs, st = _build_in_child(singles, "single", {"BVH_CUDA_TC": mode})
     assert st["cluster_tasks"] >= 1, st
     for (v, idx), (nodes, perm) in zip(singles, outs):

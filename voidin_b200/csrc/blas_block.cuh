@@ -1,5 +1,5 @@
 // blas_block.cuh -- part of blas_build.cu (included there, inside its anonymous namespace; not a stand-alone header):
-// device task queues and the block / warp tiers: k_t2<16384,1024>, k_t2<2048,256>, k_t2w.
+// device task queues and the block / warp tiers: k_t2<24576,1024>, k_t2<2048,256>, k_t2w.
 #pragma once
 
 // ------------------------------------------------------------------------------------------------

@@ -8,9 +8,9 @@
 // 3x8 exact bins plus the <=21 "unexamined" primitives that the shuffles single out.
 //
 // Six tiers, by node size (boundaries measured):
-//   k_t1_coop   n > 16384      grid-wide, level-synchronous phases over tiles of 256..2048 slots chosen per level
+//   k_t1_coop   n > 24576      grid-wide, level-synchronous phases over tiles of 256..2048 slots chosen per level
 //                              (global-memory ping-pong, one cooperative launch for all levels)
-//   k_t2 (big)  2049..16384    one 1024-thread block per node from a device task queue (payload in shared memory)
+//   k_t2 (big)  2049..24576    one 1024-thread block per node from a device task queue (payload in shared memory)
 //   k_t2        257..2048      one 256-thread block per node, second queue
 //   k_t2w       33..256        one warp per node, third queue
 //   k_t3        9..32          one warp per sub-tree, explicit DFS stack spread over the lanes
@@ -69,7 +69,10 @@ constexpr int T2_THREADS = 256;
 #ifndef T2_MIN_BLOCKS
 #define T2_MIN_BLOCKS 3  // 64 registers, no spills; 0.85 -> 0.61 ms for the tier on the dragon-class mesh (4 gives no more)
 #endif
-constexpr int T2B_CAP = 16384;  // big-block tier: 2049..16384 (1024 threads, one block per SM)
+#ifndef T2B_CAP_V
+#define T2B_CAP_V 24576  // measured on the dragon-class build: 16384 -> 6.03 ms, 20480 -> 5.91, 24576 -> 5.86, 28672 -> 6.25 (spills), 32768 -> 6.24 (profiles/r02_build_variants_ab.txt)
+#endif
+constexpr int T2B_CAP = T2B_CAP_V;  // big-block tier: 2049..T2B_CAP (1024 threads, one block per SM; 6 B of shared memory per slot)
 constexpr int T2B_THREADS = 1024;
 // Grid tier block shape: threads per block and blocks per SM.  Measured on the dragon-class build (grid tier ms):
 // see scripts/variants.py rows t1_512x2 / t1_1024x1 in profiles/r02_build_variants_ab.txt.
@@ -418,7 +421,7 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
     const bool use_tc = tc_mode != 0 && ctx->tc_clusters > 0 && ctx->tc_cluster_size > 0;
     const uint32_t tc_cap = use_tc ? (uint32_t)ctx->tc_cluster_size * (uint32_t)TC_SLOTS : (uint32_t)T2B_CAP;
     const uint32_t qc_cap = N / 4096 + NM + 64;   // nodes with 16385..tc_cap primitives
-    const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..16384 primitives
+    const uint32_t qb_cap = N / 256 + NM + 4096;  // nodes with 2049..T2B_CAP primitives
     const uint32_t q_cap = N / 32 + NM + 4096;    // nodes with 257..2048 primitives (typically ~N/100)
     const uint32_t qw_cap = N / 4 + NM + 4096;    // nodes with 33..256 primitives (typically ~N/28)
     // sub-trees of <= 32 primitives: thread tasks (<= T4_MAX) and warp tasks (the rest).  Sibling ranges are disjoint,

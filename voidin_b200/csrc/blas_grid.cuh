@@ -1,5 +1,5 @@
 // blas_grid.cuh -- part of blas_build.cu (included there, inside its anonymous namespace; not a stand-alone header):
-// the grid tier: k_t1_coop and its phases (nodes above 16384 primitives).
+// the grid tier: k_t1_coop and its phases (nodes above T2B_CAP = 24576 primitives).
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
