@@ -94,6 +94,12 @@ extern "C" {
         d_mesh_info: *mut MeshInfo, n_meshes: usize, d_nodes_out: *mut BvhNode, nodes_cap: usize,
         n_nodes_out: *mut u32, stream: *mut c_void,
     ) -> c_int;
+    fn bvh_cuda_blas_build_batch_async_dev(
+        ctx: *mut ctx_t, d_vertices: *const f32, n_vertices: usize, d_indices: *mut u32, n_indices: usize,
+        d_mesh_info: *mut MeshInfo, n_meshes: usize, d_nodes_out: *mut BvhNode, nodes_cap: usize,
+        d_result: *mut u32, stream: *mut c_void,
+    ) -> c_int;
+    fn bvh_cuda_blas_build_finish(ctx: *mut ctx_t, n_nodes_out: *mut u32) -> c_int;
     fn bvh_cuda_scene_upload(ctx: *mut ctx_t, host_desc: *const SceneDesc, out: *mut *mut scene_t) -> c_int;
     fn bvh_cuda_scene_free(ctx: *mut ctx_t, scene: *mut scene_t);
     fn bvh_cuda_trace_closest(
@@ -212,6 +218,30 @@ pub unsafe fn build_pooled_scene_dev(
         );
         check(ctx, rc);
     });
+    used
+}
+
+/// The same forest build, stream-ordered: everything is enqueued on `stream` and the call returns at once; `d_result`
+/// (device, 4 x u32, may be null) receives {nodes, status bits, interior nodes, 0}.  `finish_pooled_scene_build` waits,
+/// checks the status (panics like the blocking build) and returns the node count.  One build in flight per thread context.
+///
+/// # Safety
+/// As `build_pooled_scene_dev`; the buffers must stay valid until `finish_pooled_scene_build` returns.
+pub unsafe fn enqueue_pooled_scene_build_dev(
+    d_vertices: *const f32, n_vertices: usize, d_indices: *mut u32, n_indices: usize, d_mesh_info: *mut MeshInfo,
+    n_meshes: usize, d_nodes_out: *mut BvhNode, nodes_cap: usize, d_result: *mut u32, stream: *mut c_void,
+) {
+    CTX.with(|&ctx| {
+        let rc = bvh_cuda_blas_build_batch_async_dev(
+            ctx, d_vertices, n_vertices, d_indices, n_indices, d_mesh_info, n_meshes, d_nodes_out, nodes_cap, d_result, stream,
+        );
+        check(ctx, rc);
+    });
+}
+
+pub fn finish_pooled_scene_build() -> u32 {
+    let mut used = 0u32;
+    CTX.with(|&ctx| unsafe { check(ctx, bvh_cuda_blas_build_finish(ctx, &mut used)) });
     used
 }
 
