@@ -650,10 +650,32 @@ def run_scene1024(args, rank, local_rank, world):
     stream = torch.cuda.current_stream().cuda_stream
     leg = config5_leg(args, ctx, rank, world, dev, stream, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
     if rank == 0:
+        st = ctx.last_build_stats()  # this rank's shard: one forest build over its meshes
+        peak, src = peaks()
+        vside = args.mesh_res
+        n_shard = leg["tris"] // world
+        v_shard = (2 * vside + 1) * (vside + 1) * (args.meshes // world)
+        bb = build_bytes(n_shard, v_shard, st["sum_interior_prims"], st["n_nodes"])
+        lb_ms = leg["build"]["ms_local_forest_build"]
+        leg["roofline"] = {"bound": "hbm", "kernel": "whole forest build of this rank's shard (all tiers)", "achieved": bb / (lb_ms * 1e-3) / 1e9,
+                           "peak": peak, "unit": "GB/s", "frac": bb / (lb_ms * 1e-3) / 1e9 / peak, "peak_source": src, "algorithmic_bytes": bb,
+                           "traffic": None, "S": st["sum_interior_prims"], "M": st["n_nodes"]}
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+            from voidin_b200 import scenes as S
+            sv, si = S.displaced_sphere(vside, 2 * vside, 5000)
+            t0 = time.perf_counter()
+            rc, _, _, _, _ = O.blas_build(sv, si)
+            dt = time.perf_counter() - t0
+            cpu = {"value": si.size // 3 / dt / 1e6, "unit": "Mtris/s", "cores": 1, "kind": "port",
+                   "sample": f"one displaced sphere of the scene's mesh size ({si.size // 3} tris) of {args.meshes}, single thread, {dt:.2f} s (rc {rc})"}
+        leg["cpu_baseline"] = cpu
         print(json.dumps({"metric": leg["build"]["metric"], "value": leg["build"]["value"], "unit": "Mtris/s", "n_gpus": world,
                           "steps": leg["steps"], "warmup": leg["warmup"], "ms_per_step": leg["build"]["ms_build_plus_gather"] + leg["tlas_ms"] + leg["scene_bake_ms"] + leg["rays"]["ms"],
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": leg["workload"]}, "config5": leg}), flush=True)
+                          "config": {"workload": leg["workload"]}, "roofline": leg["roofline"], "cpu_baseline": leg["cpu_baseline"],
+                          "config5": leg}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1085,6 +1085,23 @@ int oracle_gen_shadow_rays(const float* pos, const float* nor, size_t n, const f
     return ORACLE_OK;
 }
 
+// Rect area light (corner order of crates/pools/src/light.rs:28-52): same origin, direction toward
+// (p0 + (p1 - p0) * u) + (p3 - p0) * v.  The reference has no such shader yet (README TODO "raytraced shadows" for area lights);
+// this is the CPU twin of csrc/raygen.cu k_gen_area_shadow, same operation order, no contraction.
+int oracle_gen_area_shadow_rays(const float* pos, const float* nor, const float* uv, size_t n, const float* corners, float* ro, float* rd) {
+    for (size_t i = 0; i < n; ++i) {
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        for (int k = 0; k < 3; ++k) {
+            const float p = pos[3 * i + k];
+            const float o = p + nor[3 * i + k] * 0.0001f;
+            const float t = (corners[k] + (corners[3 + k] - corners[k]) * u) + (corners[9 + k] - corners[k]) * v;
+            ro[3 * i + k] = o;
+            rd[3 * i + k] = t - o;
+        }
+    }
+    return ORACLE_OK;
+}
+
 // shaders/compute_update.wgsl:12-27 with (sin, cos) of the angle as inputs (WGSL leaves their precision open);
 // matrix product = four-term column sums left to right (math.wgsl from_rotation_z, column-major).  With
 // update_inverse the stale inv_transform is multiplied by from_rotation_z(-angle) on the right.

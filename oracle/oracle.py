@@ -203,3 +203,12 @@ def gen_shadow_rays(pos, nor, light):
     ro, rd = np.empty_like(p), np.empty_like(p)
     lib().oracle_gen_shadow_rays(_p(p), _p(n), C.c_size_t(p.shape[0]), _p(l), _p(ro), _p(rd))
     return ro, rd
+
+
+def gen_area_shadow_rays(pos, nor, uv, corners):
+    """CPU twin of bvh_cuda_gen_area_shadow_rays_dev (rect light, corner order of crates/pools/src/light.rs:28-52)."""
+    p, n, w = _f32(pos).reshape(-1, 3), _f32(nor).reshape(-1, 3), _f32(uv).reshape(-1, 2)
+    c = _f32(corners).reshape(4, 3)
+    ro, rd = np.empty_like(p), np.empty_like(p)
+    lib().oracle_gen_area_shadow_rays(_p(p), _p(n), _p(w), C.c_size_t(p.shape[0]), _p(c), _p(ro), _p(rd))
+    return ro, rd

@@ -563,7 +563,9 @@ def test_ray_generation_bit_exact(ctx, oracle):
     uv = rng.random((pos.shape[0], 2)).astype(np.float32)
     d_uv = torch.from_numpy(uv.reshape(-1)).to(dev)
     vb.gen_area_shadow_rays_dev(ctx, d_p.data_ptr(), d_n.data_ptr(), d_uv.data_ptr(), pos.shape[0], corners, d_ro.data_ptr(), d_rd.data_ptr())
-    end = d_ro.cpu().numpy().reshape(-1, 3).astype(np.float64) + d_rd.cpu().numpy().reshape(-1, 3).astype(np.float64)
+    oro, ord_ = oracle.gen_area_shadow_rays(pos, nor, uv, corners)
+    assert (d_ro.cpu().numpy().reshape(-1, 3) == oro).all() and (d_rd.cpu().numpy().reshape(-1, 3) == ord_).all()
+    end = oro.astype(np.float64) + ord_.astype(np.float64)
     expect = corners[0] + (corners[1] - corners[0]) * uv[:, :1] + (corners[3] - corners[0]) * uv[:, 1:]
     assert np.abs(end - expect).max() < 1e-4
 

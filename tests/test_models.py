@@ -444,3 +444,26 @@ def test_load_single_mesh_pools_and_rebases(tmp_path):
     assert v.shape == (6, 3) and i.tolist() == [0, 1, 2, 3, 4, 5]
     assert M.find_asset("definitely-not-there.obj") is None
     assert S is not None
+
+
+def test_models_c_abi_argument_checks(tmp_path):
+    """Raw C ABI: null arguments and out-of-range indices come back as BVH_CUDA_EINVAL (-1), nothing crashes; an OBJ has no
+    instances; the error text of a failing load is kept per thread."""
+    import ctypes as C
+
+    lib = M._lib_models()
+    h = C.c_void_p()
+    assert lib.bvh_cuda_model_load_obj(None, C.byref(h)) == -1
+    assert lib.bvh_cuda_model_load_gltf(b"/nonexistent/x.glb", C.byref(h)) == -1 and not h.value
+    assert b"cannot read" in lib.bvh_cuda_model_last_error()
+    (tmp_path / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    assert lib.bvh_cuda_model_load_obj(str(tmp_path / "t.obj").encode(), C.byref(h)) == 0 and h.value
+    assert lib.bvh_cuda_model_mesh_count(h) == 1 and lib.bvh_cuda_model_instance_count(h) == 0
+    mv = M._MeshView()
+    assert lib.bvh_cuda_model_mesh(h, 1, C.byref(mv)) == -1 and lib.bvh_cuda_model_mesh(h, 0, None) == -1
+    assert lib.bvh_cuda_model_mesh(h, 0, C.byref(mv)) == 0 and mv.n_vertices == 3 and mv.n_indices == 3 and mv.name == b"unnamed_object"
+    assert lib.bvh_cuda_model_instance(h, 0, C.byref(M._InstanceView())) == -1
+    assert lib.bvh_cuda_model_material(h, 0, C.byref(M._MaterialView())) == -1
+    lib.bvh_cuda_model_free(h)
+    lib.bvh_cuda_model_free(None)
+    assert lib.bvh_cuda_model_mesh_count(None) == 0
