@@ -58,6 +58,10 @@ constexpr int T2W_CAP = T2W_CAP_V;  // warp-per-node tier: 33..T2W_CAP
 #define T1_PB_REUSE 1
 #endif
 // 1: the grid tier picks the tile size per level (p_t1_nextlevel); 0: always T1_TILE
+// grid tier, resident-tile pull form: 0 off, 1 for levels with 256-/512-slot tiles, 2 for all levels (see blas_grid.cuh)
+#ifndef T1_PULL_DEFAULT
+#define T1_PULL_DEFAULT 0  // measured: mode 1 gains 54 us on the small-tile levels and loses 80 us on the 2048-slot levels of the same kernel (register allocation), profiles/r02_build_variants_ab.txt
+#endif
 #ifndef T1_VAR_TILE
 #define T1_VAR_TILE 1
 #endif
@@ -341,10 +345,12 @@ int blas_tc_log(unsigned long long* out, unsigned int cap_rows) {
 
 int blas_t1_coop_occupancy() {
     int occ = 0;
-    int occ_pull = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop<false>, T1_THREADS, 0) != cudaSuccess) occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pull, k_t1_coop<true>, T1_THREADS, 0) != cudaSuccess) occ_pull = 1;
-    if (occ_pull < occ) occ = occ_pull;  // one grid size for both instantiations (BVH_CUDA_T1_PULL selects at run time)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_t1_coop<0>, T1_THREADS, 0) != cudaSuccess) occ = 1;
+    int o1 = 0, o2 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_t1_coop<1>, T1_THREADS, 0) != cudaSuccess) o1 = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_t1_coop<2>, T1_THREADS, 0) != cudaSuccess) o2 = 1;
+    if (o1 < occ) occ = o1;  // one grid size for all instantiations (BVH_CUDA_T1_PULL selects at run time)
+    if (o2 < occ) occ = o2;
     return occ < 1 ? 1 : occ;
 }
 
@@ -530,10 +536,10 @@ int blas_build_device(bvh_cuda_ctx* ctx, const float* d_vertices, size_t n_verti
         uint32_t lv_cap = max_large, ep = epoch, max_levels = 4096;
         uint4* recs_p = recs;
         uint32_t* A_p = A;
-        static const uint32_t pull_env = [] { const char* e = getenv("BVH_CUDA_T1_PULL"); return e ? (uint32_t)atoi(e) : 0u; }();
+        static const uint32_t pull_env = [] { const char* e = getenv("BVH_CUDA_T1_PULL"); return e ? (uint32_t)atoi(e) : (uint32_t)T1_PULL_DEFAULT; }();
         void* args[] = {&g, &lv0, &lv1, &lv_cap, &Q, &recs_p, &A_p, &ep, &max_levels};
         const uint32_t grid = t1_grid;
-        const void* kfn = pull_env ? (const void*)k_t1_coop<true> : (const void*)k_t1_coop<false>;
+        const void* kfn = pull_env == 1 ? (const void*)k_t1_coop<1> : (pull_env >= 2 ? (const void*)k_t1_coop<2> : (const void*)k_t1_coop<0>);
         CU_CHECK(ctx, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(T1_THREADS), args, 0, stream));
         launches += 1;
     }

@@ -752,9 +752,10 @@ __device__ __forceinline__ void t1_level(const T1Args& g, const bool scanned, ui
 // of L2 round trips or of how many blocks arrive at the barrier.  Built, verified bit-exact and not faster (first form in
 // commit ac13e1f): PA + barrier + PB as one function with the tile's ballots kept in registers and the tile
 // descriptor read once per level (3.87 ms vs 3.70 ms); barriers restricted to the blocks that own a tile (3.67 vs 3.69).
-// PULL = true is a second instantiation with the resident-tile path of blas_grid_pull.cuh (45 KB of static shared memory);
-// the default build launches PULL = false, whose code and resources are exactly the two-phase tier.
-template <bool PULL>
+// PULL selects the resident-tile path of blas_grid_pull.cuh: 0 = never (pure two-phase tier), 1 = for the levels whose tiles
+// are 256 or 512 slots (per-hole rank-select variant, 10 KB of shared memory; where it measured faster), 2 = for every level
+// whose tiles all have a block (table-expansion variant, 45 KB; measured slower at 2048-slot tiles).
+template <int PULL>
 __global__ void __launch_bounds__(T1_THREADS, T1_MIN_BLOCKS) k_t1_coop(T1Args g, LevelNode* lv0, LevelNode* lv1, uint32_t lv_cap, Queues Q,
                                                         uint4* recs, uint32_t* A, uint32_t epoch, uint32_t max_levels) {
     LevelNode* lv[2] = {lv0, lv1};
@@ -777,15 +778,23 @@ __global__ void __launch_bounds__(T1_THREADS, T1_MIN_BLOCKS) k_t1_coop(T1Args g,
         g.n_nodes = n_nodes;
         g.n_tiles = n_tiles;
         bool done = false;
-        if constexpr (PULL) {
+        if constexpr (PULL == 1) {
+            __shared__ __align__(16) T1SmemSmall s_pull;
+            if (n_tiles <= gridDim.x && gridDim.x <= (uint32_t)T1_MAX_NT && g.ept <= 2) {
+                if (g.ept == 1) t1_level_pull<1, T1SmemSmall>(g, s_pull, gen, level);
+                else t1_level_pull<2, T1SmemSmall>(g, s_pull, gen, level);
+                done = true;
+            }
+        }
+        if constexpr (PULL == 2) {
             // every tile has its own block: the tile stays in shared memory and a shuffle is one barrier (blas_grid_pull.cuh)
-            __shared__ __align__(16) T1Smem s_pull;
+            __shared__ __align__(16) T1SmemFull s_pull;
             if (n_tiles <= gridDim.x && gridDim.x <= (uint32_t)T1_MAX_NT) {
                 switch (g.ept) {
-                    case 1: t1_level_pull<1>(g, s_pull, gen, level); break;
-                    case 2: t1_level_pull<2>(g, s_pull, gen, level); break;
-                    case 4: t1_level_pull<4>(g, s_pull, gen, level); break;
-                    default: t1_level_pull<8>(g, s_pull, gen, level); break;
+                    case 1: t1_level_pull<1, T1SmemFull>(g, s_pull, gen, level); break;
+                    case 2: t1_level_pull<2, T1SmemFull>(g, s_pull, gen, level); break;
+                    case 4: t1_level_pull<4, T1SmemFull>(g, s_pull, gen, level); break;
+                    default: t1_level_pull<8, T1SmemFull>(g, s_pull, gen, level); break;
                 }
                 done = true;
             }

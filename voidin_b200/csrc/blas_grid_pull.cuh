@@ -20,14 +20,61 @@
 constexpr int T1_MAX_NT = 1024;        // tiles per node the shared prefix array can hold (>= the cooperative grid)
 constexpr int T1_META = 72;            // words per tile: [0,8) warp prefixes, [8 + 8 w + i] ballot word i of warp w
 
-struct T1Smem {
-    uint32_t id[2][T1_TILE];
-    uint16_t fw[2][T1_TILE];
+// TSMAX: largest tile the instantiation keeps resident; TAB: with the rank -> position table (expansion variant) or without
+// (per-hole rank-select variant, used for the small tiles of the default build).
+template <int TSMAX, bool TAB>
+struct T1SmemT {
+    static constexpr bool has_tab = TAB;
+    static constexpr int ts_max = TSMAX;
+    uint32_t id[2][TSMAX];
+    uint16_t fw[2][TSMAX];
     uint32_t pre[T1_MAX_NT + 4];       // exclusive prefix of the node's per-tile L counts; pre[nt] = nL
     uint32_t wsum[T1_THREADS / 32];
     uint32_t wfirst[T1_THREADS / 32 + 1];  // L bit of the first slot of every warp run; [8]: of the next tile
-    uint32_t tab[T1_TILE + 8];             // rank -> source position of this tile's holes (front holes, then back holes)
+    uint32_t tab[TAB ? TSMAX + 8 : 4];     // rank -> source position of this tile's holes (front holes, then back holes)
 };
+using T1SmemSmall = T1SmemT<2 * T1_THREADS, false>;  // tiles of 256 / 512 slots: the default build's pull levels
+using T1SmemFull = T1SmemT<T1_TILE, true>;           // every tile size (BVH_CUDA_T1_PULL=2)
+
+// position of the r-th (0-based) set bit of w; r < popc(w)
+__device__ __forceinline__ uint32_t select32(uint32_t w, uint32_t r) {
+    uint32_t pos = 0, c;
+    c = __popc(w & 0xFFFFu); if (r >= c) { r -= c; pos += 16; w >>= 16; }
+    c = __popc(w & 0xFFu);   if (r >= c) { r -= c; pos += 8;  w >>= 8; }
+    c = __popc(w & 0xFu);    if (r >= c) { r -= c; pos += 4;  w >>= 4; }
+    c = __popc(w & 0x3u);    if (r >= c) { r -= c; pos += 2;  w >>= 2; }
+    c = w & 1u;              if (r >= c) { pos += 1; }
+    return pos;
+}
+
+// rank-select inside a tile from its published meta: position (relative to the node) of its r-th L (or R)
+template <int EPT, bool WANT_L>
+__device__ __forceinline__ uint32_t t1_pull_select(const uint32_t* meta_tile, uint32_t t_in_node, uint32_t r) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(meta_tile);
+    const uint4 p0 = __ldcg(m4), p1 = __ldcg(m4 + 1);
+    uint32_t wp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    uint32_t w = 0, base = 0;
+#pragma unroll
+    for (int x = 1; x < 8; ++x) {
+        if (!WANT_L) wp[x] = (uint32_t)x * (32 * EPT) - wp[x];
+        if (wp[x] <= r) { w = x; base = wp[x]; }
+    }
+    r -= base;
+    const uint4 a0 = __ldcg(m4 + 2 + 2 * w);
+    uint32_t wd[4] = {a0.x, a0.y, a0.z, a0.w};   // EPT <= 4 words per warp run in this variant
+    uint32_t word = 0, wi = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const uint32_t x = WANT_L ? wd[i] : ~wd[i];
+        const uint32_t c = __popc(x);
+        if (!found) {
+            if (r < c) { found = true; word = x; wi = i; }
+            else r -= c;
+        }
+    }
+    return t_in_node * (uint32_t)(T1_THREADS * EPT) + w * (32 * EPT) + wi * 32 + select32(word, r);
+}
 
 #ifdef BVH_T1_TIMING
 #define PULL_MARK(k)                                                                       \
@@ -45,8 +92,8 @@ struct T1Tile {
 };
 
 // Ballots of plane `c` over the tile in shared buffer `cur`; publishes count + meta; leaves bal[] / wpre to the caller.
-template <int EPT>
-__device__ __forceinline__ void t1_pull_publish(const T1Args& g, T1Smem& sm, const T1Tile& t, int cur, int c, uint32_t* bal,
+template <int EPT, class SM>
+__device__ __forceinline__ void t1_pull_publish(const T1Args& g, SM& sm, const T1Tile& t, int cur, int c, uint32_t* bal,
                                                 uint32_t& wpre) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t a, b;
@@ -79,8 +126,8 @@ __device__ __forceinline__ void t1_pull_publish(const T1Args& g, T1Smem& sm, con
 }
 
 // One shuffle of the block's tile in pull form.  `bal` / `wpre`: the tile's ballots for plane c (from t1_pull_publish).
-template <int EPT>
-__device__ __forceinline__ void t1_pull_step(const T1Args& g, T1Smem& sm, const T1Tile& t, int cur, int c, const uint32_t* bal,
+template <int EPT, class SM>
+__device__ __forceinline__ void t1_pull_step(const T1Args& g, SM& sm, const T1Tile& t, int cur, int c, const uint32_t* bal,
                                              uint32_t wpre, const uint32_t* __restrict__ ids_in, const uint16_t* __restrict__ fl_in,
                                              uint32_t* ids_out, uint16_t* fl_out, const uint32_t level) {
     (void)level;
@@ -187,7 +234,7 @@ __device__ __forceinline__ void t1_pull_step(const T1Args& g, T1Smem& sm, const 
             n1 = search_rpre(Kmax, r1lo, nt) - r1lo + 1;
         }
     }
-    {
+    if constexpr (SM::has_tab) {
         constexpr uint32_t WPT = 8 * EPT;  // ballot words per tile
         for (uint32_t x = tid; x < (n0 + n1) * WPT; x += T1_THREADS) {
             const uint32_t e = x / WPT, wi = x % WPT, w = wi / EPT, i = wi % EPT;
@@ -255,13 +302,22 @@ __device__ __forceinline__ void t1_pull_step(const T1Args& g, T1Smem& sm, const 
             else if (p < f) {
                 if (!Lp) {
                     // hole in the front: the L that has k = RF(p) L's after it, i.e. the L of rank G = nL - 1 - k
-                    q = sm.tab[nL - 1u - (p - LFp) - Gmin];
+                    const uint32_t G = nL - 1u - (p - LFp);
+                    if constexpr (SM::has_tab) q = sm.tab[G - Gmin];
+                    else {
+                        const uint32_t T = search_pre(G, r0lo, r0lo + n0);
+                        q = t1_pull_select<(EPT > 4 ? 4 : EPT), true>(meta + (size_t)(t.tile_base + T) * T1_META, T, G - sm.pre[T]);
+                    }
                 }
             } else if (p + 1 < n && !Lq) q = p + 1;
             else {
                 // hole in the back: the R that has K R's before it
                 const uint32_t K = (p + 1 == n) ? 0u : nL - (LFp + Lp);
-                q = sm.tab[h0 + K - Kmin];
+                if constexpr (SM::has_tab) q = sm.tab[h0 + K - Kmin];
+                else {
+                    const uint32_t T = search_rpre(K, r1lo, r1lo + n1);
+                    q = t1_pull_select<(EPT > 4 ? 4 : EPT), false>(meta + (size_t)(t.tile_base + T) * T1_META, T, K - (T * TS - sm.pre[T]));
+                }
             }
         }
         srcq[i] = q;
@@ -298,8 +354,8 @@ __device__ __forceinline__ void t1_pull_step(const T1Args& g, T1Smem& sm, const 
 }
 
 // All shuffles of one level, every tile resident in the shared memory of its own block.
-template <int EPT>
-__device__ __forceinline__ void t1_level_pull(const T1Args& g, T1Smem& sm, uint32_t& gen, const uint32_t level) {
+template <int EPT, class SM>
+__device__ __forceinline__ void t1_level_pull(const T1Args& g, SM& sm, uint32_t& gen, const uint32_t level) {
     (void)level;
     constexpr uint32_t TS = T1_THREADS * EPT;
     T1_PHASE(0, p_t1_init(g));
@@ -321,7 +377,7 @@ __device__ __forceinline__ void t1_level_pull(const T1Args& g, T1Smem& sm, uint3
             sm.fw[0][s] = (p < t.n) ? __ldcg(g.fl0 + t.start + p) : (uint16_t)0;
         }
         __syncthreads();
-        t1_pull_publish<EPT>(g, sm, t, cur, 0, bal, wpre);
+        t1_pull_publish<EPT, SM>(g, sm, t, cur, 0, bal, wpre);
     }
     grid_barrier(g.barrier, gen);
     for (int c = 0; c < 22; ++c) {
@@ -332,18 +388,18 @@ __device__ __forceinline__ void t1_level_pull(const T1Args& g, T1Smem& sm, uint3
         if (c == 21) {
             T1_PHASE(3, p_t1_bins<EPT>(g, ids_in, fl_in));
             T1_PHASE(4, p_t1_select(g));
-            if (has_tile) t1_pull_publish<EPT>(g, sm, t, cur, 21, bal, wpre);
+            if (has_tile) t1_pull_publish<EPT, SM>(g, sm, t, cur, 21, bal, wpre);
             grid_barrier(g.barrier, gen);
         }
 #ifdef BVH_T1_TIMING
         const unsigned long long _t0 = gtimer();
 #endif
         if (has_tile) {
-            t1_pull_step<EPT>(g, sm, t, cur, c, bal, wpre, ids_in, fl_in, ids_out, fl_out, level);
+            t1_pull_step<EPT, SM>(g, sm, t, cur, c, bal, wpre, ids_in, fl_in, ids_out, fl_out, level);
             cur ^= 1;
             if (c < 20) {
                 __syncthreads();
-                t1_pull_publish<EPT>(g, sm, t, cur, c + 1, bal, wpre);
+                t1_pull_publish<EPT, SM>(g, sm, t, cur, c + 1, bal, wpre);
             }
         }
 #ifdef BVH_T1_TIMING
