@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 1200 python -m pytest tests -m gpu -x -q -k "tlas or smoke or animated or instances" > gpurun_out/r03f_pytest.log 2>&1 ) 2>&1 | grep real
+tail -3 gpurun_out/r03f_pytest.log
+for I in 4096 32767 100000; do
+timeout 600 python bench.py --workload instances --instances $I --steps 2 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('I=$I', d['phase_ms'], d['animated_frame']['ms'])"
+done

@@ -24,6 +24,14 @@ __device__ __forceinline__ float max_rs(float acc, float v) { return (v > acc) ?
 
 constexpr int CHAIN_THREADS = 1024;
 
+// warp-wide minimum of 64-bit keys (area bits << 32 | slot) with two redux.sync instead of five 64-bit shuffle rounds
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long key) {
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mh = __reduce_min_sync(FULL_MASK, hi);
+    const uint32_t ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
 __device__ __forceinline__ float3 xform_point(const float* m, float x, float y, float z) {
     // glam Mat4::transform_point3: ((X*x + Y*y) + Z*z) + W
     float3 r;
@@ -67,7 +75,8 @@ __global__ void __launch_bounds__(256) k_tlas_leaves(const Instance* __restrict_
 
 // Block-wide find_best_match (tlas.rs:87-105).  All threads return the same slot.
 __device__ __forceinline__ uint32_t find_best_match(const float* slot_box, uint32_t n_inst, uint32_t count,
-                                                    uint32_t target, unsigned long long* s_red) {
+                                                    uint32_t target, unsigned long long* s_red, uint32_t& par) {
+    par += 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float t0 = slot_box[target], t1 = slot_box[(size_t)n_inst + target], t2 = slot_box[2 * (size_t)n_inst + target];
     const float t3 = slot_box[3 * (size_t)n_inst + target], t4 = slot_box[4 * (size_t)n_inst + target],
@@ -86,33 +95,26 @@ __device__ __forceinline__ uint32_t find_best_match(const float* slot_box, uint3
             best = key < best ? key : best;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(FULL_MASK, best, o);
-        best = y < best ? y : best;
-    }
-    if (lane == 0) s_red[warp] = best;
+    best = warp_min_key(best);
+    // s_red is double buffered by call parity: one block barrier per call is enough (a warp can be at most one call ahead)
+    unsigned long long* red = s_red + 32 * (par & 1u);
+    if (lane == 0) red[warp] = best;
     __syncthreads();
-    unsigned long long v = s_red[lane];  // CHAIN_THREADS / 32 == 32 warps
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long y = __shfl_xor_sync(FULL_MASK, v, o);
-        v = y < v ? y : v;
-    }
-    __syncthreads();
+    const unsigned long long v = warp_min_key(red[lane]);  // CHAIN_THREADS / 32 == 32 warps
     return (v == 0xFFFFFFFFFFFFFFFFull) ? target : (uint32_t)(v & 0xFFFFFFFFull);
 }
 
 __global__ void __launch_bounds__(CHAIN_THREADS) k_tlas_chain(uint32_t n_inst, TlasNode* nodes, uint32_t* children,
                                                               float* slot_box, uint32_t* node_indices) {
-    __shared__ unsigned long long s_red[32];
+    __shared__ unsigned long long s_red[64];
+    uint32_t par = 0;
     const uint32_t tid = threadIdx.x;
     uint32_t count = n_inst;
     uint32_t used = 1 + n_inst;
     uint32_t a = 0;
-    uint32_t b = find_best_match(slot_box, n_inst, count, a, s_red);
+    uint32_t b = find_best_match(slot_box, n_inst, count, a, s_red, par);
     while (count > 0) {
-        const uint32_t c = find_best_match(slot_box, n_inst, count, b, s_red);
+        const uint32_t c = find_best_match(slot_box, n_inst, count, b, s_red, par);
         if (a == c) {
             if (tid == 0) {
                 const uint32_t idx_a = node_indices[a], idx_b = node_indices[b];
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_tlas_chain(uint32_t n_inst, T
             used += 1;
             count -= 1;
             __syncthreads();
-            b = find_best_match(slot_box, n_inst, count, a, s_red);
+            b = find_best_match(slot_box, n_inst, count, a, s_red, par);
         } else {
             a = b;
             b = c;
@@ -159,7 +161,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_tlas_chain(uint32_t n_inst, T
 // node ids, count, nodes_used) is replicated in every thread, so no CTA ever waits to learn what to do next.
 // Same sequence of operations as tlas.rs:56-84, same tie rules.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int CL_THREADS = 512;
+#ifndef CL_THREADS_V
+#define CL_THREADS_V 512
+#endif
+constexpr int CL_THREADS = CL_THREADS_V;
 constexpr int CL_MAX = 16;
 
 struct Cand {
@@ -178,8 +183,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_tlas_chain_cluster(uint32_t n_in
     float* bx = s_dyn;                                              // [6][cap] boxes of my slots
     uint32_t* ni = reinterpret_cast<uint32_t*>(s_dyn + 6 * (size_t)cap);  // [cap] node index of my slots
     __shared__ Cand s_cl[2][CL_MAX];
-    __shared__ unsigned long long s_red[CL_THREADS / 32];
-    __shared__ unsigned long long s_blk;
+    __shared__ unsigned long long s_red[2][CL_THREADS / 32];
     const uint32_t base = rank * cap;
 
     for (uint32_t j = tid; j < cap; j += CL_THREADS) {
@@ -219,24 +223,11 @@ __global__ void __launch_bounds__(CL_THREADS) k_tlas_chain_cluster(uint32_t n_in
                 key = k2 < key ? k2 : key;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long y = __shfl_xor_sync(FULL_MASK, key, o);
-            key = y < key ? y : key;
-        }
-        if (lane == 0) s_red[warp] = key;
+        key = warp_min_key(key);
+        // one block barrier per call: s_red is double buffered by call parity (as is the exchange buffer s_cl)
+        if (lane == 0) s_red[par][warp] = key;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long v = (lane < CL_THREADS / 32) ? s_red[lane] : 0xFFFFFFFFFFFFFFFFull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long y = __shfl_xor_sync(FULL_MASK, v, o);
-                v = y < v ? y : v;
-            }
-            if (lane == 0) s_blk = v;
-        }
-        __syncthreads();
-        const unsigned long long bkey = s_blk;
+        const unsigned long long bkey = warp_min_key((lane < CL_THREADS / 32) ? s_red[par][lane] : 0xFFFFFFFFFFFFFFFFull);
         // publish my CTA's candidate into every CTA's exchange buffer (thread t writes to CTA t)
         if (tid < C) {
             Cand c;
@@ -364,20 +355,22 @@ int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_i
     bool clustered = false;
     static const bool no_cluster = [] { const char* e = getenv("BVH_CUDA_TLAS"); return e && e[0] == 'b'; }();  // "block": force the one-block kernel
     if (I > 12288 && !no_cluster) {  // measured crossover: 4 096 -> block 16.7 ms vs cluster 25.1 ms; 32 767 -> 594 ms vs 234 ms
-        const uint32_t cap = (I + CL_MAX - 1) / CL_MAX;
+        static const uint32_t cl_env = [] { const char* e = getenv("BVH_CUDA_TLAS_CL"); const int v = e ? atoi(e) : 0; return (uint32_t)((v == 2 || v == 4 || v == 8 || v == 16) ? v : 0); }();
+        const uint32_t csize = cl_env ? cl_env : (uint32_t)CL_MAX;  // CTAs per cluster (A/B: BVH_CUDA_TLAS_CL=8)
+        const uint32_t cap = (I + csize - 1) / csize;
         const size_t smem = sizeof(float) * 6 * (size_t)cap + sizeof(uint32_t) * (size_t)cap;
         if (smem <= 200 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_tlas_chain_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tlas_chain_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) {
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(CL_MAX);
+                cfg.gridDim = dim3(csize);
                 cfg.blockDim = dim3(CL_THREADS);
                 cfg.dynamicSmemBytes = smem;
                 cfg.stream = stream;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = CL_MAX;
+                attr[0].val.clusterDim.x = csize;
                 attr[0].val.clusterDim.y = 1;
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
