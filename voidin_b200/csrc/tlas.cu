@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(CL_THREADS) k_tlas_chain_cluster(uint32_t n_in
                 for (int k = 0; k < 6; ++k) bx[(size_t)k * cap + j] = lb[k];
                 ni[j] = l_ni;
             }
-            cluster.sync();
+            // A block barrier is enough here: every CTA scans only its own slots, the only remote access of the update is
+            // the read of slot `last`, which nobody writes in this step, and the next remote access to the two rewritten
+            // slots comes after the cluster barrier inside the find_best_match below.
+            __syncthreads();
 #pragma unroll
             for (int k = 0; k < 6; ++k) a_box[k] = u[k];
             a_ni = used;
