@@ -280,6 +280,35 @@ def test_tlas_invariants(oracle):
             assert tl["instance_idx"][k] == 0xFFFFFFFF
 
 
+def test_tlas_best_match_cache_model_is_exact_and_saves_little(oracle):
+    """tests/tlas_cache_model.py: Tlas::build with every slot's find_best_match answer cached and repaired per merge.  The model
+    reproduces the oracle's bytes (random instances, lattices full of exact ties, the stale slot `a`), which pins the cache
+    rules — and it shows why the CUDA chain does not use them: the slots the walk visits next are the ones a merge has just
+    invalidated, so 2.8-2.9 full scans per merge remain against the reference's ~3.1 calls."""
+    import tlas_cache_model as TM
+    from voidin_b200.types import MESH_INFO
+
+    infos = np.zeros(3, dtype=MESH_INFO)
+    infos["min"] = [[-1, -1, -1], [-0.5, -2, -0.5], [-3, -0.2, -1]]
+    infos["max"] = [[1, 1, 1], [0.5, 2, 0.5], [3, 0.2, 1]]
+    cases = [S.random_instances(n, 3, seed=n, extent=e) for n, e in ((1, 20.0), (2, 20.0), (5, 500.0), (17, 20.0), (300, 500.0), (700, 20.0))]
+    mats = []
+    for x in range(6):
+        for y in range(5):
+            for z in range(4):
+                m = np.eye(4); m[:3, 3] = [3.0 * x, 3.0 * y, 3.0 * z]; mats.append(m)
+    cases.append(S.make_instances(np.stack(mats), [0] * len(mats)))
+    for inst in cases:
+        n = len(inst)
+        rc, tl, kids, calls, _ = oracle.tlas_build(inst, infos)
+        lo, hi, lr, k2, st = TM.build(tl["min"][1:n + 1].copy(), tl["max"][1:n + 1].copy())
+        assert rc == 0 and lo.tobytes() == np.ascontiguousarray(tl["min"]).tobytes() and hi.tobytes() == np.ascontiguousarray(tl["max"]).tobytes()
+        assert (lr == tl["left_right"]).all() and (k2 == kids).all()
+        assert st["merges"] == n and st["scans"] + st["lookups"] + 1 >= calls - n  # every reference call is a scan or a lookup
+        if n >= 300:
+            assert st["scans"] > 2.0 * n  # the cache removes well under half of the scans
+
+
 def test_traversal_equals_brute_force(oracle):
     v, idx = S.displaced_sphere(36, 72, 9)
     rc, nodes, perm, _, _ = oracle.blas_build(v, idx)
