@@ -310,6 +310,43 @@ def test_async_builds_on_two_contexts_overlap_and_match(oracle):
     assert e.value.code == -2
 
 
+def test_host_pointer_trace_pipeline_equals_device_calls(ctx):
+    """bvh_cuda_trace_any / _closest with host pointers cut the batch into chunks that alternate between two compute streams
+    and the scene's two control slots (csrc/api.cu).  1.3 Mi rays = 3 chunks: the results must equal one device-pointer
+    launch over the same rays, bit for bit, on both slots, pinned or pageable."""
+    import torch
+
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, inst = make_scene(builder, n_inst=200)
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    n = (1 << 20) + (1 << 18) + 777
+    ro, rd = S.rays_toward_box(n, [-20, -20, -20], [20, 20, 20], seed=91)
+    dev = torch.device("cuda", 0)
+    d_ro, d_rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    d_occ = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_t = torch.empty(n, dtype=torch.float32, device=dev)
+    d_tri = torch.empty(n, dtype=torch.int32, device=dev)
+    d_ins = torch.empty(n, dtype=torch.int32, device=dev)
+    scene.occluded_dev(d_ro.data_ptr(), d_rd.data_ptr(), n, d_occ.data_ptr())
+    scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), n, d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr())
+    torch.cuda.synchronize()
+    for pinned in (False, True):
+        h_ro = torch.from_numpy(ro).pin_memory().numpy() if pinned else ro
+        h_rd = torch.from_numpy(rd).pin_memory().numpy() if pinned else rd
+        for _ in range(2):  # the second call reuses both deferral lists and control slots
+            occ = scene.occluded(h_ro, h_rd)
+            t, tri, ins = scene.traverse_tlas(h_ro, h_rd)
+            assert (occ == d_occ.cpu().numpy()).all()
+            assert t.tobytes() == d_t.cpu().numpy().tobytes()
+            assert (tri == d_tri.cpu().numpy().view(np.uint32)).all() and (ins == d_ins.cpu().numpy().view(np.uint32)).all()
+    assert 0.05 < occ.mean() < 0.95
+
+
 def test_trace_with_staged_tlas_top_equals_default(ctx, oracle):
     """BVH_CUDA_TLAS_TOP=1 (read once per process, hence the child) serves the 255 TLAS nodes nearest the root, node 0 and
     their child pairs from shared memory (csrc/trace.cu TlasTop; off by default because it measured slower,

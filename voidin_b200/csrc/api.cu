@@ -128,6 +128,7 @@ int bvh_cuda_create(int device, bvh_cuda_ctx** out) {
         if (nc > 0) { ctx->tc_cluster_size = cs; ctx->tc_clusters = nc; break; }
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     for (auto& row : ctx->pipe_ev) for (auto& e : row) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -142,6 +143,8 @@ void bvh_cuda_destroy(bvh_cuda_ctx* ctx) {
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->trace_counter) cudaFree(ctx->trace_counter);
     if (ctx->defer_list) cudaFree(ctx->defer_list);
+    if (ctx->defer_list2) cudaFree(ctx->defer_list2);
+    if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& row : ctx->pipe_ev) for (auto& e : row) if (e) cudaEventDestroy(e);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -482,23 +485,29 @@ static int trace_host_pipelined(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, 
     uint32_t* dinst = st.ptr<uint32_t>(iin);
     const bool pipe = ctx->h2d_stream && ctx->d2h_stream && ctx->pipe_ev[1][15];
     cudaStream_t s = ctx->own_stream, sin = pipe ? ctx->h2d_stream : s, sout = pipe ? ctx->d2h_stream : s;
+    // chunks alternate between two compute streams (and the scene's two control slots): the tail of one chunk's persistent
+    // kernel -- a few long rays, ~0.3 ms -- overlaps the start of the next chunk instead of idling the GPU.
+    static const bool two = [] { const char* e = getenv("BVH_CUDA_TRACE_STREAMS"); return !(e && atoi(e) == 1); }();
+    cudaStream_t cs[2] = {s, (pipe && two && ctx->own_stream2) ? ctx->own_stream2 : s};
     static const size_t n_chunks = [] { const char* e = getenv("BVH_CUDA_TRACE_CHUNKS"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();
     size_t chunk = (n_rays + n_chunks - 1) / n_chunks;
     if (chunk < ((size_t)1 << 19)) chunk = (size_t)1 << 19;
     int k = 0;
     for (size_t b0 = 0; b0 < n_rays; b0 += chunk, ++k) {
         const size_t m = (n_rays - b0 < chunk) ? n_rays - b0 : chunk;
+        const int slot = (cs[1] != cs[0]) ? (k & 1) : 0;
+        cudaStream_t sc = cs[slot];
         CU_CHECK(ctx, cudaMemcpyAsync(dro + 3 * b0, ray_o + 3 * b0, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, sin));
         CU_CHECK(ctx, cudaMemcpyAsync(drd + 3 * b0, ray_d + 3 * b0, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, sin));
         if (pipe) {
             CU_CHECK(ctx, cudaEventRecord(ctx->pipe_ev[0][k], sin));
-            CU_CHECK(ctx, cudaStreamWaitEvent(s, ctx->pipe_ev[0][k], 0));
+            CU_CHECK(ctx, cudaStreamWaitEvent(sc, ctx->pipe_ev[0][k], 0));
         }
-        rc = any_hit ? trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 1, nullptr, nullptr, nullptr, docc + b0, s)
-                     : trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 0, dt + b0, dtri + b0, dinst + b0, nullptr, s);
+        rc = any_hit ? trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 1, nullptr, nullptr, nullptr, docc + b0, sc, slot)
+                     : trace_scene_device(ctx, scene, dro + 3 * b0, drd + 3 * b0, m, tmax, 0, dt + b0, dtri + b0, dinst + b0, nullptr, sc, slot);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         if (pipe) {
-            CU_CHECK(ctx, cudaEventRecord(ctx->pipe_ev[1][k], s));
+            CU_CHECK(ctx, cudaEventRecord(ctx->pipe_ev[1][k], sc));
             CU_CHECK(ctx, cudaStreamWaitEvent(sout, ctx->pipe_ev[1][k], 0));
         }
         if (any_hit) {
@@ -514,6 +523,7 @@ static int trace_host_pipelined(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, 
         CU_CHECK(ctx, cudaStreamSynchronize(sout));
     }
     CU_CHECK(ctx, cudaStreamSynchronize(s));
+    if (cs[1] != s) CU_CHECK(ctx, cudaStreamSynchronize(cs[1]));
     return BVH_CUDA_OK;
 }
 

@@ -23,6 +23,7 @@ struct bvh_cuda_ctx {
     std::string err;
     uint64_t launches = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream2 = nullptr;  // second compute stream of the host-pointer trace pipeline (chunks alternate)
     // host-pointer trace calls: uploads and read-backs run on their own streams, pipelined against the kernels
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t pipe_ev[2][16] = {};
@@ -47,6 +48,8 @@ struct bvh_cuda_ctx {
     void* trace_counter = nullptr;  // persistent-warp ray counter of trace_blas
     uint32_t* defer_list = nullptr;  // rays the order-free any-hit kernel hands to the exact kernel
     size_t defer_cap = 0;
+    uint32_t* defer_list2 = nullptr;  // the same for launches in control slot 1 (two traces of one scene in flight)
+    size_t defer_cap2 = 0;
     // optional per-phase timing
     bool profiling = false;
     cudaEvent_t ev[10] = {};
@@ -101,7 +104,7 @@ int trace_blas_rec_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float
                           uint8_t* d_hit, cudaStream_t stream);
 int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
                        const float* d_ray_d, size_t n_rays, float tmax, int any_hit, float* d_t, uint32_t* d_tri,
-                       uint32_t* d_inst, uint8_t* d_occ, cudaStream_t stream);
+                       uint32_t* d_inst, uint8_t* d_occ, cudaStream_t stream, int slot = 0);
 
 #ifdef __CUDACC__
 // Order-preserving float <-> uint map (so min/max can use integer redux / atomics).  -0.0 sorts below +0.0.

@@ -778,7 +778,9 @@ int trace_blas_rec_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float
 
 int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o, const float* d_ray_d,
                        size_t n_rays, float tmax, int any_hit, float* d_t, uint32_t* d_tri, uint32_t* d_inst,
-                       uint8_t* d_occ, cudaStream_t stream) {
+                       uint8_t* d_occ, cudaStream_t stream, int slot) {
+    // slot 0 / 1: which of the scene's two control blocks (ray counter, deferral counters) and of the context's two deferral
+    // lists this launch uses, so that two launches on one scene can be in flight on two streams (host-pointer pipeline)
     if (!scene || !d_ray_o || !d_ray_d) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null pointer");
     if (any_hit ? !d_occ : (!d_t || !d_tri || !d_inst)) return ctx_fail(ctx, BVH_CUDA_EINVAL, "trace: null output");
     if (n_rays == 0) return BVH_CUDA_OK;
@@ -795,8 +797,10 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     }();
     (void)votes_set;
     // persistent warps: the ray counters live in the scene's control block, reset per launch
-    unsigned long long* counter = reinterpret_cast<unsigned long long*>(scene->counter);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(scene->counter) + 4 * (slot ? 1 : 0);
     CU_CHECK(ctx, cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), stream));
+    uint32_t*& dlist = slot ? ctx->defer_list2 : ctx->defer_list;
+    size_t& dcap = slot ? ctx->defer_cap2 : ctx->defer_cap;
     size_t want = (n_rays + 127) / 128;
     const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
@@ -805,12 +809,12 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     static const bool top = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e && atoi(e) != 0; }();
     if (any_hit && !wide_off && tmax <= MAXD && n_rays < 0xFFFFFFFFull) {
         // order-free kernel first; whatever it defers (normally nothing) goes through the exact kernel
-        if (ctx->defer_cap < n_rays) {
-            if (ctx->defer_list) cudaFree(ctx->defer_list);
-            ctx->defer_list = nullptr; ctx->defer_cap = 0;
-            cudaError_t e = cudaMalloc(&ctx->defer_list, n_rays * sizeof(uint32_t));
+        if (dcap < n_rays) {
+            if (dlist) cudaFree(dlist);
+            dlist = nullptr; dcap = 0;
+            cudaError_t e = cudaMalloc(&dlist, n_rays * sizeof(uint32_t));
             if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(defer list)");
-            ctx->defer_cap = n_rays;
+            dcap = n_rays;
         }
         // persistent grid: exactly the resident blocks (more warps than that only start when the rays are gone)
         static const int any_bps = [] {
@@ -824,12 +828,12 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
         const unsigned blocks_any = (unsigned)(want < cap_any ? want : cap_any);
         // BVH_CUDA_TRACE_STEAL=0 switches the tail's intra-warp work stealing off (A/B)
         static const uint32_t steal = [] { const char* e = getenv("BVH_CUDA_TRACE_STEAL"); return (e && atoi(e) == 0) ? 0u : 1u; }();
-        if (top) k_trace_any<true><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list, steal);
-        else k_trace_any<false><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, ctx->defer_list, steal);
+        if (top) k_trace_any<true><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, dlist, steal);
+        else k_trace_any<false><<<blocks_any, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_occ, counter, dlist, steal);
         ctx->launches++;
         // (the deferral pass normally finds an empty list: it runs without staging)
         k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
-                                                                counter + CTL_DEFER_RAY, ctx->defer_list, counter + CTL_DEFER_N);
+                                                                counter + CTL_DEFER_RAY, dlist, counter + CTL_DEFER_N);
     } else if (any_hit) {
         if (top) k_trace_scene<true, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
         else k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
