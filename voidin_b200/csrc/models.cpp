@@ -7,6 +7,7 @@
 //                                                      :209-220 (data_of_accessor)            gltf 1.2.0
 // tobj and gltf are crates.io dependencies that are not part of the voidin checkout (Cargo.lock pins them); what is
 // restated here is their published behaviour for exactly the options voidin passes.  Host code only, no CUDA.
+#include <ctype.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -683,7 +684,7 @@ int load_gltf(const std::string& path, bvh_cuda_model& model) {
             } else {
                 std::string rel;  // percent-decoding, as gltf::import does for file uris
                 for (size_t k = 0; k < uri->s.size(); ++k) {
-                    if (uri->s[k] == '%' && k + 2 < uri->s.size() + 0 && isxdigit((unsigned char)uri->s[k + 1]) && isxdigit((unsigned char)uri->s[k + 2])) {
+                    if (uri->s[k] == '%' && k + 2 < uri->s.size() && isxdigit((unsigned char)uri->s[k + 1]) && isxdigit((unsigned char)uri->s[k + 2])) {
                         rel += (char)strtol(uri->s.substr(k + 1, 2).c_str(), nullptr, 16);
                         k += 2;
                     } else rel += uri->s[k];
