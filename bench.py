@@ -989,6 +989,7 @@ def run_dragon(args, rank, local_rank, world):
                       "launch_ms": grid_ms, "share_of_build": grid_ms / lib_ms["ms_total"],
                       "algorithmic_bytes": grid_bytes, "S_grid": s_grid, "nodes_grid": n_grid,
                       "traffic_note": "ncu DRAM bytes of that launch; far below the algorithmic bytes because the working set stays in L2",
+                      "issue": (tr.get("k_t1_coop_issue") if tr else None),
                       "whole_build": {"achieved": bb / (lib_ms["ms_total"] * 1e-3) / 1e9, "frac": bb / (lib_ms["ms_total"] * 1e-3) / 1e9 / peak,
                                       "algorithmic_bytes": bb, "S": st["sum_interior_prims"], "M": st["n_nodes"],
                                       "note": "plane + dragon forest build, all tiers (latency-bound chain of dependent passes); per-phase device ms in phase_ms_dragon"}}
