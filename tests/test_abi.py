@@ -88,12 +88,22 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, str(c_src), "-o", str(tmp_path / "t_c")])
     assert subprocess.call([str(tmp_path / "t_c")]) == 0
     cxx_src = tmp_path / "t.cpp"
+    (tmp_path / "tri.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nf 1 2 3 4\n")
     cxx_src.write_text(
         '#include "bvh_cuda.hpp"\n#include <cstdio>\n'
-        "int main(){ try { bvh_cuda::Context c(0); std::puts(\"ctx\"); } catch (const bvh_cuda::Error& e) { std::puts(\"nogpu\"); }\n"
+        "int main(int argc, char** argv){\n"
+        "  bvh_cuda::Model m = bvh_cuda::ObjModel::import(argv[1]);  // host only: works without a GPU\n"
+        "  if (m.meshes.size() != 1 || m.meshes[0].vertices.size() != 12 || m.meshes[0].indices.size() != 6) return 2;\n"
+        "  try { bvh_cuda::GltfDocument::import(\"/nonexistent.glb\"); return 3; } catch (const bvh_cuda::Error&) {}\n"
+        "  try { bvh_cuda::Context c(0); std::puts(\"ctx\");\n"
+        "        bvh_cuda::Mesh& q = m.meshes[0];\n"
+        "        bvh_cuda::Bvh b = bvh_cuda::BvhBuilder(c, q.vertices.data(), 4, q.indices.data(), 2).set_bin_number(8).build();\n"
+        "        std::vector<bvh_cuda::Ray> rays(1); rays[0] = bvh_cuda::Ray{{0.25f, 0.25f, 1.0f}, {0.0f, 0.0f, -1.0f}};\n"
+        "        if (!b.traverse_iter(c, q.vertices.data(), 4, q.indices.data(), 2, rays)[0].hit) return 4;\n"
+        "  } catch (const bvh_cuda::Error& e) { std::puts(\"nogpu\"); }\n"
         " return bvh_cuda_abi_version() == 5 ? 0 : 1; }\n")
     libdir = os.path.join(ROOT, "voidin_b200")
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I", inc, str(cxx_src), "-o", str(tmp_path / "t_cxx"), "-L", libdir,
                            "-lbvh_cuda", f"-Wl,-rpath,{libdir}"])
-    out = subprocess.run([str(tmp_path / "t_cxx")], capture_output=True, text=True)
+    out = subprocess.run([str(tmp_path / "t_cxx"), str(tmp_path / "tri.obj")], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() in ("ctx", "nogpu")
