@@ -225,8 +225,11 @@ int bvh_cuda_trace_closest_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, c
                                const float* d_ray_d, size_t n_rays, float tmax, float* d_t_out,
                                uint32_t* d_tri_out, uint32_t* d_inst_out, void* stream);
 
-/* Shadow rays: occluded[r] = traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102), computed with
- * early exit at the first accepted triangle of the same traversal order. */
+/* Shadow rays: occluded[r] = traverse_tlas(ray).hit (src/bin/raytraced_shadows.wgsl:98-102).  The boolean does not depend
+ * on the visit order, so the kernel is free to reorder the traversal (two stacks per lane, lanes of a warp sharing the last
+ * long rays); rays for which that argument does not hold (zero / non-finite reciprocal direction, stack overflow) run in
+ * the reference's order.  Every entry of the output is written.  The host-pointer calls cut large batches into chunks and
+ * overlap upload, kernels (two compute streams) and read-back; give them pinned buffers. */
 int bvh_cuda_trace_any(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* ray_o, const float* ray_d,
                        size_t n_rays, float tmax, uint8_t* occluded_out);
 int bvh_cuda_trace_any_dev(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const float* d_ray_o,
