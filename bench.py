@@ -412,6 +412,8 @@ def run_small_configs(args, local_rank):
                          d_inds.data_ptr(), ctx, device_ptrs=True,
                          counts={"tlas_nodes": 2 * n_inst + 1, "instances": n_inst, "meshes": len(meshes), "bvh_nodes": mm[0],
                                  "vertices": d_verts.numel() // 3, "indices": d_inds.numel()}, stream=stream)
+        # tight per-instance world boxes for the exact-order kernels (a wrapped scene: recomputed whenever the instance buffer changes)
+        scene.instance_boxes(True, stream)
         n_rays = 1 << 20 if args.rays == N_RAYS else args.rays
         ro, rd = S.rays_sphere_to_cube(n_rays, 1200.0, 500.0, seed=13)
         d_ro, d_rd = up(ro, np.float32), up(rd, np.float32)
@@ -452,6 +454,7 @@ def run_small_configs(args, local_rank):
             ang = np.float32(2.0 * np.sin(tm_s * 0.5)) * np.float32(dt)
             vb.instances_rotate_z_dev(ctx, d_inst.data_ptr(), None, n_inst, float(np.sin(ang)), float(np.cos(ang)), True, stream)
             ctx.tlas_build_dev(d_inst.data_ptr(), n_inst, d_info.data_ptr(), len(meshes), d_tlas.data_ptr(), d_kids.data_ptr(), stream)
+            scene.instance_boxes(True, stream)
             scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), n_rays, d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr(), 1e30, stream)
 
         f_ms = timed(animated_frame, max(1, min(steps, 3)))

@@ -186,6 +186,16 @@ int bvh_cuda_scene_wrap_dev(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* dev_desc,
 /* Re-bakes a wrapped scene after its buffers were rewritten in place (e.g. a BLAS rebuilt into the same node /
  * index buffers); dev_desc may be NULL to keep the pointers, or carry new pointers/counts with the same n_indices. */
 int bvh_cuda_scene_refresh_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, const BvhCudaSceneDesc* dev_desc, void* stream);
+/* Instance culling for the exact-order kernels (bvh_cuda_trace_closest*, and the any-hit rays that need the reference's
+ * order).  Tlas::build seeds every leaf box with the UNtransformed local box (tlas.rs:39), so instances far from the origin get
+ * leaf boxes stretched back to it and a ray "enters" many instances only to miss the children of their BLAS root
+ * (instance_intersect, bvh.wgsl:78-87).  With enable != 0 the library computes, from the scene's CURRENT instance / mesh / node
+ * buffers, a tight world box per instance (BLAS root box mapped through the inverse of inv_transform, grown well beyond the
+ * rounding error of the object-space tests) and drops visits whose box the ray misses -- results are identical, the
+ * TlasNode bytes are untouched.  Uploaded scenes (immutable copies) have it on from the start.  For wrapped scenes it is
+ * off until this call, and the boxes go STALE when the caller rewrites the instance buffer: call again (or
+ * bvh_cuda_scene_refresh_dev, which recomputes them when enabled) after every such change.  enable = 0 switches it off. */
+int bvh_cuda_scene_instance_boxes_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, int enable, void* stream);
 void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene);
 
 /* ---- traversal ----------------------------------------------------------------------------------------- *

@@ -310,6 +310,55 @@ def test_async_builds_on_two_contexts_overlap_and_match(oracle):
     assert e.value.code == -2
 
 
+def test_instance_culling_keeps_results_on_a_config3_like_scene(ctx, oracle):
+    """Uploaded scenes cull instance visits with tight world boxes (csrc/trace.cu k_instance_wbox).  BASELINE config 3's shape:
+    thousands of instances far from the origin, whose TLAS leaf boxes are stretched back to it (tlas.rs:39), so nearly every
+    visit is one the culling drops.  Closest-hit ids / t and the exact-order any-hit flags must equal the oracle's, for primary-like
+    rays and for rays aimed exactly at mesh vertices of far instances (grazing the instance's own box), incl. a sheared and a
+    mirrored instance, a singular one (never culled) and non-uniform scales."""
+    def builder(v, i):
+        b, gi = gpu_build(ctx, v, i)
+        return b.nodes, gi
+
+    verts, inds, nodes, infos, _ = make_scene(builder, n_inst=4)
+    inst = S.random_instances(3000, infos.shape[0], seed=33, extent=400.0)
+    # odd ones: non-uniform scale, shear, mirror, singular (inverse of a singular matrix is whatever the caller supplies)
+    def set_tf(k, m):
+        inst["transform"][k] = m.T.reshape(-1).astype(np.float32)
+        inst["inv_transform"][k] = np.linalg.inv(m).T.reshape(-1).astype(np.float32)
+    base = np.eye(4); base[:3, 3] = [120.0, -80.0, 60.0]
+    set_tf(0, base @ np.diag([3.0, 0.4, 1.5, 1.0]))
+    sh = np.eye(4); sh[0, 1] = 0.7; sh[2, 0] = -0.3
+    set_tf(1, base @ sh)
+    set_tf(2, base @ np.diag([-1.0, 1.0, 1.0, 1.0]))
+    inst["inv_transform"][3] = 0.0
+    inst["inv_transform"][3][15] = 1.0
+    tl = vb.Tlas.empty(ctx)
+    tl.build(inst, infos)
+    scene = vb.Scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ctx)
+    ro, rd = S.rays_sphere_to_cube(60_000, 900.0, 400.0, seed=13)
+    # rays toward vertices of the meshes of far instances, through the instance's forward transform
+    rng = np.random.default_rng(8)
+    pick = rng.integers(0, len(inst), 40_000)
+    vo = infos["vertex_offset"][inst["mesh"][pick]].astype(np.int64)
+    nv = np.append(infos["vertex_offset"][1:], verts.shape[0]).astype(np.int64)[inst["mesh"][pick]] - vo
+    local = verts[vo + (rng.integers(0, 1 << 30, pick.size) % nv)]
+    M = inst["transform"][pick].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    world = np.einsum("nij,nj->ni", M[:, :3, :3], local.astype(np.float64)) + M[:, :3, 3]
+    org = (rng.normal(size=world.shape) * 300.0)
+    ro = np.concatenate([ro, org.astype(np.float32)])
+    rd = np.concatenate([rd, (world - org).astype(np.float32)])
+    t, tri, ins = scene.traverse_tlas(ro, rd)
+    ot, otri, oins, _, st = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
+    assert (tri == otri).all() and (ins == oins).all() and np.allclose(t, ot, rtol=T_RTOL, atol=0.0)
+    assert (otri != 0xFFFFFFFF).sum() > 5_000 and st["instance_visits"] > 50 * len(ro)  # the reference really does enter them all
+    # exact-order any-hit (tmax above 1e30 routes every ray through k_trace_scene<true>)
+    occ = scene.occluded(ro[:30_000], rd[:30_000], tmax=3e38)
+    _, _, _, oocc, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro[:30_000], rd[:30_000], tmax=3e38,
+                                          any_hit=True, threads=oracle.max_threads())
+    assert (occ == oocc).all()
+
+
 def test_host_pointer_trace_pipeline_equals_device_calls(ctx):
     """bvh_cuda_trace_any / _closest with host pointers cut the batch into chunks that alternate between two compute streams
     and the scene's two control slots (csrc/api.cu).  1.3 Mi rays = 3 chunks: the results must equal one device-pointer
@@ -666,6 +715,8 @@ def test_animated_instances_frame_loop(ctx, oracle):
         ctx.tlas_build_dev(d_inst.data_ptr(), n, d_info.data_ptr(), infos.shape[0], d_tlas.data_ptr(), d_kids.data_ptr())
         rc, otl, okids, _, _ = oracle.tlas_build(ref, infos)
         assert d_tlas.cpu().numpy().view(TLAS_NODE).tobytes() == otl.tobytes()
+        if frame >= 1:
+            scene.instance_boxes(True)  # wrapped scene: the culling boxes follow the rewritten instance buffer (frame 0: off)
         scene.traverse_tlas_dev(d_ro.data_ptr(), d_rd.data_ptr(), len(ro), d_t.data_ptr(), d_tri.data_ptr(), d_ins.data_ptr())
         ot, otri, oins, _, _ = oracle.trace_scene(otl, okids, ref, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
         assert (d_tri.cpu().numpy().view(np.uint32) == otri).all() and (d_ins.cpu().numpy().view(np.uint32) == oins).all()

@@ -29,6 +29,7 @@ SYMBOLS = [
     "bvh_cuda_scene_upload",
     "bvh_cuda_scene_wrap_dev",
     "bvh_cuda_scene_refresh_dev",
+    "bvh_cuda_scene_instance_boxes_dev",
     "bvh_cuda_scene_free",
     "bvh_cuda_trace_blas",
     "bvh_cuda_trace_blas_dev",
@@ -131,6 +132,7 @@ def load() -> C.CDLL:
     lib.bvh_cuda_scene_upload.argtypes = [vp, C.POINTER(SceneDesc), C.POINTER(vp)]
     lib.bvh_cuda_scene_wrap_dev.argtypes = [vp, C.POINTER(SceneDesc), vp, C.POINTER(vp)]
     lib.bvh_cuda_scene_refresh_dev.argtypes = [vp, vp, C.POINTER(SceneDesc), vp]
+    lib.bvh_cuda_scene_instance_boxes_dev.argtypes = [vp, vp, C.c_int, vp]
     lib.bvh_cuda_scene_free.argtypes = [vp, vp]
     lib.bvh_cuda_scene_free.restype = None
     lib.bvh_cuda_trace_blas.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, vp, sz, vp, vp]

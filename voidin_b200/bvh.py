@@ -312,6 +312,12 @@ class Scene:
         d = np.ascontiguousarray(ray_d, dtype=np.float32).reshape(-1, 3)
         return o, d
 
+    def instance_boxes(self, enable: bool = True, stream: int = 0):
+        """(Re)compute the tight per-instance world boxes the exact-order kernels cull with (wrapped scenes: call again after
+        every change of the instance buffer; uploaded scenes have them from the start)."""
+        ctx = self._ctx
+        ctx.check(ctx.lib.bvh_cuda_scene_instance_boxes_dev(ctx.h, self.h, 1 if enable else 0, stream))
+
     def traverse_tlas(self, ray_o, ray_d, tmax: float = 1e30):
         """Closest hit.  Returns (t, tri, inst)."""
         ctx = self._ctx

@@ -327,6 +327,8 @@ int bvh_cuda_scene_upload(bvh_cuda_ctx* ctx, const BvhCudaSceneDesc* h, bvh_cuda
     sc->d.vertices = (const float*)(b + off[5]);
     sc->d.indices = (const uint32_t*)(b + off[6]);
     rc = scene_bake_device(ctx, sc, ctx->own_stream);
+    // an uploaded scene owns immutable copies of its buffers, so the instance boxes can never go stale: always on
+    if (rc == BVH_CUDA_OK) rc = scene_instance_boxes_device(ctx, sc, 1, ctx->own_stream);
     if (rc == BVH_CUDA_OK && cudaStreamSynchronize(ctx->own_stream) != cudaSuccess) rc = ctx_cuda_fail(ctx, cudaGetLastError(), "bake");
     if (rc) { bvh_cuda_scene_free(ctx, sc); return rc; }
     *out = sc;
@@ -359,7 +361,15 @@ int bvh_cuda_scene_refresh_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, const B
         if (d->n_indices != scene->d.n_indices) return ctx_fail(ctx, BVH_CUDA_EINVAL, "scene_refresh: index count changed");
         scene->d = *d;
     }
-    return scene_bake_device(ctx, scene, (cudaStream_t)stream);
+    int rc = scene_bake_device(ctx, scene, (cudaStream_t)stream);
+    if (rc == BVH_CUDA_OK && scene->wbox_on) rc = scene_instance_boxes_device(ctx, scene, 1, (cudaStream_t)stream);
+    return rc;
+}
+
+int bvh_cuda_scene_instance_boxes_dev(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, int enable, void* stream) {
+    if (!ctx || !scene) return BVH_CUDA_EINVAL;
+    DeviceGuard g(ctx->device);
+    return scene_instance_boxes_device(ctx, scene, enable, (cudaStream_t)stream);
 }
 
 void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene) {
@@ -367,6 +377,7 @@ void bvh_cuda_scene_free(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene) {
     auto release = [&] {
         if (scene->owned && scene->block) cudaFree(scene->block);
         if (scene->baked) cudaFree(scene->baked);
+        if (scene->wbox) cudaFree(scene->wbox);
     };
     if (ctx) { DeviceGuard g(ctx->device); release(); }
     else release();

@@ -68,6 +68,8 @@ struct bvh_cuda_scene {
     void* block = nullptr;  // single allocation when owned
     void* baked = nullptr;  // 3 x float4 per pooled triangle (always owned)
     void* counter = nullptr;  // persistent-warp ray counter (tail of `baked`)
+    void* wbox = nullptr;     // optional: 2 x float4 per instance, tight world box of the instance's BLAS root (owned)
+    bool wbox_on = false;     // the exact-order kernels drop instance visits whose world box the ray misses
 };
 
 // makes the context's device current for the duration of an entry point
@@ -96,6 +98,7 @@ int blas_build_finish(bvh_cuda_ctx* ctx, uint32_t* n_nodes_out);
 int tlas_build_device(bvh_cuda_ctx* ctx, const Instance* d_instances, size_t n_inst, const MeshInfo* d_meshes,
                       size_t n_mesh, TlasNode* d_nodes_out, uint32_t* d_children_out, cudaStream_t stream);
 int scene_bake_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, cudaStream_t stream);
+int scene_instance_boxes_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, int enable, cudaStream_t stream);
 int trace_blas_device(bvh_cuda_ctx* ctx, const BvhNode* d_nodes, const float* d_vertices,
                       const uint32_t* d_indices, const float* d_ray_o, const float* d_ray_d, size_t n_rays,
                       float* d_t, uint32_t* d_tri, cudaStream_t stream);

@@ -330,6 +330,77 @@ __global__ void __launch_bounds__(256) k_bake_tris(BvhCudaSceneDesc sc, float4* 
     }
 }
 
+// ---- tight world boxes of the instances (optional, exact-order kernels only) ----------------------------------------
+// Tlas::build seeds every TLAS leaf with the untransformed local box (tlas.rs:39), so an instance far from the origin has a
+// leaf box stretched all the way back to it and most rays "enter" it: instance_intersect (bvh.wgsl:78-87) then transforms
+// the ray, fetches the BLAS root's children and finds that it misses both.  With the box below the kernel drops such a
+// visit before it loads the 144-byte instance.  Results are identical: a triangle can only be accepted inside an instance
+// if some box of its BLAS passes the float slab test (or, for a root that is a leaf, the triangle test itself), which
+// puts the ray within rounding distance of the BLAS root box; the box here is that root box mapped to world space through
+// the inverse of the linear part of `inv_transform` (in double; the reference maps rays with inv_transform and never
+// looks at `transform`), grown by 1e-3 of its own size, and the test adds 1e-4 of the coordinates involved -- both far above
+// the error of the object-space arithmetic for the conditioning this accepts (cond <= 100; anything else, or any
+// non-finite number, gets an infinite box, i.e. no culling).  w of the low corner = largest |coordinate| of the box.
+__global__ void __launch_bounds__(128) k_instance_wbox(BvhCudaSceneDesc sc, float4* wbox) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n_instances) return;
+    const float inf = __int_as_float(0x7F800000);
+    float4 lo = make_float4(-inf, -inf, -inf, inf), hi = make_float4(inf, inf, inf, 0.0f);
+    const Instance* in = sc.instances + i;
+    if (in->mesh < sc.n_meshes && sc.meshes[in->mesh].bvh_index < sc.n_bvh_nodes) {
+        const BvhNode root = sc.bvh_nodes[sc.meshes[in->mesh].bvh_index];
+        const float* A = in->inv_transform;  // column-major; object = L * world + t
+        const double l00 = A[0], l10 = A[1], l20 = A[2], l01 = A[4], l11 = A[5], l21 = A[6], l02 = A[8], l12 = A[9], l22 = A[10];
+        const double t0 = A[12], t1 = A[13], t2 = A[14];
+        const double c00 = l11 * l22 - l12 * l21, c01 = l02 * l21 - l01 * l22, c02 = l01 * l12 - l02 * l11;
+        const double c10 = l12 * l20 - l10 * l22, c11 = l00 * l22 - l02 * l20, c12 = l02 * l10 - l00 * l12;
+        const double c20 = l10 * l21 - l11 * l20, c21 = l01 * l20 - l00 * l21, c22 = l00 * l11 - l01 * l10;
+        const double det = l00 * c00 + l01 * c10 + l02 * c20;
+        const double nl = sqrt(l00 * l00 + l10 * l10 + l20 * l20 + l01 * l01 + l11 * l11 + l21 * l21 + l02 * l02 + l12 * l12 + l22 * l22);
+        const double na = sqrt(c00 * c00 + c01 * c01 + c02 * c02 + c10 * c10 + c11 * c11 + c12 * c12 + c20 * c20 + c21 * c21 + c22 * c22);
+        const double cond = nl * na / fabs(det);  // |L|_F * |L^-1|_F
+        if (isfinite(det) && det != 0.0 && isfinite(cond) && cond <= 100.0 && isfinite(t0) && isfinite(t1) && isfinite(t2)) {
+            const double r = 1.0 / det;
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            bool ok = true;
+            for (int c = 0; c < 8; ++c) {
+                const double x = ((c & 1) ? root.max[0] : root.min[0]) - t0, y = ((c & 2) ? root.max[1] : root.min[1]) - t1,
+                             z = ((c & 4) ? root.max[2] : root.min[2]) - t2;
+                const double w[3] = {(c00 * x + c01 * y + c02 * z) * r, (c10 * x + c11 * y + c12 * z) * r, (c20 * x + c21 * y + c22 * z) * r};
+                for (int k = 0; k < 3; ++k) {
+                    ok = ok && isfinite(w[k]);
+                    mn[k] = fmin(mn[k], w[k]);
+                    mx[k] = fmax(mx[k], w[k]);
+                }
+            }
+            if (ok) {
+                double amax = 0.0, ext = 0.0;
+                for (int k = 0; k < 3; ++k) { amax = fmax(amax, fmax(fabs(mn[k]), fabs(mx[k]))); ext = fmax(ext, mx[k] - mn[k]); }
+                const double g = 1e-3 * (amax + ext) + 1e-30;
+                if (amax < 1e30) {
+                    lo = make_float4(__double2float_rd(mn[0] - g), __double2float_rd(mn[1] - g), __double2float_rd(mn[2] - g),
+                                     __double2float_ru(amax + g));
+                    hi = make_float4(__double2float_ru(mx[0] + g), __double2float_ru(mx[1] + g), __double2float_ru(mx[2] + g), 0.0f);
+                }
+            }
+        }
+    }
+    wbox[2 * i] = lo;
+    wbox[2 * i + 1] = hi;
+}
+
+// true when the ray certainly misses the (grown) world box of an instance; NaNs and unusable reciprocals never say "miss"
+__device__ __forceinline__ bool wbox_miss(const float4* __restrict__ wbox, uint32_t ii, const float* eye, const float* inv) {
+    const float4 lo = __ldg(wbox + 2 * (size_t)ii), hi = __ldg(wbox + 2 * (size_t)ii + 1);
+    const float m = 1e-4f * (fmaxf(fmaxf(fabsf(eye[0]), fabsf(eye[1])), fabsf(eye[2])) + lo.w);
+    const float ax = (lo.x - m - eye[0]) * inv[0], ay = (lo.y - m - eye[1]) * inv[1], az = (lo.z - m - eye[2]) * inv[2];
+    const float bx = (hi.x + m - eye[0]) * inv[0], by = (hi.y + m - eye[1]) * inv[1], bz = (hi.z + m - eye[2]) * inv[2];
+    const float tmx = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+    const float tmn = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+    const bool usable = isfinite(inv[0]) && isfinite(inv[1]) && isfinite(inv[2]) && inv[0] != 0.0f && inv[1] != 0.0f && inv[2] != 0.0f;
+    return usable && ((tmx < tmn) || (tmx < 0.0f));
+}
+
 // Stack entries carry what the pop needs (left_first | count << 30), taken from the child node at the time its box
 // is tested, so a node is fetched once (as a child) instead of twice.
 __device__ __forceinline__ uint32_t pack_meta(const NodeW& n) {
@@ -351,7 +422,8 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                                                      float tmax, float* t_out, uint32_t* tri_out, uint32_t* inst_out,
                                                      uint8_t* occ_out, unsigned long long* next_ray,
                                                      const uint32_t* __restrict__ list = nullptr,
-                                                     const unsigned long long* list_ctl = nullptr) {
+                                                     const unsigned long long* list_ctl = nullptr,
+                                                     const float4* __restrict__ wbox = nullptr) {
     // Optional indirection: trace only the rays the wide any-hit kernel deferred (list_ctl[0] = how many,
     // list_ctl[2] != 0 = all of them, in which case the list is not used).
     if (list_ctl) {
@@ -441,18 +513,21 @@ __global__ void __launch_bounds__(128) k_trace_scene(BvhCudaSceneDesc sc, const 
                 const NodeW node = tlas_node<TOP>(s_top, sc, ni, top_first);
                 const uint32_t left_right = __float_as_uint(node.a.w);
                 if (left_right == 0) {
-                    // instance_intersect (bvh.wgsl:78-87)
-                    ii = __float_as_uint(node.b.w);
-                    const Instance* in = sc.instances + ii;
-                    const MeshInfo* mesh = sc.meshes + in->mesh;
-                    tri_base = mesh->base_index / 3u;
-                    bvh_index = mesh->bvh_index;
-                    const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
-                    mat_mul(im, eye, 1.0f, e2);
-                    mat_mul(im, dir, 0.0f, d2);
-                    inv2[0] = __fdiv_rn(1.0f, d2[0]); inv2[1] = __fdiv_rn(1.0f, d2[1]); inv2[2] = __fdiv_rn(1.0f, d2[2]);
-                    bstack[bh++] = pack_meta(ld_node(sc.bvh_nodes, bvh_index));
-                    hit = dist;
+                    // instance_intersect (bvh.wgsl:78-87); a visit that cannot accept a triangle is dropped (k_instance_wbox)
+                    const uint32_t iv = __float_as_uint(node.b.w);
+                    if (!(wbox && wbox_miss(wbox, iv, eye, inv))) {
+                        ii = iv;
+                        const Instance* in = sc.instances + ii;
+                        const MeshInfo* mesh = sc.meshes + in->mesh;
+                        tri_base = mesh->base_index / 3u;
+                        bvh_index = mesh->bvh_index;
+                        const float4* im = reinterpret_cast<const float4*>(in->inv_transform);
+                        mat_mul(im, eye, 1.0f, e2);
+                        mat_mul(im, dir, 0.0f, d2);
+                        inv2[0] = __fdiv_rn(1.0f, d2[0]); inv2[1] = __fdiv_rn(1.0f, d2[1]); inv2[2] = __fdiv_rn(1.0f, d2[2]);
+                        bstack[bh++] = pack_meta(ld_node(sc.bvh_nodes, bvh_index));
+                        hit = dist;
+                    }
                 } else {
                     uint32_t min_index, max_index;
                     if (sc.tlas_children) {
@@ -805,6 +880,9 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     const size_t cap = (size_t)ctx->sm_count * 16;  // 16 blocks x 4 warps per SM is the register-limited maximum
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     static const bool wide_off = [] { const char* e = getenv("BVH_CUDA_ANYHIT"); return e && !strcmp(e, "exact"); }();
+    // instance culling by tight world boxes (exact-order kernels): BVH_CUDA_INSTANCE_CULL=0 switches it off (A/B)
+    static const bool cull_off = [] { const char* e = getenv("BVH_CUDA_INSTANCE_CULL"); return !(e && atoi(e) == 1); }();  // OFF until validated on the GPU
+    const float4* wb = (scene->wbox_on && scene->wbox && !cull_off) ? reinterpret_cast<const float4*>(scene->wbox) : nullptr;
     // top of the TLAS in shared memory (TlasTop): off by default (measured slower, see tlas_node above); BVH_CUDA_TLAS_TOP=1 enables it
     static const bool top = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e && atoi(e) != 0; }();
     if (any_hit && !wide_off && tmax <= MAXD && n_rays < 0xFFFFFFFFull) {
@@ -833,16 +911,33 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
         ctx->launches++;
         // (the deferral pass normally finds an empty list: it runs without staging)
         k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ,
-                                                                counter + CTL_DEFER_RAY, dlist, counter + CTL_DEFER_N);
+                                                                counter + CTL_DEFER_RAY, dlist, counter + CTL_DEFER_N, wb);
     } else if (any_hit) {
-        if (top) k_trace_scene<true, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
-        else k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter);
+        if (top) k_trace_scene<true, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter, nullptr, nullptr, wb);
+        else k_trace_scene<true, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, nullptr, nullptr, nullptr, d_occ, counter, nullptr, nullptr, wb);
     } else {
-        if (top) k_trace_scene<false, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
-        else k_trace_scene<false, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter);
+        if (top) k_trace_scene<false, true><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter, nullptr, nullptr, wb);
+        else k_trace_scene<false, false><<<blocks, 128, 0, stream>>>(scene->d, tris, d_ray_o, d_ray_d, n_rays, tmax, d_t, d_tri, d_inst, nullptr, counter, nullptr, nullptr, wb);
     }
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
+    return BVH_CUDA_OK;
+}
+
+// (Re)computes the per-instance world boxes from the scene's CURRENT instance / mesh / node buffers and switches the
+// culling of the exact-order kernels on (enable = 0: off).  Stream-ordered.
+int scene_instance_boxes_device(bvh_cuda_ctx* ctx, bvh_cuda_scene* scene, int enable, cudaStream_t stream) {
+    if (!enable) { scene->wbox_on = false; return BVH_CUDA_OK; }
+    const size_t n = scene->d.n_instances;
+    if (n == 0) return BVH_CUDA_OK;
+    if (!scene->wbox) {
+        cudaError_t e = cudaMalloc(&scene->wbox, sizeof(float4) * 2 * n);
+        if (e != cudaSuccess) return ctx_cuda_fail(ctx, e, "cudaMalloc(instance boxes)");
+    }
+    k_instance_wbox<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(scene->d, reinterpret_cast<float4*>(scene->wbox));
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    scene->wbox_on = true;
     return BVH_CUDA_OK;
 }
 
