@@ -352,9 +352,11 @@ def test_instance_culling_keeps_results_on_a_config3_like_scene(ctx, oracle):
     ot, otri, oins, _, st = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
     assert (tri == otri).all() and (ins == oins).all() and np.allclose(t, ot, rtol=T_RTOL, atol=0.0)
     assert (otri != 0xFFFFFFFF).sum() > 5_000 and st["instance_visits"] > 50 * len(ro)  # the reference really does enter them all
-    # exact-order any-hit (tmax above 1e30 routes every ray through k_trace_scene<true>)
-    occ = scene.occluded(ro[:30_000], rd[:30_000], tmax=3e38)
-    _, _, _, oocc, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro[:30_000], rd[:30_000], tmax=3e38,
+    # exact-order any-hit (tmax above 1e30 routes every ray through k_trace_scene<true>; the reference then visits EVERY node of
+    # every instance it enters, so only a handful of rays: 48 rays cost the oracle ~3e8 node visits)
+    sel = np.r_[0:24, len(ro) - 24:len(ro)]
+    occ = scene.occluded(ro[sel], rd[sel], tmax=3e38)
+    _, _, _, oocc, _ = oracle.trace_scene(tl.nodes, tl.children, inst, infos, nodes, verts, inds, ro[sel], rd[sel], tmax=3e38,
                                           any_hit=True, threads=oracle.max_threads())
     assert (occ == oocc).all()
 

@@ -881,7 +881,7 @@ int trace_scene_device(bvh_cuda_ctx* ctx, const bvh_cuda_scene* scene, const flo
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
     static const bool wide_off = [] { const char* e = getenv("BVH_CUDA_ANYHIT"); return e && !strcmp(e, "exact"); }();
     // instance culling by tight world boxes (exact-order kernels): BVH_CUDA_INSTANCE_CULL=0 switches it off (A/B)
-    static const bool cull_off = [] { const char* e = getenv("BVH_CUDA_INSTANCE_CULL"); return !(e && atoi(e) == 1); }();  // OFF until validated on the GPU
+    static const bool cull_off = [] { const char* e = getenv("BVH_CUDA_INSTANCE_CULL"); return e && atoi(e) == 0; }();
     const float4* wb = (scene->wbox_on && scene->wbox && !cull_off) ? reinterpret_cast<const float4*>(scene->wbox) : nullptr;
     // top of the TLAS in shared memory (TlasTop): off by default (measured slower, see tlas_node above); BVH_CUDA_TLAS_TOP=1 enables it
     static const bool top = [] { const char* e = getenv("BVH_CUDA_TLAS_TOP"); return e && atoi(e) != 0; }();
