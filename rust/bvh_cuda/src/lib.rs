@@ -101,6 +101,7 @@ extern "C" {
     ) -> c_int;
     fn bvh_cuda_blas_build_finish(ctx: *mut ctx_t, n_nodes_out: *mut u32) -> c_int;
     fn bvh_cuda_scene_upload(ctx: *mut ctx_t, host_desc: *const SceneDesc, out: *mut *mut scene_t) -> c_int;
+    fn bvh_cuda_scene_instance_boxes_dev(ctx: *mut ctx_t, scene: *mut scene_t, enable: c_int, stream: *mut c_void) -> c_int;
     fn bvh_cuda_scene_free(ctx: *mut ctx_t, scene: *mut scene_t);
     fn bvh_cuda_trace_closest(
         ctx: *mut ctx_t, scene: *const scene_t, ray_o: *const f32, ray_d: *const f32, n_rays: usize, tmax: f32,
@@ -306,6 +307,14 @@ impl Scene {
             check(ctx, bvh_cuda_trace_any(ctx, self.handle, o.as_ptr() as *const f32, d.as_ptr() as *const f32, n, 1e30, occ.as_mut_ptr()))
         });
         occ.into_iter().map(|b| b != 0).collect()
+    }
+}
+
+impl Scene {
+    /// Recompute the tight per-instance world boxes the exact-order kernels cull with (uploaded scenes have them from the
+    /// start; only scenes wrapped around caller-owned device buffers need this after the instance buffer was rewritten).
+    pub fn refresh_instance_boxes(&self) {
+        CTX.with(|&ctx| unsafe { check(ctx, bvh_cuda_scene_instance_boxes_dev(ctx, self.handle, 1, std::ptr::null_mut())) });
     }
 }
 
