@@ -309,6 +309,59 @@ def test_tlas_best_match_cache_model_is_exact_and_saves_little(oracle):
             assert st["scans"] > 2.0 * n  # the cache removes well under half of the scans
 
 
+def test_instance_cull_boxes_never_drop_a_hit(oracle):
+    """CPU replica of csrc/trace.cu k_instance_wbox / wbox_miss (the tight per-instance world boxes the exact-order kernels cull
+    with): on a config-3-like scene no ray is culled at the instance the oracle reports its hit in -- also for rays aimed exactly
+    at mesh vertices -- while nearly every other (ray, instance) pair is.  The GPU suite checks the kernels themselves against the
+    oracle's ids (test_instance_culling_keeps_results_on_a_config3_like_scene)."""
+    F = np.float32
+
+    def builder(v, i):
+        rc, nodes, perm, _, _ = oracle.blas_build(v, i)
+        return nodes, perm
+
+    verts, inds, nodes, infos, _ = make_scene(builder, n_inst=4)
+    inst = S.random_instances(1200, infos.shape[0], seed=33, extent=400.0)
+    rc, tl, kids, _, _ = oracle.tlas_build(inst, infos)
+    ro, rd = S.rays_sphere_to_cube(12_000, 900.0, 400.0, seed=13)
+    rng = np.random.default_rng(8)
+    pick = rng.integers(0, len(inst), 12_000)
+    vo = infos["vertex_offset"][inst["mesh"][pick]].astype(np.int64)
+    nv = np.append(infos["vertex_offset"][1:], verts.shape[0]).astype(np.int64)[inst["mesh"][pick]] - vo
+    local = verts[vo + (rng.integers(0, 1 << 30, pick.size) % nv)]
+    M = inst["transform"][pick].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    world = np.einsum("nij,nj->ni", M[:, :3, :3], local.astype(np.float64)) + M[:, :3, 3]
+    org = rng.normal(size=world.shape) * 300.0
+    ro = np.concatenate([ro, org.astype(F)])
+    rd = np.concatenate([rd, (world - org).astype(F)])
+    _, tri, ins, _, st = oracle.trace_scene(tl, kids, inst, infos, nodes, verts, inds, ro, rd, threads=oracle.max_threads())
+    # the boxes: BLAS root box through the inverse of the linear part of inv_transform, in double, grown by 1e-3 of its size
+    A = inst["inv_transform"].reshape(-1, 4, 4).transpose(0, 2, 1).astype(np.float64)
+    Linv = np.linalg.inv(A[:, :3, :3])
+    root = nodes[infos["bvh_index"][inst["mesh"]]]
+    bits = np.array([[(c >> k) & 1 for k in range(3)] for c in range(8)])
+    corners = np.where(bits[None, :, :] == 1, root["max"][:, None, :].astype(np.float64), root["min"][:, None, :].astype(np.float64))
+    w = np.einsum("nij,ncj->nci", Linv, corners - A[:, None, :3, 3])
+    mn, mx = w.min(1), w.max(1)
+    amax = np.maximum(np.abs(mn), np.abs(mx)).max(1)
+    g = 1e-3 * (amax + (mx - mn).max(1))
+    lo, hi, low = (mn - g[:, None]).astype(F), (mx + g[:, None]).astype(F), (amax + g).astype(F)
+
+    def miss(e, d, j):
+        inv = (F(1) / d).astype(F)
+        m = (F(1e-4) * (np.abs(e).max(1) + low[j])).astype(F)
+        a = ((lo[j] - m[:, None] - e) * inv).astype(F)
+        b = ((hi[j] + m[:, None] - e) * inv).astype(F)
+        tmx, tmn = np.maximum(a, b).min(1), np.minimum(a, b).max(1)
+        return (tmx < tmn) | (tmx < 0)
+
+    h = tri != 0xFFFFFFFF
+    assert h.sum() > 3_000 and st["instance_visits"] > 100 * len(ro)
+    assert not miss(ro[h], rd[h], ins[h]).any()
+    ri, jj = rng.integers(0, len(ro), 20_000), rng.integers(0, len(inst), 20_000)
+    assert miss(ro[ri], rd[ri], jj).mean() > 0.99
+
+
 def test_traversal_equals_brute_force(oracle):
     v, idx = S.displaced_sphere(36, 72, 9)
     rc, nodes, perm, _, _ = oracle.blas_build(v, idx)
